@@ -1,0 +1,142 @@
+/*
+ * libtmdnet_b200.so -- C ABI of the B200-native (sm_100a) TensorNet / ET energy+force hot path.
+ *
+ * This is the drop-in boundary that replaces torchmd-net's `torchmdnet/extensions` (NVIDIA-Warp kernels
+ * wrapped as torch custom ops).  Conventions, shared by every entry point:
+ *   - plain pointers + sizes, no torch / Warp types; all pointers are DEVICE pointers;
+ *   - the CALLER allocates every output and workspace (the reference's op wrappers do the same with
+ *     torch.empty/zeros, e.g. warp_ops/neighbors.py:69-72, warp_ops/tensornet_mp.py:57-59); kernels never
+ *     allocate or free; inputs are read-only;
+ *   - `stream` is a cudaStream_t; every call is an asynchronous launch with no host synchronisation, hence
+ *     CUDA-graph capturable (reference: wp.launch(..., stream=torch stream), warp_kernels/utils.py:84-88);
+ *   - return value: 0 on success, <0 for invalid arguments / launch errors (text via tmd_last_error());
+ *     device-side conditions (neighbour-list overflow) are reported through an output counter, exactly like
+ *     the reference's `num_pairs` (models/utils.py:297-300);
+ *   - fp32 tensors are F-last and contiguous: X [N,3,3,F]; I [N,1,F], A [N,3,F], S [N,5,F] with component
+ *     order A = (01,02,12), S = (00,01,02,11,12), S22 = -(S00+S11) (warp_kernels/compose_tensor.py:54-98).
+ *     F must be a multiple of 4 for the message-passing entry points (128-bit loads).
+ *
+ * Reference paths below are relative to torchmd/torchmd-net @ 833c0770.
+ */
+#ifndef TMDNET_B200_H
+#define TMDNET_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int tmd_abi_version(void);
+const char* tmd_last_error(void);
+
+/* ---- a1: neighbour list ---------------------------------------------------------------------------------
+ * Replaces torch.ops.torchmdnet.warp_neighbor_brute_fwd / warp_neighbor_cell_fwd
+ * (extensions/warp_ops/neighbors.py:34-148, :196-289; kernels warp_kernels/neighbors_brute.py:32-205,
+ * neighbors_cell.py:17-147).  Same pair semantics (same `batch`, cutoff_lower <= r < cutoff_upper compared
+ * squared, self pairs bypass the lower cutoff, triclinic minimum image by sequential z,y,x rounding, canonical
+ * orientation = larger index first, transposed pair negated).  Output is sorted by (i, j) and therefore IS a
+ * CSR: indptr[n+1], nbr_i/nbr_j/vec/dist[max_pairs].  num_pairs[0] = pairs found (may exceed max_pairs; slots
+ * past max_pairs are dropped).  Slots >= num_pairs are left untouched (caller pre-fills -1 / 0).
+ * box: [1 or n_batch,3,3]; box_stride = 0 (shared) or 9 (per sample).  rev (optional, may be NULL): slot of the
+ * transposed pair.  workspace: 3*n+1 int32.  transpose=0 gives the half list (j <= i). */
+int tmd_neighbor_csr_f32(const float* pos, const int64_t* batch, const float* box, int box_stride, int periodic,
+                         int n, double cutoff_lower, double cutoff_upper, int loop, int transpose, int max_pairs,
+                         int* indptr, int* nbr_i, int* nbr_j, float* vec, float* dist, int* num_pairs, int* rev,
+                         int* workspace, void* stream);
+int tmd_neighbor_csr_f64(const double* pos, const int64_t* batch, const double* box, int box_stride, int periodic,
+                         int n, double cutoff_lower, double cutoff_upper, int loop, int transpose, int max_pairs,
+                         int* indptr, int* nbr_i, int* nbr_j, double* vec, double* dist, int* num_pairs, int* rev,
+                         int* workspace, void* stream);
+
+/* ---- a2: position gradient of the neighbour outputs -------------------------------------------------------
+ * Replaces neighbor_grad_positions (extensions/neighbor_utils.py:11-46; two index_add_ with atomics).
+ * _csr: deterministic gather over the symmetric CSR (needs rev); _coo: any -1 padded int64 [2,P] list, atomics,
+ * gpos must be zero-initialised.  gvec / gdist may be NULL. */
+int tmd_neighbor_grad_csr_f32(const int* indptr, const int* rev, const int* num_pairs, int max_pairs, int n,
+                              const float* vec, const float* dist, const float* gvec, const float* gdist,
+                              float* gpos, void* stream);
+int tmd_neighbor_grad_csr_f64(const int* indptr, const int* rev, const int* num_pairs, int max_pairs, int n,
+                              const double* vec, const double* dist, const double* gvec, const double* gdist,
+                              double* gpos, void* stream);
+int tmd_neighbor_grad_coo_f32(const int64_t* neighbors, long long P, const float* vec, const float* dist,
+                              const float* gvec, const float* gdist, float* gpos_zeroed, void* stream);
+int tmd_neighbor_grad_coo_f64(const int64_t* neighbors, long long P, const double* vec, const double* dist,
+                              const double* gvec, const double* gdist, double* gpos_zeroed, void* stream);
+
+/* ---- a3: COO -> CSR + CSC ------------------------------------------------------------------------------------
+ * Replaces nvtnet::count_row_col_primitive + nvtnet::convert_to_sparse_primitive + 2 torch.cumsum
+ * (extensions/warp_ops/graph_transform.py:160-179; warp_kernels/graph_transform.py:33-79).
+ * edge_index int32 [2,E], negative entries are padding.  Slots inside a row are ordered by edge id
+ * (deterministic; the reference's order is atomic-dependent).  workspace: 2*(n+1) int32. */
+int tmd_graph_transform(const int* edge_index, int E, int n, int* row_data, int* row_indices, int* row_indptr,
+                        int* col_data, int* col_indices, int* col_indptr, int* workspace, void* stream);
+
+/* ---- a5: embedding ("radial") message passing -----------------------------------------------------------------
+ * Replaces tensornet::radial_message_passing_{fwd,bwd}_primitive (warp_ops/tensornet_radial_mp.py:37-191;
+ * kernels warp_kernels/tensornet_radial_mp.py:43-189).  rhat [E,3], edge_attr [E,3,F]; CSR row_indptr[n+1] with
+ * optional edge-id indirection row_data (NULL: slot k is edge k).  The sign of A follows the reference's PyTorch
+ * path (models/tensornet.py:84-103).  Backward has one writer per edge (no fp atomics). */
+int tmd_radial_mp_fwd(const float* rhat, const float* edge_attr, const int* row_data, const int* row_indptr, int n,
+                      int F, float* out_I, float* out_A, float* out_S, void* stream);
+int tmd_radial_mp_bwd(const float* rhat, const float* edge_attr, const int* row_data, const int* row_indptr, int n,
+                      int F, const float* dI, const float* dA, const float* dS, float* d_edge_attr, float* d_rhat,
+                      void* stream);
+
+/* ---- a7: interaction message passing ----------------------------------------------------------------------------
+ * Replaces tensornet::message_passing_{fwd,bwd}_primitive (warp_ops/tensornet_mp.py:37-210; kernels
+ * warp_kernels/tensornet_mp.py:42-131).  fwd gathers over CSR rows, bwd over the CSC columns (d_edge_attr may be
+ * NULL when the edge weights need no gradient). */
+int tmd_mp_fwd(const float* I, const float* A, const float* S, const float* edge_attr, const int* row_data,
+               const int* row_indices, const int* row_indptr, int n, int F, float* out_I, float* out_A, float* out_S,
+               void* stream);
+int tmd_mp_bwd(const float* I, const float* A, const float* S, const float* edge_attr, const float* dout_I,
+               const float* dout_A, const float* dout_S, const int* col_data, const int* col_indices,
+               const int* col_indptr, int n, int F, float* dI, float* dA, float* dS, float* d_edge_attr, void* stream);
+
+/* ---- a8/a10: per-(atom,channel) tensor algebra, the reference's granular op set ----------------------------------
+ * Replace tensornet::{compose_tensor,decompose_tensor,tensor_matmul_o3_3x3,tensor_matmul_so3_3x3,tensor_norm3}
+ * _{fwd,bwd}_primitive (warp_ops/*.py; kernels warp_kernels/compose_tensor.py:54-148, decompose_tensor.py:56-140,
+ * equivariant_o3_matmul.py:42-101, equivariant_so3_matmul.py:42-99, tensor_norm3.py:48-138). */
+int tmd_compose_fwd(const float* I, const float* A, const float* S, float* X, int N, int F, void* stream);
+int tmd_compose_bwd(const float* dX, float* dI, float* dA, float* dS, int N, int F, void* stream);
+int tmd_decompose_fwd(const float* X, float* I, float* A, float* S, int N, int F, void* stream);
+int tmd_decompose_bwd(const float* dI, const float* dA, const float* dS, float* dX, int N, int F, void* stream);
+int tmd_matmul_o3_fwd(const float* A, const float* B, float* C, int N, int F, void* stream);
+int tmd_matmul_o3_bwd(const float* A, const float* B, const float* dC, float* dA, float* dB, int N, int F, void* stream);
+int tmd_matmul_so3_fwd(const float* A, const float* B, float* C, int N, int F, void* stream);
+int tmd_matmul_so3_bwd(const float* A, const float* B, const float* dC, float* dA, float* dB, int N, int F, void* stream);
+int tmd_norm3_fwd(const float* X, float* out, int N, int F, void* stream);
+int tmd_norm3_bwd(const float* dout, const float* X, float* dX, int N, int F, void* stream);
+
+/* ---- a8/a10 fused: compact-irreps stages used by the B200 model path -----------------------------------------------
+ * One kernel each for what models/tensornet.py expresses as chains of the granular ops:
+ *   norm2c : |X|^2 [N,F]                          (tensornet.py:589, tensor_norm of the composed tensor)
+ *   norm3c : (3I^2,|A|^2,|S|^2) [N,3F]            (tensornet.py:384-398)
+ *   gate   : (I g0, A g1, S g2), g [N,3,F]        (tensornet.py:607-615)
+ *   p1     : X/(|X|^2+1)                          (tensornet.py:745)
+ *   p2     : decompose(C)/(|C|^2+1), C = qf (YM+MY) [o3=1] or 2 YM [o3=0]     (tensornet.py:786-806)
+ *   p3     : X + dX + qf dX.dX                    (tensornet.py:812)
+ * qf [N] = 1 + 0.1 q_atom. */
+int tmd_norm2c_fwd(const float* I, const float* A, const float* S, float* out, int N, int F, void* stream);
+int tmd_norm2c_bwd(const float* I, const float* A, const float* S, const float* dout, float* dI, float* dA, float* dS, int N, int F, void* stream);
+int tmd_norm3c_fwd(const float* I, const float* A, const float* S, float* out, int N, int F, void* stream);
+int tmd_norm3c_bwd(const float* I, const float* A, const float* S, const float* dout, float* dI, float* dA, float* dS, int N, int F, void* stream);
+int tmd_gate_fwd(const float* I, const float* A, const float* S, const float* g, float* oI, float* oA, float* oS, int N, int F, void* stream);
+int tmd_gate_bwd(const float* I, const float* A, const float* S, const float* g, const float* dI, const float* dA, const float* dS,
+                 float* gI, float* gA, float* gS, float* dg, int N, int F, void* stream);
+int tmd_p1_fwd(const float* I, const float* A, const float* S, float* oI, float* oA, float* oS, int N, int F, void* stream);
+int tmd_p1_bwd(const float* I, const float* A, const float* S, const float* dI, const float* dA, const float* dS,
+               float* gI, float* gA, float* gS, int N, int F, void* stream);
+int tmd_p2_fwd(const float* YI, const float* YA, const float* YS, const float* MI, const float* MA, const float* MS,
+               const float* qf, int o3, float* oI, float* oA, float* oS, int N, int F, void* stream);
+int tmd_p2_bwd(const float* YI, const float* YA, const float* YS, const float* MI, const float* MA, const float* MS,
+               const float* qf, int o3, const float* dI, const float* dA, const float* dS, float* gYI, float* gYA,
+               float* gYS, float* gMI, float* gMA, float* gMS, int N, int F, void* stream);
+int tmd_p3_fwd(const float* XI, const float* XA, const float* XS, const float* DI, const float* DA, const float* DS,
+               const float* qf, float* oI, float* oA, float* oS, int N, int F, void* stream);
+int tmd_p3_bwd(const float* DI, const float* DA, const float* DS, const float* qf, const float* dI, const float* dA,
+               const float* dS, float* gXI, float* gXA, float* gXS, float* gDI, float* gDA, float* gDS, int N, int F, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMDNET_B200_H */

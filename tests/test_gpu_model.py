@@ -1,0 +1,135 @@
+"""-m gpu: end-to-end energy+force parity of the B200 path against (1) the committed reference outputs
+(tests/golden, generated from the unmodified reference in fp32 and fp64) and (2) the CPU oracle.
+
+Bar (BASELINE.json north_star): energies and forces within 1e-4 relative fp32.  'Relative' is taken w.r.t.
+max|F| (resp. max(1,|E|)) of the fp64 reference, the same normalisation oracle/make_golden.py prints.
+The reference's own fp32 path sits at ~3e-6 on this scale.
+"""
+import glob
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import tensornet_oracle as orc
+import systems
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+dev = torch.device("cuda:0")
+TOL = 1e-4
+
+
+def seeded_model(hp, seed):
+    from torchmdnet_b200.models.model import create_model
+    random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
+    return create_model(dict(hp))
+
+
+def build(fx):
+    if "state_dict" in fx:
+        from torchmdnet_b200.models.model import create_model
+        m = create_model(dict(fx["hparams"]))
+        m.load_state_dict(fx["state_dict"])
+    else:
+        m = seeded_model(fx["hparams"], fx.get("weight_seed", fx.get("seed")))
+    return m.eval().to(dev)
+
+
+def rel(a, b):
+    return ((a.double().cpu() - b.double()).abs().max() / max(1.0, b.abs().max().item())).item()
+
+
+def relF(a, b):
+    return ((a.double().cpu() - b.double()).abs().max() / b.abs().max()).item()
+
+
+def run(m, fx, **kw):
+    g = lambda t: None if t is None else t.to(dev)
+    return m(fx["z"].to(dev), fx["pos"].to(dev).clone(), g(fx["batch"]), box=g(fx["box"]), q=g(fx["q"]), **kw)
+
+
+CASES = [os.path.basename(f)[:-3] for f in sorted(glob.glob(os.path.join(GOLDEN, "*.pt")))
+         if "neighbor" not in f and "caffeine_tensornet_q2" not in f]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_energy_forces(name):
+    fx = torch.load(os.path.join(GOLDEN, name + ".pt"), weights_only=False)
+    m = build(fx)
+    y, f = run(m, fx)
+    eE, eF = rel(y, fx["ref_E64"]), relF(f, fx["ref_F64"])
+    print(f"{name}: relE={eE:.2e} relF={eF:.2e}  (reference fp32 vs fp64: {rel(fx['ref_E32'], fx['ref_E64']):.2e} {relF(fx['ref_F32'], fx['ref_F64']):.2e})")
+    assert eE < TOL and eF < TOL
+    assert rel(y, fx["ref_E32"].double()) < TOL and relF(f, fx["ref_F32"].double()) < TOL
+
+
+def test_caffeine_known_answer_and_charge():
+    """reference tests/test_calculator.py:85-162 through load_model (old-layout checkpoint), atol 1e-4;
+    energy.backward() as TMDNETCalculator does (calculators.py:315), derivative=False."""
+    from torchmdnet_b200.models.model import load_model
+    fx = torch.load(os.path.join(GOLDEN, "caffeine_tensornet.pt"), weights_only=False)
+    m = load_model(os.path.join(GOLDEN, "example_tensornet_slim.ckpt"), derivative=False, max_num_neighbors=64,
+                   static_shapes=False, device=dev).eval()
+    for p in m.parameters():
+        p.requires_grad = False
+    pos = fx["pos"].to(dev).clone().requires_grad_(True)
+    e, _ = m(fx["z"].to(dev), pos, fx["batch"].to(dev), q=torch.tensor([0.0], device=dev))
+    e.backward()
+    forces = -pos.grad
+    assert abs(e.item() - fx["kat_E"]) < 1e-4
+    assert (forces[0].cpu() - fx["kat_F0"]).abs().max() < 1e-4 and (forces[23].cpu() - fx["kat_F23"]).abs().max() < 1e-4
+    assert (forces.cpu() - fx["ref_F32"]).abs().max() < 1e-4
+    fq = torch.load(os.path.join(GOLDEN, "caffeine_tensornet_q2.pt"), weights_only=False)
+    pos2 = fx["pos"].to(dev).clone().requires_grad_(True)
+    e2, _ = m(fx["z"].to(dev), pos2, fx["batch"].to(dev), q=torch.tensor([2.0], device=dev))
+    e2.backward()
+    assert rel(e2.detach(), fq["ref_E64"]) < TOL and relF(-pos2.grad, fq["ref_F64"]) < TOL
+    assert abs(e2.item() - e.item()) > 1e-3  # the charge matters
+
+
+def test_expected_pkl():
+    """reference tests/test_model.py:277-329, atol/rtol 1e-5, weights rebuilt from seed 1234."""
+    for name in ("expected_tensornet", "expected_equivariant_transformer"):
+        fx = torch.load(os.path.join(GOLDEN, name + ".pt"), weights_only=False)
+        y, f = run(build(fx), fx)
+        torch.testing.assert_close(y.cpu(), fx["pkl_pred"], atol=1e-5, rtol=1e-5)
+        torch.testing.assert_close(f.cpu(), fx["pkl_deriv"], atol=1e-5, rtol=1e-5)
+
+
+def test_static_shapes_equal_dynamic():
+    """reference tests/test_staticshapes.py:58-87."""
+    fx = torch.load(os.path.join(GOLDEN, "box300_tensornet_L2.pt"), weights_only=False)
+    outs = []
+    for static in (False, True):
+        hp = dict(fx["hparams"]); hp["static_shapes"] = static
+        m = seeded_model(hp, fx["weight_seed"]).eval().to(dev)
+        outs.append(run(m, fx, num_systems=1))
+    assert rel(outs[1][0], outs[0][0].double().cpu()) < 1e-6 and relF(outs[1][1], outs[0][1].double().cpu()) < 1e-5
+
+
+def test_against_oracle_fresh_system():
+    """a system that is NOT in tests/golden: CUDA path vs the CPU oracle (fp32 and fp64) on the spot."""
+    hp = systems.tensornet_hparams(num_layers=2, F=128, R=32, max_nb=96)
+    m = seeded_model(hp, 7).eval()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    z, pos, batch, box = systems.water_box(n_side=4, L=12.4, seed=3)
+    y64, f64 = orc.energy_and_forces(orc.cast_state_dict(sd, torch.float64), hp, z, pos.double(), batch, box.double())
+    m = m.to(dev)
+    y, f = m(z.to(dev), pos.to(dev), batch.to(dev), box=box.to(dev))
+    assert rel(y, y64) < TOL and relF(f, f64) < TOL
+
+
+def test_multi_molecule_batch_and_permutation():
+    """independent molecules: per-molecule energies are unchanged when evaluated alone (no cross-batch edges)."""
+    hp = systems.tensornet_hparams(num_layers=1, F=64, R=16, max_nb=64)
+    m = seeded_model(hp, 3).eval().to(dev)
+    z, pos, batch, _ = systems.molecule_batch(n_mol=5, seed=1)
+    y, f = m(z.to(dev), pos.to(dev), batch.to(dev))
+    for k in range(5):
+        sel = batch == k
+        yk, fk = m(z[sel].to(dev), pos[sel].to(dev), torch.zeros(int(sel.sum()), dtype=torch.long, device=dev))
+        assert abs(yk.item() - y[k].item()) < 1e-4 * max(1, abs(y[k].item()))
+        assert (fk - f[sel.to(dev)]).abs().max() < 1e-4 * f.abs().max()

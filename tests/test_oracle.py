@@ -1,0 +1,106 @@
+"""Pins the CPU oracle (oracle/tensornet_oracle.py) to the committed fixtures generated from the unmodified
+reference (oracle/make_golden.py), and checks the host-side model logic: seeded construction reproduces the
+reference's weights bit-for-bit and load_model applies the old-layout remap."""
+import glob
+import hashlib
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import tensornet_oracle as orc
+from conftest import GOLDEN
+
+
+def digest(sd):
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode()); h.update(sd[k].detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def seeded_model(hp, seed):
+    from torchmdnet_b200.models.model import create_model
+    random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
+    return create_model(dict(hp))
+
+
+def model_cases():
+    out = []
+    for f in sorted(glob.glob(os.path.join(GOLDEN, "*.pt"))):
+        if os.path.basename(f) != "neighbor_cases.pt":
+            out.append(os.path.basename(f)[:-3])
+    return out
+
+
+def load_case(name):
+    fx = torch.load(os.path.join(GOLDEN, name + ".pt"), weights_only=False)
+    if "state_dict" in fx:
+        sd = fx["state_dict"]
+    elif name == "caffeine_tensornet_q2":
+        sd = torch.load(os.path.join(GOLDEN, "caffeine_tensornet.pt"), weights_only=False)["state_dict"]
+    else:
+        sd = seeded_model(fx["hparams"], fx.get("weight_seed", fx.get("seed"))).state_dict()
+    return fx, {k: v.detach().clone() for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("name", model_cases())
+def test_seeded_weights_match_reference(name):
+    fx, sd = load_case(name)
+    assert digest(sd) == fx["sd_digest"], "create_model(seed) no longer reproduces the reference's weights"
+
+
+@pytest.mark.parametrize("name", [n for n in model_cases() if "1000" not in n])
+def test_oracle_reproduces_reference(name):
+    fx, sd = load_case(name)
+    hp = fx["hparams"]
+    y64, f64 = orc.energy_and_forces(orc.cast_state_dict(sd, torch.float64), hp, fx["z"], fx["pos"].double(), fx["batch"],
+                                     None if fx["box"] is None else fx["box"].double(), None if fx["q"] is None else fx["q"].double())
+    assert torch.allclose(y64, fx["ref_E64"], rtol=1e-11, atol=1e-11)
+    assert torch.allclose(f64, fx["ref_F64"], rtol=1e-9, atol=1e-10)
+    y32, f32 = orc.energy_and_forces(sd, hp, fx["z"], fx["pos"], fx["batch"], fx["box"], fx["q"])
+    scale = fx["ref_F32"].abs().max()
+    assert (y32 - fx["ref_E32"]).abs().max() <= 2e-5 * max(1.0, fx["ref_E32"].abs().max())
+    assert (f32 - fx["ref_F32"]).abs().max() <= 2e-5 * max(1.0, scale)
+
+
+def test_caffeine_known_answer():
+    """tests/test_calculator.py:102-141 of the reference: E = -113.6652, forces atol 1e-4."""
+    fx, sd = load_case("caffeine_tensornet")
+    y, f = orc.energy_and_forces(sd, fx["hparams"], fx["z"], fx["pos"], fx["batch"], None, fx["q"])
+    assert abs(y.item() - fx["kat_E"]) < 1e-4
+    assert (f[0] - fx["kat_F0"]).abs().max() < 1e-4 and (f[23] - fx["kat_F23"]).abs().max() < 1e-4
+
+
+def test_expected_pkl():
+    """tests/test_model.py:277-329 of the reference (expected.pkl, atol/rtol 1e-5)."""
+    for name in ("expected_tensornet", "expected_equivariant_transformer"):
+        fx, sd = load_case(name)
+        y, f = orc.energy_and_forces(sd, fx["hparams"], fx["z"], fx["pos"], fx["batch"])
+        torch.testing.assert_close(y, fx["pkl_pred"], atol=1e-5, rtol=1e-5)
+        torch.testing.assert_close(f, fx["pkl_deriv"], atol=1e-5, rtol=1e-5)
+
+
+def test_load_model_old_layout_remap():
+    from torchmdnet_b200.models.model import load_model
+    with pytest.warns(UserWarning, match="Old-format checkpoint"):
+        m = load_model(os.path.join(GOLDEN, "example_tensornet_slim.ckpt"), derivative=True, max_num_neighbors=64,
+                       static_shapes=False)
+    fx = torch.load(os.path.join(GOLDEN, "caffeine_tensornet.pt"), weights_only=False)
+    assert digest(m.state_dict()) == fx["sd_digest"]
+
+
+def test_oracle_neighbors_match_numpy_reference():
+    cases = torch.load(os.path.join(GOLDEN, "neighbor_cases.pt"), weights_only=False)
+    assert len(cases) == 48
+    for c in cases:
+        ei, vec, dist = orc.neighbor_list(c["pos"], c["batch"], c["box_vectors"], 0.0, c["cutoff"], c["loop"], c["include_transpose"])
+        assert torch.equal(ei, c["neighbors"])
+        assert torch.allclose(vec, c["deltas"], atol=1e-5) and torch.allclose(dist, c["distances"], atol=1e-5)
+
+
+def test_round_half_away():
+    x = torch.tensor([0.5, -0.5, 1.5, 2.5, -2.5, 0.49999997, 2.4, -2.6])
+    assert torch.equal(orc.round_half_away(x), torch.tensor([1.0, -1.0, 2.0, 3.0, -3.0, 0.0, 2.0, -3.0]))

@@ -1,0 +1,232 @@
+"""Model API kept from the reference: `create_model`, `load_model`, `load_ensemble`, `TorchMD_Net`,
+`Ensemble`, `create_prior_models` (reference `torchmdnet/models/model.py:21-680`).
+
+`torchmd-train` (LNNP, module.py:86-89) and `TMDNETCalculator` (calculators.py:213-225) only touch these
+entry points, the `hyper_parameters` dict and the state-dict keys -- all preserved -- so they run on the
+B200 kernels unchanged.  Architectures in scope: "tensornet" and "equivariant-transformer"
+(SURVEY.md section 8); the deprecated graph-network / transformer models and TensorNet2 raise.
+"""
+import os
+import re
+import tempfile
+import warnings
+import zipfile
+from glob import glob
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from . import output_modules
+from .utils import dtype_mapping
+from .. import priors
+
+
+def create_model(args, prior_model=None, mean=None, std=None):
+    """Build a TorchMD_Net from the reference's hyper-parameter dict (model.py:21-164)."""
+    dtype = dtype_mapping[args["precision"]]
+    args.setdefault("box_vecs", None)
+    args.setdefault("static_shapes", False)
+    args.setdefault("vector_cutoff", False)
+    shared = dict(
+        hidden_channels=args["embedding_dimension"], num_layers=args["num_layers"], num_rbf=args["num_rbf"],
+        rbf_type=args["rbf_type"], trainable_rbf=args["trainable_rbf"], activation=args["activation"],
+        cutoff_lower=float(args["cutoff_lower"]), cutoff_upper=float(args["cutoff_upper"]), max_z=args["max_z"],
+        max_num_neighbors=args["max_num_neighbors"],
+        box_vecs=torch.tensor(args["box_vecs"], dtype=dtype) if args["box_vecs"] is not None else None, dtype=dtype)
+    kind = args["model"]
+    if kind == "tensornet":
+        from .tensornet import TensorNet
+        is_equivariant = False  # TensorNet feeds the plain Scalar head
+        representation = TensorNet(equivariance_invariance_group=args["equivariance_invariance_group"],
+                                   static_shapes=args["static_shapes"], **shared)
+    elif kind == "equivariant-transformer":
+        from .torchmd_et import TorchMD_ET
+        is_equivariant = True
+        representation = TorchMD_ET(attn_activation=args["attn_activation"], num_heads=args["num_heads"],
+                                    distance_influence=args["distance_influence"],
+                                    neighbor_embedding=args["neighbor_embedding"], vector_cutoff=args["vector_cutoff"],
+                                    **shared)
+    elif kind in ("graph-network", "transformer", "tensornet2"):
+        raise ValueError(f'architecture "{kind}" is outside the B200 hot-path scope (tensornet, equivariant-transformer)')
+    else:
+        raise ValueError(f'Unknown architecture: {kind}')
+
+    if args.get("atom_filter", -1) > -1:
+        raise ValueError("atom_filter is not supported by torchmdnet_b200 (incompatible with forces in the reference too)")
+    if args["prior_model"] and prior_model is None:
+        prior_model = create_prior_models(args)
+
+    head_name = ("Equivariant" if is_equivariant else "") + args["output_model"]
+    if not hasattr(output_modules, head_name):
+        raise ValueError(f'output model "{head_name}" is outside the B200 hot-path scope (Scalar / EquivariantScalar)')
+    output_model = getattr(output_modules, head_name)(
+        args["embedding_dimension"], activation=args["activation"], reduce_op=args["reduce_op"], dtype=dtype,
+        static_shapes=args.get("static_shapes", False), num_hidden_layers=args.get("output_mlp_num_layers", 0),
+        num_layers=0)
+    return TorchMD_Net(representation, output_model, prior_model=prior_model, mean=mean, std=std,
+                       derivative=args["derivative"], dtype=dtype)
+
+
+def load_ensemble(filepath, args=None, device="cpu", return_std=False, **kwargs):
+    """Ensemble from a list of checkpoints or a zip of *.ckpt (model.py:167-205)."""
+    if isinstance(filepath, (list, tuple)):
+        assert all(isinstance(f, str) for f in filepath), "Invalid filepath list."
+        models = [load_model(f, args=args, device=device, **kwargs) for f in filepath]
+    elif filepath.endswith(".zip"):
+        with tempfile.TemporaryDirectory() as tmp:
+            with zipfile.ZipFile(filepath, "r") as zf:
+                zf.extractall(tmp)
+            ckpts = glob(os.path.join(tmp, "*.ckpt"))
+            assert len(ckpts) > 0, "No checkpoint files found in zip file."
+            models = [load_model(f, args=args, device=device, **kwargs) for f in ckpts]
+    else:
+        raise ValueError("Invalid filepath. Must be a list of paths or a path to a zip file.")
+    return Ensemble(models, return_std=return_std)
+
+
+def _remix_rows(weight, bias):
+    """Old [N,F,3,3] checkpoints store the 3F output rows channel-major (f*3+k); the new layout is
+    irrep-major (k*F+f)  (model.py:321-331)."""
+    a, b = weight.shape
+    return (weight.view(a // 3, 3, b).transpose(0, 1).reshape(a, b), bias.view(a // 3, 3).transpose(0, 1).reshape(a))
+
+
+def load_model(filepath, args=None, device="cpu", return_std=False, **kwargs):
+    """Load a Lightning checkpoint written by torchmd-train (model.py:208-374): hyper_parameters -> kwargs
+    override -> create_model -> key patches -> old-layout remap -> load_state_dict."""
+    if isinstance(filepath, (list, tuple)) or filepath.endswith(".zip"):
+        return load_ensemble(filepath, args=args, device=device, return_std=return_std, **kwargs)
+    assert isinstance(filepath, str)
+    ckpt = torch.load(filepath, map_location="cpu", weights_only=False)
+    if args is None:
+        args = ckpt["hyper_parameters"]
+    delta_learning = args.get("remove_ref_energy", False)
+    for key, value in kwargs.items():
+        if key not in args:
+            warnings.warn(f"Unknown hyperparameter: {key}={value}")
+        args[key] = value
+    if args["model"] in ("tensornetv2_alt", "tensornet-nqe"):
+        args["model"] = "tensornet2"
+    model = create_model(args)
+    if delta_learning and "remove_ref_energy" in kwargs and not kwargs["remove_ref_energy"]:
+        assert len(model.prior_model) > 0, "Atomref prior must be added during training (with enable=False) for total energy prediction."
+        assert isinstance(model.prior_model[-1], priors.Atomref), "I expected the last prior to be Atomref."
+        model.prior_model[-1].enable = True
+
+    sd = {re.sub(r"^model\.", "", k): v for k, v in ckpt["state_dict"].items()}
+    for pat, rep in ((r"output_model.output_network.(\d+).update_net.(\d+).", r"output_model.output_network.\1.update_net.layers.\2."),
+                     (r"output_model.output_network.([02]).(weight|bias)", r"output_model.output_network.layers.\1.\2")):
+        sd = {re.sub(pat, rep, k): v for k, v in sd.items()}
+    sd.setdefault("representation_model.distance.box", torch.zeros(3, 3))
+
+    old_layout = "check_errors" in ckpt.get("hyper_parameters", {})
+    if kwargs.get("compatibility_load", old_layout) and args["model"] == "tensornet":
+        if old_layout and "compatibility_load" not in kwargs:
+            warnings.warn("Old-format checkpoint detected ('check_errors' found in hyper_parameters). "
+                          "Automatically applying compatibility_load to remap linear-layer weights. "
+                          "Pass compatibility_load=False to suppress this.")
+        keys = ["representation_model.tensor_embedding.linears_scalar.1"]
+        keys += [f"representation_model.layers.{l}.linears_scalar.2" for l in range(args["num_layers"])]
+        for k in keys:
+            sd[k + ".weight"], sd[k + ".bias"] = _remix_rows(sd[k + ".weight"], sd[k + ".bias"])
+    model.load_state_dict(sd)
+    return model.to(device)
+
+
+def create_prior_models(args, dataset=None):
+    """Parse `prior_model` / `prior_args` (model.py:377-448); only Atomref is in scope."""
+    out = []
+    if not args["prior_model"]:
+        return out
+    spec = args["prior_model"] if isinstance(args["prior_model"], list) else [args["prior_model"]]
+    names, pargs = [], []
+    for item in spec:
+        if isinstance(item, dict):
+            for k, v in item.items():
+                names.append(k)
+                pargs.append({} if v is None else v)
+        else:
+            names.append(item)
+            pargs.append({})
+    if args.get("prior_args") is not None:
+        pargs = args["prior_args"] if isinstance(args["prior_args"], list) else [args["prior_args"]]
+    for name, a in zip(names, pargs):
+        assert hasattr(priors, name), f"Unknown prior model {name}. Available models are {', '.join(priors.__all__)}"
+        out.append(getattr(priors, name)(dataset=dataset, **a))
+    return out
+
+
+class TorchMD_Net(nn.Module):
+    """representation -> output head -> *std -> priors -> per-molecule reduce -> +mean -> forces
+    (reference model.py:451-631; same constructor and forward signature)."""
+
+    def __init__(self, representation_model, output_model, prior_model=None, mean=None, std=None, derivative=False,
+                 dtype=torch.float32):
+        super().__init__()
+        self.representation_model = representation_model.to(dtype=dtype)
+        self.output_model = output_model.to(dtype=dtype)
+        if not output_model.allow_prior_model and prior_model is not None:
+            prior_model = None
+            warnings.warn("Prior model was given but the output model does not allow prior models. Dropping the prior model.")
+        if isinstance(prior_model, priors.BasePrior):
+            prior_model = [prior_model]
+        self.prior_model = None if prior_model is None else nn.ModuleList(prior_model).to(dtype=dtype)
+        self.derivative = derivative
+        self.register_buffer("mean", (torch.scalar_tensor(0) if mean is None else mean).to(dtype=dtype))
+        self.register_buffer("std", (torch.scalar_tensor(1) if std is None else std).to(dtype=dtype))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.representation_model.reset_parameters()
+        self.output_model.reset_parameters()
+        if self.prior_model is not None:
+            for prior in self.prior_model:
+                prior.reset_parameters()
+
+    def forward(self, z: Tensor, pos: Tensor, batch: Optional[Tensor] = None, box: Optional[Tensor] = None,
+                q: Optional[Tensor] = None, s: Optional[Tensor] = None, extra_args: Optional[Dict[str, Tensor]] = None,
+                num_systems: Optional[int] = None) -> Tuple[Tensor, Tensor]:
+        assert z.dim() == 1 and z.dtype == torch.long
+        if not pos.is_cuda:
+            raise RuntimeError("torchmdnet_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        batch = torch.zeros_like(z) if batch is None else batch
+        if self.derivative:
+            pos.requires_grad_(True)
+        x, v, z, pos, batch = self.representation_model(z, pos, batch, box=box, q=q, s=s)
+        x = self.output_model.pre_reduce(x, v, z, pos, batch, box=box)
+        if self.std is not None:
+            x = x * self.std
+        if self.prior_model is not None:
+            for prior in self.prior_model:
+                x = prior.pre_reduce(x, z, pos, batch, extra_args)
+        x = self.output_model.reduce(x, batch, num_systems=num_systems)
+        if self.mean is not None:
+            x = x + self.mean
+        y = self.output_model.post_reduce(x)
+        if self.prior_model is not None:
+            for prior in self.prior_model:
+                y = prior.post_reduce(y, z, pos, batch, box, extra_args)
+        if self.derivative:
+            dy = torch.autograd.grad([y], [pos], grad_outputs=[torch.ones_like(y)], create_graph=self.training,
+                                     retain_graph=self.training)[0]
+            assert dy is not None, "Autograd returned None for the force prediction."
+            return y, -dy
+        return y, torch.empty(0)
+
+
+class Ensemble(nn.ModuleList):
+    """Mean (and optionally std) over several TorchMD_Net models (model.py:634-680)."""
+
+    def __init__(self, modules: List[nn.Module], return_std: bool = False):
+        for m in modules:
+            assert isinstance(m, TorchMD_Net)
+        super().__init__(modules)
+        self.return_std = return_std
+
+    def forward(self, *args, **kwargs):
+        ys, fs = zip(*[m(*args, **kwargs)[:2] for m in self])
+        y, f = torch.stack(ys), torch.stack(fs)
+        if self.return_std:
+            return y.mean(0), f.mean(0), y.std(0), f.std(0)
+        return y.mean(0), f.mean(0)
