@@ -20,6 +20,8 @@ re-checks it against the committed fixtures in tests/golden/ on every run.
 from __future__ import annotations
 
 import math
+
+import numpy as np
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -101,7 +103,9 @@ def neighbor_list(
         ok = (d2 < hi2) & (d2 >= lo2)
         ii, jj = ii[ok], jj[ok]
         v = torch.stack([dx[ok], dy[ok], dz[ok]], dim=1)
-        d = torch.sqrt(d2[ok])
+        # numpy's sqrt is the IEEE correctly-rounded one (torch's vectorised CPU sqrt is off by 1 ulp on some
+        # inputs); CUDA's sqrtf / __fsqrt_rn -- what the reference's Warp kernel and ours use -- is IEEE too
+        d = torch.from_numpy(np.sqrt(d2[ok].numpy()))
         out_i.append(ii); out_j.append(jj); out_v.append(v); out_d.append(d)
         if include_transpose:
             out_i.append(jj); out_j.append(ii); out_v.append(-v); out_d.append(d)
