@@ -136,6 +136,35 @@ int tmd_p3_fwd(const float* XI, const float* XA, const float* XS, const float* D
 int tmd_p3_bwd(const float* DI, const float* DA, const float* DS, const float* qf, const float* dI, const float* dA,
                const float* dS, float* gXI, float* gXA, float* gXS, float* gDI, float* gDA, float* gDS, int N, int F, void* stream);
 
+/* ---- a4+a5+a6+a7 fused: radial pipeline on unique pairs -----------------------------------------------------------
+ * Replaces, for inference+forces, the reference's per-edge chain ExpNormalSmearing -> CosineCutoff -> 3x(Linear+SiLU)
+ * (models/tensornet.py:738-743; models/utils.py:356-407,500-528) and the embedding's radial projections
+ * (tensornet.py:558-567), which the reference runs as cuBLAS SGEMMs + elementwise launches on every directed edge.
+ *   tmd_pair_index : unique pairs of the symmetric CSR (canonical edge j <= i): pair_ptr[n+1], pid[E] (edge -> pair),
+ *                    pair_edge[P], pair_r[P], num_unique[1].  workspace: n int32.
+ *   tmd_pair_chain : out_f[p,:] = chain(rbf(r_p)) (x cutoff), out_fp[p,:] = d/dr of it (NULL: value only).
+ *                    WTl: transposed Linear weight [K_l][N_l]; dims = {R, N_0, N_1, N_2}; N_l % 32 == 0, <= 384.
+ *   tmd_mp_pair_bwd: backward of tmd_mp_fwd with pair-indexed weights: dY and (if fp != NULL) dE/dr_p = <dE/df_p, f'_p>
+ *                    fused into the transposed gather -- no [E,3F] gradient, no backward GEMM.
+ *   tmd_embed_fwd/bwd: embedding message passing with w = C(r) (U_i + V_j) dp_p computed in-kernel (U, V per atom:
+ *                    emb2([Z_i;Z_j]) = U_i + V_j); bwd returns dE/d dist[e], dE/d rhat[e,3]. */
+int tmd_pair_index(const int* indptr, const int* nbr_i, const int* nbr_j, const int* rev, const int* num_edges,
+                   int max_edges, int n, const float* dist, int* pair_ptr, int* pid, int* pair_edge, float* pair_r,
+                   int* num_unique, int* workspace, void* stream);
+int tmd_pair_chain(const float* pair_r, const int* num_unique, int max_pairs, const float* WT0, const float* b0,
+                   const float* WT1, const float* b1, const float* WT2, const float* b2, const int* dims, int n_layers,
+                   int act, int mul_cutoff, const float* means, const float* betas, double alpha, double lo, double hi,
+                   float* out_f, float* out_fp, void* stream);
+int tmd_mp_pair_bwd(const float* YI, const float* YA, const float* YS, const float* dMI, const float* dMA,
+                    const float* dMS, const float* f, const float* fp, const int* pid, const int* nbr_j,
+                    const int* indptr, int n, int F, float* dYI, float* dYA, float* dYS, float* d_pair_r, void* stream);
+int tmd_embed_fwd(const float* rhat, const float* dist, const float* dp, const int* pid, const int* nbr_j,
+                  const int* indptr, const float* U, const float* V, double lo, double hi, int n, int F, float* oI,
+                  float* oA, float* oS, void* stream);
+int tmd_embed_bwd(const float* rhat, const float* dist, const float* dp, const float* dpp, const int* pid,
+                  const int* nbr_j, const int* indptr, const float* U, const float* V, double lo, double hi, int n,
+                  int F, const float* dI, const float* dA, const float* dS, float* g_dist, float* g_rhat, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,10 +55,19 @@ CASES = [os.path.basename(f)[:-3] for f in sorted(glob.glob(os.path.join(GOLDEN,
          if "neighbor" not in f and "caffeine_tensornet_q2" not in f]
 
 
+@pytest.mark.parametrize("path", ["fused", "composed"])
 @pytest.mark.parametrize("name", CASES)
-def test_golden_energy_forces(name):
+def test_golden_energy_forces(name, path):
+    """path=fused: pair pipeline (tmd_pair_chain + fused message-passing backward); path=composed: the autograd-composed
+    granular kernels (what training uses).  ET has a single path."""
     fx = torch.load(os.path.join(GOLDEN, name + ".pt"), weights_only=False)
     m = build(fx)
+    if fx["hparams"]["model"] == "tensornet":
+        m.representation_model.fused_edge_path = None if path == "fused" else False
+        if path == "fused" and fx["hparams"]["embedding_dimension"] <= 128:
+            assert m.representation_model._fused_path_ok()
+    elif path == "composed":
+        pytest.skip("single path")
     y, f = run(m, fx)
     eE, eF = rel(y, fx["ref_E64"]), relF(f, fx["ref_F64"])
     print(f"{name}: relE={eE:.2e} relF={eF:.2e}  (reference fp32 vs fp64: {rel(fx['ref_E32'], fx['ref_E64']):.2e} {relF(fx['ref_F32'], fx['ref_F64']):.2e})")

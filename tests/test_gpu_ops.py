@@ -44,8 +44,8 @@ def check(outs, refs, ins, tol=2e-5):
     for o, r in zip(outs, refs):
         assert o.shape == r.shape
         assert (o - r).abs().max() <= tol * (1 + r.abs().max()), (o - r).abs().max().item()
-    g1 = torch.autograd.grad(sum((o * w).sum() for o, w in zip(outs, ws)), ins, allow_unused=True)
-    g2 = torch.autograd.grad(sum((r * w).sum() for r, w in zip(refs, ws)), ins, allow_unused=True)
+    g1 = torch.autograd.grad(sum((o * w).sum() for o, w in zip(outs, ws)), ins, allow_unused=True, retain_graph=True)
+    g2 = torch.autograd.grad(sum((r * w).sum() for r, w in zip(refs, ws)), ins, allow_unused=True, retain_graph=True)
     for a, b in zip(g1, g2):
         assert (a - b).abs().max() <= tol * 10 * (1 + b.abs().max()), (a - b).abs().max().item()
 

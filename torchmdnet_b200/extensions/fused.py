@@ -1,0 +1,173 @@
+"""Fused inference+force path of the TensorNet edge pipeline (C ABI: tmd_pair_*, tmd_mp_pair_bwd, tmd_embed_*).
+
+Used by `models/tensornet.py` when the radial weights need no gradient (evaluation / MD): the per-edge
+rbf -> MLP -> cutoff chain runs once per unordered pair with its d/dr tangent, and the backward of the
+message passing is a single gather kernel that emits dE/dr per pair.  Training (weight gradients) keeps
+using the autograd-composed ops of tensornet_ops.py.
+"""
+import ctypes
+from typing import NamedTuple, Sequence
+
+import torch
+from torch import Tensor
+
+from .. import _lib
+from .neighbors import NeighborGraph
+
+p = _lib.ptr
+
+
+class PairIndex(NamedTuple):
+    pid: Tensor         # [E_cap] int32  directed edge slot -> pair id
+    pair_edge: Tensor   # [P_cap] int32  pair id -> its canonical edge slot (j <= i)
+    pair_r: Tensor      # [P_cap] fp32   |r| of the pair (no autograd)
+    num_unique: Tensor  # [1] int32
+    pair_ptr: Tensor    # [N+1] int32
+
+
+def build_pair_index(g: NeighborGraph) -> PairIndex:
+    n = g.indptr.shape[0] - 1
+    cap = g.dist.shape[0]
+    dev = g.dist.device
+    i32 = dict(device=dev, dtype=torch.int32)
+    pid = torch.zeros(cap, **i32)
+    pair_edge = torch.zeros(cap, **i32)
+    pair_r = torch.zeros(cap, device=dev, dtype=torch.float32)
+    num_unique = torch.zeros(1, **i32)
+    pair_ptr = torch.empty(n + 1, **i32)
+    ws = torch.empty(max(n, 1), **i32)
+    _lib.call("tmd_pair_index", p(g.indptr), p(g.nbr_i), p(g.nbr_j), p(g.rev), p(g.num_pairs), cap, n, p(g.dist.detach()),
+              p(pair_ptr), p(pid), p(pair_edge), p(pair_r), p(num_unique), p(ws), device=dev)
+    return PairIndex(pid, pair_edge, pair_r, num_unique, pair_ptr)
+
+
+class _PairDist(torch.autograd.Function):
+    """pair_r[p] = dist[pair_edge[p]]; backward splits dE/dr_p evenly over the two directed edges (the position
+    gradient kernel turns g_e - g_rev(e) back into the full pair force)."""
+
+    @staticmethod
+    def forward(ctx, dist, pair_edge, pid, P):
+        ctx.save_for_backward(pid)
+        ctx.E = dist.shape[0]
+        return dist.index_select(0, pair_edge[:P].long())
+
+    @staticmethod
+    def backward(ctx, g_pair):
+        (pid,) = ctx.saved_tensors
+        return 0.5 * g_pair.index_select(0, pid[:ctx.E].long().clamp_(max=g_pair.shape[0] - 1)), None, None, None
+
+
+def pair_distances(dist: Tensor, pidx: PairIndex, P: int) -> Tensor:
+    return _PairDist.apply(dist, pidx.pair_edge, pidx.pid, P)
+
+
+class RadialChain:
+    """Host-side cache of the transposed weights of a Linear stack (rebuilt when a weight is modified in place).
+    Each layer is a list of nn.Linear sharing the same input, concatenated along the output axis (the embedding's
+    three radial projections form one [R,3F] layer)."""
+
+    def __init__(self, layers: Sequence[Sequence[torch.nn.Linear]], act: bool, mul_cutoff: bool):
+        self.layers, self.act, self.mul_cutoff = [list(l) for l in layers], act, mul_cutoff
+        self._key, self._wt, self._b, self._dims = None, None, None, None
+
+    def supported(self) -> bool:
+        widths = [sum(m.out_features for m in l) for l in self.layers]
+        R = self.layers[0][0].in_features
+        return R % 4 == 0 and len(widths) <= 3 and all(w % 32 == 0 and w <= 384 for w in widths)
+
+    def frozen(self) -> bool:
+        return not any(t.requires_grad for l in self.layers for m in l for t in (m.weight, m.bias))
+
+    def tensors(self):
+        key = tuple((m.weight.data_ptr(), m.weight._version, m.bias.data_ptr(), m.bias._version) for l in self.layers for m in l)
+        if key != self._key:
+            self._wt = [torch.cat([m.weight.detach() for m in l], 0).t().contiguous() for l in self.layers]
+            self._b = [torch.cat([m.bias.detach() for m in l], 0).contiguous() for l in self.layers]
+            dims = [self.layers[0][0].in_features] + [w.shape[1] for w in self._wt]
+            self._dims = (ctypes.c_int * 4)(*(dims + [0] * 3)[:4])
+            self._key = key
+        return self._wt, self._b, self._dims
+
+
+def run_chain(chain: RadialChain, pair_r: Tensor, num_unique: Tensor, rbf_mod, lo: float, hi: float, want_tangent: bool):
+    """-> (f [P,N_last], f' or None).  `rbf_mod` is the ExpNormalSmearing module (means/betas/alpha)."""
+    wt, b, dims = chain.tensors()
+    P = pair_r.shape[0]
+    n_last = wt[-1].shape[1]
+    f = torch.empty(P, n_last, device=pair_r.device, dtype=torch.float32)
+    fp = torch.empty_like(f) if want_tangent else None
+    wt3 = wt + [None] * (3 - len(wt))
+    b3 = b + [None] * (3 - len(b))
+    _lib.call("tmd_pair_chain", p(pair_r), p(num_unique), P, p(wt3[0]), p(b3[0]), p(wt3[1]), p(b3[1]), p(wt3[2]), p(b3[2]),
+              ctypes.cast(dims, ctypes.c_void_p), len(wt), int(chain.act), int(chain.mul_cutoff), p(rbf_mod.means.detach()),
+              p(rbf_mod.betas.detach()), float(rbf_mod.alpha), float(lo), float(hi), p(f), p(fp), device=pair_r.device)
+    return f, fp
+
+
+def _triple(N, F, dev):
+    return (torch.empty(N, 1, F, device=dev), torch.empty(N, 3, F, device=dev), torch.empty(N, 5, F, device=dev))
+
+
+class _InteractionMP(torch.autograd.Function):
+    """M = sum_e f(r_e) * Y_j with f = cutoff * MLP(rbf(r)) evaluated per pair (rows a6 + a7)."""
+
+    @staticmethod
+    def forward(ctx, YI, YA, YS, pair_r, chain, rbf_mod, lo, hi, g, pidx):
+        YI, YA, YS = YI.contiguous(), YA.contiguous(), YS.contiguous()
+        need = pair_r.requires_grad
+        f, fp = run_chain(chain, pair_r.detach(), pidx.num_unique, rbf_mod, lo, hi, need)
+        N, F = YI.shape[0], YI.shape[-1]
+        M = _triple(N, F, YI.device)
+        _lib.call("tmd_mp_fwd", p(YI), p(YA), p(YS), p(f), p(pidx.pid), p(g.nbr_j), p(g.indptr), N, F, p(M[0]), p(M[1]), p(M[2]),
+                  device=YI.device)
+        ctx.save_for_backward(YI, YA, YS, f, fp if fp is not None else f, pidx.pid, g.nbr_j, g.indptr)
+        ctx.has_fp = fp is not None
+        ctx.P = pair_r.shape[0]
+        return M
+
+    @staticmethod
+    def backward(ctx, dI, dA, dS):
+        YI, YA, YS, f, fp, pid, nbr_j, indptr = ctx.saved_tensors
+        N, F = YI.shape[0], YI.shape[-1]
+        dY = _triple(N, F, YI.device)
+        d_r = torch.zeros(ctx.P, device=YI.device, dtype=torch.float32) if ctx.has_fp else None
+        _lib.call("tmd_mp_pair_bwd", p(YI), p(YA), p(YS), p(dI.contiguous()), p(dA.contiguous()), p(dS.contiguous()), p(f),
+                  p(fp) if ctx.has_fp else None, p(pid), p(nbr_j), p(indptr), N, F, p(dY[0]), p(dY[1]), p(dY[2]), p(d_r),
+                  device=YI.device)
+        return dY[0], dY[1], dY[2], d_r, None, None, None, None, None, None
+
+
+def interaction_message_passing(Y, pair_r, chain, rbf_mod, lo, hi, g, pidx):
+    return _InteractionMP.apply(Y[0], Y[1], Y[2], pair_r, chain, rbf_mod, lo, hi, g, pidx)
+
+
+class _EmbeddingMP(torch.autograd.Function):
+    """I/A/S of the TensorNet embedding from (dist, rhat) with w = C(r)(U_i+V_j)(W_k rbf + b_k) built in-kernel (row a5)."""
+
+    @staticmethod
+    def forward(ctx, dist, rhat, U, V, pair_r, chain, rbf_mod, lo, hi, g, pidx):
+        need = dist.requires_grad or rhat.requires_grad
+        dp, dpp = run_chain(chain, pair_r.detach(), pidx.num_unique, rbf_mod, lo, hi, need)
+        dist_c, rhat_c, U, V = dist.detach().contiguous(), rhat.detach().contiguous(), U.contiguous(), V.contiguous()
+        N, F = U.shape[0], U.shape[-1]
+        out = _triple(N, F, U.device)
+        _lib.call("tmd_embed_fwd", p(rhat_c), p(dist_c), p(dp), p(pidx.pid), p(g.nbr_j), p(g.indptr), p(U), p(V), float(lo),
+                  float(hi), N, F, p(out[0]), p(out[1]), p(out[2]), device=U.device)
+        ctx.save_for_backward(dist_c, rhat_c, dp, dpp if dpp is not None else dp, pidx.pid, g.nbr_j, g.indptr, U, V)
+        ctx.has_tangent, ctx.lo, ctx.hi = dpp is not None, float(lo), float(hi)
+        return out
+
+    @staticmethod
+    def backward(ctx, dI, dA, dS):
+        dist, rhat, dp, dpp, pid, nbr_j, indptr, U, V = ctx.saved_tensors
+        if not ctx.has_tangent:
+            return (None,) * 11
+        N, F = U.shape[0], U.shape[-1]
+        g_dist, g_rhat = torch.zeros_like(dist), torch.zeros_like(rhat)
+        _lib.call("tmd_embed_bwd", p(rhat), p(dist), p(dp), p(dpp), p(pid), p(nbr_j), p(indptr), p(U), p(V), ctx.lo, ctx.hi,
+                  N, F, p(dI.contiguous()), p(dA.contiguous()), p(dS.contiguous()), p(g_dist), p(g_rhat), device=U.device)
+        return g_dist, g_rhat, None, None, None, None, None, None, None, None, None
+
+
+def embedding_message_passing(dist, rhat, U, V, pair_r, chain, rbf_mod, lo, hi, g, pidx):
+    return _EmbeddingMP.apply(dist, rhat, U, V, pair_r, chain, rbf_mod, lo, hi, g, pidx)

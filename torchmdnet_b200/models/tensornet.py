@@ -21,6 +21,7 @@ from torch import Tensor, nn
 
 from .utils import CosineCutoff, OptimizedDistance, act_class_mapping, rbf_class_mapping
 from ..extensions import tensornet_ops as ops
+from ..extensions import fused
 
 __all__ = ["TensorNet"]
 
@@ -63,9 +64,25 @@ class TensorEmbedding(nn.Module):
         dp = torch.nn.functional.linear(rbf, W, b).view(-1, 3, F_)
         return CZ.unsqueeze(1) * dp
 
-    def forward(self, z, g, nbr_i, nbr_j, cut, rhat, rbf):
-        w = self.pair_weights(z, nbr_i, nbr_j, cut, rbf)
-        I, A, S = ops.fn_radial_message_passing(rhat, w, None, g.indptr)
+    def radial_chain(self) -> "fused.RadialChain":
+        if getattr(self, "_chain", None) is None:
+            self._chain = fused.RadialChain([[self.distance_proj1, self.distance_proj2, self.distance_proj3]], act=False,
+                                            mul_cutoff=False)
+        return self._chain
+
+    def forward(self, z, g, nbr_i, nbr_j, cut, rhat, rbf, fast=None):
+        if fast is not None:
+            # fused path: U/V per atom, radial projections per pair (with d/dr), w assembled inside the kernel
+            F_ = self.hidden_channels
+            Z = self.emb(z)
+            U = torch.nn.functional.linear(Z, self.emb2.weight[:, :F_])
+            V = torch.nn.functional.linear(Z, self.emb2.weight[:, F_:], self.emb2.bias)
+            dist, pair_r, pidx, rbf_mod = fast
+            I, A, S = fused.embedding_message_passing(dist, rhat, U.detach(), V.detach(), pair_r, self.radial_chain(), rbf_mod,
+                                                      self.cutoff.cutoff_lower, self.cutoff.cutoff_upper, g, pidx)
+        else:
+            w = self.pair_weights(z, nbr_i, nbr_j, cut, rbf)
+            I, A, S = ops.fn_radial_message_passing(rhat, w, None, g.indptr)
         norm = self.init_norm(ops.norm2_compact(I, A, S))
         for lin in self.linears_scalar:
             norm = self.act(lin(norm))
@@ -103,14 +120,25 @@ class Interaction(nn.Module):
             f = self.act(lin(f))
         return (f * cut.unsqueeze(-1)).view(-1, 3, self.hidden_channels)
 
-    def forward(self, X, g, rbf, cut, qf):
+    def radial_chain(self) -> "fused.RadialChain":
+        if getattr(self, "_chain", None) is None:
+            self._chain = fused.RadialChain([[l] for l in self.linears_scalar], act=True, mul_cutoff=True)
+        return self._chain
+
+    def forward(self, X, g, rbf, cut, qf, fast=None):
         lt = self.linears_tensor
-        f = self.edge_weights(rbf, cut)
         Xn = ops.interaction_normalize(*X)
         Y = (lt[0](Xn[0]), lt[1](Xn[1]), lt[2](Xn[2]))
-        # the neighbour list is symmetric and f depends on |r| only, so the CSC of the graph is
-        # (indptr, nbr_j, rev): the transposed edge of slot k in row b lives at rev[k]
-        M = ops.fn_message_passing(Y[0], Y[1], Y[2], f, None, g.nbr_j, g.indptr, g.rev, g.nbr_j, g.indptr)
+        if fast is not None:
+            # fused path: f (and df/dr) once per unordered pair, message passing reads it through the pair index
+            dist, pair_r, pidx, rbf_mod = fast
+            M = fused.interaction_message_passing(Y, pair_r, self.radial_chain(), rbf_mod, self.cutoff.cutoff_lower,
+                                                  self.cutoff.cutoff_upper, g, pidx)
+        else:
+            f = self.edge_weights(rbf, cut)
+            # the neighbour list is symmetric and f depends on |r| only, so the CSC of the graph is
+            # (indptr, nbr_j, rev): the transposed edge of slot k in row b lives at rev[k]
+            M = ops.fn_message_passing(Y[0], Y[1], Y[2], f, None, g.nbr_j, g.indptr, g.rev, g.nbr_j, g.indptr)
         Cn = ops.interaction_product(Y[0], Y[1], Y[2], M[0], M[1], M[2], qf, self.equivariance_invariance_group == "O(3)")
         dX = (lt[3](Cn[0]), lt[4](Cn[1]), lt[5](Cn[2]))
         return ops.interaction_update(Xn[0], Xn[1], Xn[2], dX[0], dX[1], dX[2], qf)
@@ -147,6 +175,7 @@ class TensorNet(nn.Module):
         self.distance = OptimizedDistance(cutoff_lower, cutoff_upper, max_num_pairs=-max_num_neighbors, return_vecs=True,
                                           loop=True, resize_to_fit=not static_shapes, box=box_vecs, long_edge_index=True)
         self.cutoff = CosineCutoff(cutoff_lower, cutoff_upper)
+        self.fused_edge_path = None  # None: automatic; False: force the autograd-composed ops
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -156,27 +185,56 @@ class TensorNet(nn.Module):
         self.linear.reset_parameters()
         self.out_norm.reset_parameters()
 
+    def _fused_path_ok(self) -> bool:
+        """The fused pair pipeline differentiates w.r.t. geometry only: use it when the radial weights need no
+        gradient (eval mode, or frozen parameters as TMDNETCalculator sets them); otherwise the autograd-composed ops."""
+        if self.fused_edge_path is False or self.rbf_type != "expnorm" or self.activation != "silu":
+            return False
+        chains = [self.tensor_embedding.radial_chain()] + [l.radial_chain() for l in self.layers]
+        if not all(c.supported() for c in chains):
+            return False
+        rbf_frozen = not any(t.requires_grad for t in (self.distance_expansion.means, self.distance_expansion.betas))
+        emb = self.tensor_embedding
+        emb_frozen = not any(t.requires_grad for t in (emb.emb.weight, emb.emb2.weight, emb.emb2.bias))
+        frozen = rbf_frozen and emb_frozen and all(c.frozen() for c in chains)
+        return frozen or not (self.training and torch.is_grad_enabled())
+
     def forward(self, z: Tensor, pos: Tensor, batch: Tensor, box: Optional[Tensor] = None, q: Optional[Tensor] = None,
                 s: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor], Tensor, Tensor, Tensor]:
         if pos.dtype != torch.float32:
             raise RuntimeError("torchmdnet_b200 TensorNet kernels are fp32 (precision: 32)")
         g = self.distance.graph(pos, batch, box)
         nbr_i, nbr_j, dist, vec = g.nbr_i, g.nbr_j, g.dist, g.vec
+        use_fused = self._fused_path_ok()
+        pidx = fused.build_pair_index(g) if use_fused else None
+        P = dist.shape[0]
         if not self.static_shapes:
-            # dynamic shapes: one host read of the pair counter, then exact-size views (the reference pays a
+            # dynamic shapes: one host read of the pair counters, then exact-size views (the reference pays a
             # boolean-mask compaction here, models/utils.py:303-307)
-            E = min(int(g.num_pairs.item()), dist.shape[0])
+            if use_fused:
+                E, P = torch.cat([g.num_pairs, pidx.num_unique]).tolist()
+                P = min(P, dist.shape[0])
+            else:
+                E = int(g.num_pairs.item())
+            E = min(E, dist.shape[0])
             nbr_i, nbr_j, dist, vec = nbr_i[:E], nbr_j[:E], dist[:E], vec[:E]
-        # padded slots (static shapes) belong to no CSR row; clamp their indices so gathers stay in range
-        li, lj = nbr_i.clamp(min=0).long(), nbr_j.clamp(min=0).long()
         qf = torch.ones(z.shape[0], device=pos.device, dtype=pos.dtype) if q is None else 1 + 0.1 * q[batch].to(pos.dtype)
-        rbf = self.distance_expansion(dist)
-        cut = self.cutoff(dist)
         # unit vectors; self loops (dist == 0) keep a zero vector (tensornet.py:363-366)
         rhat = vec / dist.masked_fill(dist == 0, 1).unsqueeze(1)
-        X = self.tensor_embedding(z, g, li, lj, cut, rhat, rbf)
-        for layer in self.layers:
-            X = layer(X, g, rbf, cut, qf)
+        if use_fused:
+            pair_r = fused.pair_distances(dist, pidx, P)
+            fast = (dist, pair_r, pidx, self.distance_expansion)
+            X = self.tensor_embedding(z, g, None, None, None, rhat, None, fast=fast)
+            for layer in self.layers:
+                X = layer(X, g, None, None, qf, fast=fast)
+        else:
+            # padded slots (static shapes) belong to no CSR row; clamp their indices so gathers stay in range
+            li, lj = nbr_i.clamp(min=0).long(), nbr_j.clamp(min=0).long()
+            rbf = self.distance_expansion(dist)
+            cut = self.cutoff(dist)
+            X = self.tensor_embedding(z, g, li, lj, cut, rhat, rbf)
+            for layer in self.layers:
+                X = layer(X, g, rbf, cut, qf)
         x = self.out_norm(ops.norm3_compact(*X))
         x = self.act(self.linear(x))
         return x, None, z, pos, batch
