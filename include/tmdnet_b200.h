@@ -155,6 +155,15 @@ int tmd_pair_chain(const float* pair_r, const int* num_unique, int max_pairs, co
                    const float* WT1, const float* b1, const float* WT2, const float* b2, const int* dims, int n_layers,
                    int act, int mul_cutoff, const float* means, const float* betas, double alpha, double lo, double hi,
                    float* out_f, float* out_fp, void* stream);
+/* Tensor-core version of tmd_pair_chain: every layer is a 3xTF32 GEMM on tcgen05 (TMA-fed, TMEM accumulators).
+ * W_hi/W_lo[l]: TF32 (cvt.rna) split of the Linear weight [N_l, K_l] with K_0 zero-padded to a multiple of 32;
+ * hidden widths % 32 == 0, every N_l % 64 == 0.  Workspaces act_{a,b}_{hi,lo}: >= roundup(max_pairs*(out_fp?2:1),128)
+ * x max(K_l) floats each.  Same outputs as tmd_pair_chain to ~1e-6 relative. */
+int tmd_pair_chain_tc(const float* pair_r, const int* num_unique, int max_pairs, const float* const* W_hi,
+                      const float* const* W_lo, const float* const* bias, const int* dims, int n_layers, int act,
+                      int mul_cutoff, const float* means, const float* betas, double alpha, double lo, double hi,
+                      float* act_a_hi, float* act_a_lo, float* act_b_hi, float* act_b_lo, float* out_f, float* out_fp,
+                      void* stream);
 int tmd_mp_pair_bwd(const float* YI, const float* YA, const float* YS, const float* dMI, const float* dMA,
                     const float* dMS, const float* f, const float* fp, const int* pid, const int* nbr_j,
                     const int* indptr, int n, int F, float* dYI, float* dYA, float* dYS, float* d_pair_r, void* stream);

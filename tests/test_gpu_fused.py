@@ -36,9 +36,12 @@ def test_pair_index():
     assert torch.equal(pidx.pair_r[:P], g.dist[:E][ce])
 
 
+@pytest.mark.parametrize("tc", [True, False])
 @pytest.mark.parametrize("cfg", ["interaction", "embedding", "single_act"])
-def test_pair_chain_value_and_tangent(cfg):
+def test_pair_chain_value_and_tangent(cfg, tc, monkeypatch):
+    """tc=True: tcgen05 3xTF32 GEMM chain (tmd_pair_chain_tc); tc=False: fp32 CUDA-core chain (tmd_pair_chain)."""
     from torchmdnet_b200.extensions import fused
+    monkeypatch.setattr(fused, "USE_TENSOR_CORES", tc)
     from torchmdnet_b200.models.utils import ExpNormalSmearing, CosineCutoff
     torch.manual_seed(0)
     R, F = 32, 128

@@ -16,6 +16,9 @@ from .neighbors import NeighborGraph
 
 p = _lib.ptr
 
+# tcgen05 (3xTF32) radial chain; False selects the fp32 CUDA-core chain kernel (kept as the arbiter in tests)
+USE_TENSOR_CORES = True
+
 
 class PairIndex(NamedTuple):
     pid: Tensor         # [E_cap] int32  directed edge slot -> pair id
@@ -75,6 +78,33 @@ class RadialChain:
         R = self.layers[0][0].in_features
         return R % 4 == 0 and len(widths) <= 3 and all(w % 32 == 0 and w <= 384 for w in widths)
 
+    def supported_tc(self) -> bool:
+        """tcgen05 path: hidden widths % 32 == 0, every output width % 64 == 0."""
+        widths = [sum(m.out_features for m in l) for l in self.layers]
+        return len(widths) <= 3 and all(w % 64 == 0 for w in widths) and all(w % 32 == 0 for w in widths[:-1])
+
+    def tc_tensors(self):
+        """TF32 (round-to-nearest-away, = cvt.rna.tf32.f32) hi/lo split of every weight, K of layer 0 zero-padded to a
+        multiple of 32, plus the pointer tables the C ABI takes."""
+        self.tensors()
+        if getattr(self, "_tc_key", None) != self._key:
+            def rna(x):
+                b = x.contiguous().view(torch.int32)
+                return ((b + 0x1000) & -8192).view(torch.float32)
+            his, los = [], []
+            for wt in self._wt:               # wt is [K, N]; the tensor core wants W = [N, K], K contiguous
+                w = wt.t().contiguous()
+                kpad = (-w.shape[1]) % 32
+                if kpad:
+                    w = torch.nn.functional.pad(w, (0, kpad))
+                hi = rna(w)
+                his.append(hi.contiguous()); los.append(rna(w - hi).contiguous())
+            n = len(his)
+            mk = lambda ts: (ctypes.c_void_p * 3)(*([t.data_ptr() for t in ts] + [None] * (3 - n)))
+            self._tc = (his, los, mk(his), mk(los), mk(self._b))
+            self._tc_key = self._key
+        return self._tc
+
     def frozen(self) -> bool:
         return not any(t.requires_grad for l in self.layers for m in l for t in (m.weight, m.bias))
 
@@ -96,6 +126,17 @@ def run_chain(chain: RadialChain, pair_r: Tensor, num_unique: Tensor, rbf_mod, l
     n_last = wt[-1].shape[1]
     f = torch.empty(P, n_last, device=pair_r.device, dtype=torch.float32)
     fp = torch.empty_like(f) if want_tangent else None
+    if USE_TENSOR_CORES and chain.supported_tc() and P > 0:
+        his, los, p_hi, p_lo, p_b = chain.tc_tensors()
+        rows_pad = -(-(P * (2 if want_tangent else 1)) // 128) * 128
+        width = max([his[0].shape[1]] + [w.shape[1] for w in wt[:-1]])
+        ws = torch.empty(4, rows_pad, width, device=pair_r.device, dtype=torch.float32)
+        _lib.call("tmd_pair_chain_tc", p(pair_r), p(num_unique), P, ctypes.cast(p_hi, ctypes.c_void_p),
+                  ctypes.cast(p_lo, ctypes.c_void_p), ctypes.cast(p_b, ctypes.c_void_p), ctypes.cast(dims, ctypes.c_void_p),
+                  len(wt), int(chain.act), int(chain.mul_cutoff), p(rbf_mod.means.detach()), p(rbf_mod.betas.detach()),
+                  float(rbf_mod.alpha), float(lo), float(hi), p(ws[0]), p(ws[1]), p(ws[2]), p(ws[3]), p(f), p(fp),
+                  device=pair_r.device)
+        return f, fp
     wt3 = wt + [None] * (3 - len(wt))
     b3 = b + [None] * (3 - len(b))
     _lib.call("tmd_pair_chain", p(pair_r), p(num_unique), P, p(wt3[0]), p(b3[0]), p(wt3[1]), p(b3[1]), p(wt3[2]), p(b3[2]),
