@@ -14,7 +14,7 @@
 //   warp 0      : TMA producer   - A_hi/A_lo [128 x 32] and W_hi/W_lo [BN x 32] fp32 boxes per K-block, mbarrier ring
 //   warp 1      : MMA issuer     - allocates 512 TMEM columns, one elected lane issues 12 tcgen05.mma per K-block
 //                                  (4 K-steps of 8 x 3 split terms), tcgen05.commit frees the SMEM stage / publishes D
-//   warps 2..5  : epilogue       - tcgen05.ld 32x32b.x32 (thread = TMEM lane = output row), bias + SiLU + tangent
+//   warps 2..9  : epilogue       - tcgen05.ld 32x32b.x32 (thread = TMEM lane = output row), bias + SiLU + tangent
 //                                  (+ cutoff on the last layer), re-split to (hi, lo) or final fp32 f / f' to HBM;
 //                                  double-buffered accumulator (2 x 256 columns) overlaps it with the next item's MMAs
 #include <cuda.h>
@@ -24,7 +24,9 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 32;                 // 32 fp32 = 128 B = one SWIZZLE_128B row
-constexpr int TC_THREADS = 192;
+constexpr int EPI_WARPS = 8;             // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int MAX_N = 1024;              // bias staged in shared memory
 constexpr int A_TILE_BYTES = BM * BK * 4;  // 16 KB
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -147,6 +149,8 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float bias_s[MAX_N];
+  for (int i = threadIdx.x; i < P.N; i += TC_THREADS) bias_s[i] = P.bias[i];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_pairs = min(*P.num_unique, P.max_pairs);
@@ -158,7 +162,7 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: all 512 columns (one CTA per SM)
@@ -221,8 +225,9 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
+    // ------------------------------------------------------------------ epilogue (warps 2..9 -> TMEM lane quarters 2,3,0,1,2,3,0,1)
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;  // which of the alternating 32-column chunks this warp drains
     const int row_in_tile = q * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
     const bool jvp = P.rows_per_pair == 2;
@@ -240,7 +245,7 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
-      for (int c0 = 0; c0 < P.BN; c0 += 32) {
+      for (int c0 = half * 32; c0 < P.BN; c0 += 64) {
         uint32_t v[32];
         tmem_ld32(t_row + (uint32_t)c0, v);
         const int col0 = n_blk * P.BN + c0;
@@ -248,19 +253,24 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const float own = __uint_as_float(v[i]);
-          const float b = __ldg(P.bias + col0 + i);
+          const float b = bias_s[col0 + i];
           float res;
           if (jvp) {
             const float other = __shfl_xor_sync(0xffffffffu, own, 1);
             const float z = (tangent ? other : own) + b;
             const float t = tangent ? own : other;
             float h = z, dh = t;
-            if (P.act) { const float g = tn::silu_grad(z); h = tn::silu(z); dh = g * t; }
+            if (P.act) {
+              // sigmoid with the SFU (ex2 + rcp): |err| ~1e-7 relative, far inside the 3xTF32 error budget
+              const float sg = __fdividef(1.f, 1.f + __expf(-z));
+              h = z * sg;
+              dh = sg * (1.f + z * (1.f - sg)) * t;
+            }
             if (P.final_layer && P.mul_cutoff) { dh = dh * cut + h * dcut; h *= cut; }
             res = tangent ? dh : h;
           } else {
             const float z = own + b;
-            res = P.act ? tn::silu(z) : z;
+            res = P.act ? z * __fdividef(1.f, 1.f + __expf(-z)) : z;
             if (P.final_layer && P.mul_cutoff) res *= cut;
           }
           o[i] = res;
@@ -394,6 +404,7 @@ int tmd_pair_chain_tc(const float* pair_r, const int* num_unique, int max_pairs,
     const int BN = pick_bn(N);
     TMD_REQUIRE(BN > 0, "pair_chain_tc: layer widths must be multiples of 64");
     TMD_REQUIRE(l == n_layers - 1 || N % BK == 0, "pair_chain_tc: hidden widths must be multiples of 32");
+    TMD_REQUIRE(N <= MAX_N, "pair_chain_tc: layer wider than 1024");
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
     if ((rc = make_map(&ma_hi, in_hi, rows_pad, K, BM))) return rc;
