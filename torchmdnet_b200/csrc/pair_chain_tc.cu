@@ -14,7 +14,7 @@
 //   warp 0      : TMA producer   - A_hi/A_lo [128 x 32] and W_hi/W_lo [BN x 32] fp32 boxes per K-block, mbarrier ring
 //   warp 1      : MMA issuer     - allocates 512 TMEM columns, one elected lane issues 12 tcgen05.mma per K-block
 //                                  (4 K-steps of 8 x 3 split terms), tcgen05.commit frees the SMEM stage / publishes D
-//   warps 2..9  : epilogue       - tcgen05.ld 32x32b.x32 (thread = TMEM lane = output row), bias + SiLU + tangent
+//   warps 2..17 : epilogue       - tcgen05.ld 32x32b.x32 (thread = TMEM lane = output row), bias + SiLU + tangent
 //                                  (+ cutoff on the last layer), re-split to (hi, lo) or final fp32 f / f' to HBM;
 //                                  double-buffered accumulator (2 x 256 columns) overlaps it with the next item's MMAs
 #include <cuda.h>
@@ -24,7 +24,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 32;                 // 32 fp32 = 128 B = one SWIZZLE_128B row
-constexpr int EPI_WARPS = 8;             // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int EPI_WARPS = 16;            // four warps per TMEM lane quarter, round-robin over 32-column chunks
 constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int MAX_N = 1024;              // bias staged in shared memory
 constexpr int A_TILE_BYTES = BM * BK * 4;  // 16 KB
@@ -225,17 +225,20 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..9 -> TMEM lane quarters 2,3,0,1,2,3,0,1)
+    // ------------------------------------------------------------------ epilogue (warps 2..17; TMEM lane quarter = warp & 3)
+    // jvp: lanes (2m, 2m+1) hold the value / tangent rows of pair m.  They swap halves of the 32-column chunk so that
+    // each lane evaluates the activation ONCE for 16 columns and produces both h and dh for them.
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;  // which of the alternating 32-column chunks this warp drains
+    const int sub = (warp - 2) >> 2;  // which of the round-robin 32-column chunks this warp drains
     const int row_in_tile = q * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
     const bool jvp = P.rows_per_pair == 2;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int m_tile = item / n_blks, n_blk = item - m_tile * n_blks;
       const int row = m_tile * BM + row_in_tile;
-      const bool valid = row < rows_valid;
       const bool tangent = jvp && (row & 1);
+      const int row_v = jvp ? (row & ~1) : row;          // the value row of this lane's pair
+      const bool valid = row_v < rows_valid;
       const int pair = jvp ? (row >> 1) : row;
       float cut = 1.f, dcut = 0.f;
       if (P.final_layer && P.mul_cutoff) {
@@ -245,51 +248,80 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
-      for (int c0 = half * 32; c0 < P.BN; c0 += 64) {
+      for (int c0 = sub * 32; c0 < P.BN; c0 += 32 * (EPI_WARPS / 4)) {
         uint32_t v[32];
         tmem_ld32(t_row + (uint32_t)c0, v);
         const int col0 = n_blk * P.BN + c0;
-        float o[32];
+        if (jvp) {
+          const int cb = col0 + (tangent ? 16 : 0);        // this lane's 16 columns
+          float h[16], dh[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float own = __uint_as_float(v[i]);
-          const float b = bias_s[col0 + i];
-          float res;
-          if (jvp) {
-            const float other = __shfl_xor_sync(0xffffffffu, own, 1);
-            const float z = (tangent ? other : own) + b;
-            const float t = tangent ? own : other;
-            float h = z, dh = t;
+          for (int i = 0; i < 16; ++i) {
+            const float send = __uint_as_float(tangent ? v[i] : v[16 + i]);
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            const float z = (tangent ? recv : __uint_as_float(v[i])) + bias_s[cb + i];
+            const float t = tangent ? __uint_as_float(v[16 + i]) : recv;
+            float hh = z, dd = t;
             if (P.act) {
-              // sigmoid with the SFU (ex2 + rcp): |err| ~1e-7 relative, far inside the 3xTF32 error budget
+              // sigmoid on the SFU (ex2 + rcp): ~1e-7 relative, far inside the 3xTF32 error budget
               const float sg = __fdividef(1.f, 1.f + __expf(-z));
-              h = z * sg;
-              dh = sg * (1.f + z * (1.f - sg)) * t;
+              hh = z * sg;
+              dd = sg * fmaf(z, 1.f - sg, 1.f) * t;
             }
-            if (P.final_layer && P.mul_cutoff) { dh = dh * cut + h * dcut; h *= cut; }
-            res = tangent ? dh : h;
-          } else {
-            const float z = own + b;
-            res = P.act ? z * __fdividef(1.f, 1.f + __expf(-z)) : z;
-            if (P.final_layer && P.mul_cutoff) res *= cut;
+            if (P.final_layer && P.mul_cutoff) { dd = fmaf(dd, cut, hh * dcut); hh *= cut; }
+            h[i] = hh; dh[i] = dd;
           }
-          o[i] = res;
-        }
-        if (valid) {
-          if (P.final_layer) {
-            float* dst = (tangent ? P.out_fp : P.out_f) + (size_t)pair * P.N + col0;
+          if (valid) {
+            if (P.final_layer) {
+              float* d0 = P.out_f + (size_t)pair * P.N + cb;
+              float* d1 = P.out_fp + (size_t)pair * P.N + cb;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) st4(dst + i, make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]));
-          } else {
-            float* dh = P.out_hi + (size_t)row * P.N + col0;
-            float* dl = P.out_lo + (size_t)row * P.N + col0;
+              for (int i = 0; i < 16; i += 4) {
+                st4(d0 + i, make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]));
+                st4(d1 + i, make_float4(dh[i], dh[i + 1], dh[i + 2], dh[i + 3]));
+              }
+            } else {
+              const size_t o0 = (size_t)row_v * P.N + cb, o1 = o0 + P.N;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float hi4[4], lo4[4];
+              for (int i = 0; i < 16; i += 4) {
+                float a[4], b[4], c[4], d[4];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) { hi4[u] = tf32_rna(o[i + u]); lo4[u] = tf32_rna(o[i + u] - hi4[u]); }
-              st4(dh + i, make_float4(hi4[0], hi4[1], hi4[2], hi4[3]));
-              st4(dl + i, make_float4(lo4[0], lo4[1], lo4[2], lo4[3]));
+                for (int u = 0; u < 4; ++u) {
+                  a[u] = tf32_rna(h[i + u]);  b[u] = tf32_rna(h[i + u] - a[u]);
+                  c[u] = tf32_rna(dh[i + u]); d[u] = tf32_rna(dh[i + u] - c[u]);
+                }
+                st4(P.out_hi + o0 + i, make_float4(a[0], a[1], a[2], a[3]));
+                st4(P.out_lo + o0 + i, make_float4(b[0], b[1], b[2], b[3]));
+                st4(P.out_hi + o1 + i, make_float4(c[0], c[1], c[2], c[3]));
+                st4(P.out_lo + o1 + i, make_float4(d[0], d[1], d[2], d[3]));
+              }
+            }
+          }
+        } else {
+          float o[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float z = __uint_as_float(v[i]) + bias_s[col0 + i];
+            float res = P.act ? z * __fdividef(1.f, 1.f + __expf(-z)) : z;
+            if (P.final_layer && P.mul_cutoff) res *= cut;
+            o[i] = res;
+          }
+          if (valid) {
+            if (P.final_layer) {
+              float* dst = P.out_f + (size_t)pair * P.N + col0;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) st4(dst + i, make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]));
+            } else {
+              float* dhp = P.out_hi + (size_t)row * P.N + col0;
+              float* dlp = P.out_lo + (size_t)row * P.N + col0;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float hi4[4], lo4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { hi4[u] = tf32_rna(o[i + u]); lo4[u] = tf32_rna(o[i + u] - hi4[u]); }
+                st4(dhp + i, make_float4(hi4[0], hi4[1], hi4[2], hi4[3]));
+                st4(dlp + i, make_float4(lo4[0], lo4[1], lo4[2], lo4[3]));
+              }
             }
           }
         }
