@@ -61,30 +61,33 @@ def seeded_model(hp, seed=1):
 
 
 class ClockSampler:
+    """Samples SM clock / power / throttle reasons with ONE streaming nvidia-smi process (-lms 100) during the timed region."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
-        self.rows, self.stop, self.index = [], False, index
-        self.t = threading.Thread(target=self._run, daemon=True)
-
-    def _run(self):
-        while not self.stop:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        self.rows, self.index, self.proc = [], index, None
 
     def __enter__(self):
-        self.t.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.35)  # first sample lands before the timed region starts
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self.stop = True
-        self.t.join(timeout=6)
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill(); out = ""
+            for line in out.strip().splitlines():
+                c = [x.strip() for x in line.split(",")]
+                if len(c) >= 7:
+                    self.rows.append(c)
 
     def summary(self):
         if not self.rows:
@@ -97,11 +100,12 @@ class ClockSampler:
 
 
 def measured_peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s burst, source) from the driver-written MEASURED_PEAKS.json, else the recipe's fallback."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(d["hbm_gbs"]), float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
 def cpu_oracle_frames_per_s(hp, n_side, L, steps, threads, full_atoms):
@@ -254,27 +258,53 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant hand-written kernel: interaction message passing (a7), HBM-bound ----
+    # ---- roofline of the dominant hand-written kernel: the tcgen05 radial chain of one interaction layer (a6) ----
     from torchmdnet_b200.extensions import tensornet_ops as ops
-    g = model.representation_model.distance.graph(pos_d, bd, boxd)
-    E = int(g.num_pairs.item()); N = z.numel(); F = hp["embedding_dimension"]
+    from torchmdnet_b200.extensions import fused
+    rep = model.representation_model
+    g = rep.distance.graph(pos_d, bd, boxd)
+    pidx = fused.build_pair_index(g)
+    E, Pn = torch.cat([g.num_pairs, pidx.num_unique]).tolist()
+    N = z.numel(); F = hp["embedding_dimension"]; R = hp["num_rbf"]
+    pair_r = pidx.pair_r[:Pn].contiguous()
+    chain = rep.layers[0].radial_chain()
+    run = lambda: fused.run_chain(chain, pair_r, pidx.num_unique, rep.distance_expansion, 0.0, hp["cutoff_upper"], True)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    reps = 10
+    ev0.record()
+    for _ in range(reps):
+        run()
+    ev1.record(); torch.cuda.synchronize()
+    c_ms = ev0.elapsed_time(ev1) / reps
+    hbm_peak, tc_peak, how = measured_peaks()
+    # algorithmic flops of one chain call: value + d/dr rows (2 per pair) through R->F->2F->3F (2(RF+2F^2+6F^2)
+    # = 270 336 flop per evaluated row at F=128, R=32); the 3xTF32 split executes 3x this on the tensor pipe
+    flops = 2 * Pn * 2 * (R * F + F * 2 * F + 2 * F * 3 * F)
+    ach_tf = flops / (c_ms * 1e-3) / 1e12
+    roofline = {"kernel": "gemm3x_tf32_kernel x3 (+ pair_rbf_split): tcgen05 radial chain of one interaction layer, value + d/dr on unique pairs",
+                "bound": "tensor", "achieved": ach_tf, "peak": tc_peak, "peak_source": how + " dense bf16 burst", "unit": "TFLOP/s",
+                "frac": ach_tf / tc_peak, "frac_of_3xtf32_ceiling": ach_tf / (tc_peak / 6.0),
+                "note": "fp32-parity path: TF32 runs at 1/2 the bf16 rate and each product needs 3 split MMAs, so the ceiling for this kernel is peak/6",
+                "traffic": 4.257e9, "traffic_source": "ncu --set full r01 (dram read+write summed over the 3 GEMM launches of one chain call, profiles/r01_gemm3x_ncu.md)",
+                "algorithmic_flops": flops, "kernel_ms": c_ms, "pairs": Pn}
+    # ---- secondary: interaction message passing forward (a7), HBM/L2-gather bound ----
     I_, A_, S_ = (torch.randn(N, k, F, device=dev) for k in (1, 3, 5))
     w = torch.randn(E, 3, F, device=dev)
     for _ in range(3):
         ops.fn_message_passing(I_, A_, S_, w, None, g.nbr_j, g.indptr, g.rev, g.nbr_j, g.indptr)
     torch.cuda.synchronize()
-    reps = 10
     ev0.record()
     for _ in range(reps):
         ops.fn_message_passing(I_, A_, S_, w, None, g.nbr_j, g.indptr, g.rev, g.nbr_j, g.indptr)
     ev1.record(); torch.cuda.synchronize()
     k_ms = ev0.elapsed_time(ev1) / reps
     alg_bytes = 4 * (3 * E * F + 2 * 9 * N * F) + 4 * (2 * E + N + 1)  # edge weights + node in/out + CSR
-    peak, how = measured_peaks()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    roofline = {"kernel": "mp_fwd_kernel (interaction message passing fwd, one layer)", "bound": "hbm", "achieved": achieved,
-                "peak": peak, "peak_source": how, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "algorithmic_bytes": alg_bytes, "kernel_ms": k_ms, "edges": E}
+    roofline2 = {"kernel": "mp_fwd_kernel (interaction message passing fwd, one layer)", "bound": "hbm", "achieved": achieved,
+                 "peak": hbm_peak, "peak_source": how, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                 "algorithmic_bytes": alg_bytes, "kernel_ms": k_ms, "edges": E}
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -293,7 +323,7 @@ def main():
            "clocks": clocks.summary(),
            "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": ms_e2e / args.steps},
-           "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+           "gpu_launches": launches, "roofline": roofline, "roofline_secondary": roofline2, "cpu_baseline": cpu}
     print(json.dumps(out), flush=True)
     if dist_on:
         dist.destroy_process_group()

@@ -37,15 +37,17 @@ const char* tmd_last_error(void);
  * CSR: indptr[n+1], nbr_i/nbr_j/vec/dist[max_pairs].  num_pairs[0] = pairs found (may exceed max_pairs; slots
  * past max_pairs are dropped).  Slots >= num_pairs are left untouched (caller pre-fills -1 / 0).
  * box: [1 or n_batch,3,3]; box_stride = 0 (shared) or 9 (per sample).  rev (optional, may be NULL): slot of the
- * transposed pair.  workspace: 3*n+1 int32.  transpose=0 gives the half list (j <= i). */
+ * transposed pair.  transpose=0 gives the half list (j <= i).  max_cells > 0 enables the O(N) cell-grid candidate
+ * search for one rectangular periodic box with >= 3 cells per axis (decided on the device; identical output, other
+ * inputs use the ordered batch-segment scan).  workspace: 5*n + 8 + 3*(max_cells+1) int32. */
 int tmd_neighbor_csr_f32(const float* pos, const int64_t* batch, const float* box, int box_stride, int periodic,
                          int n, double cutoff_lower, double cutoff_upper, int loop, int transpose, int max_pairs,
-                         int* indptr, int* nbr_i, int* nbr_j, float* vec, float* dist, int* num_pairs, int* rev,
-                         int* workspace, void* stream);
+                         int max_cells, int* indptr, int* nbr_i, int* nbr_j, float* vec, float* dist, int* num_pairs,
+                         int* rev, int* workspace, void* stream);
 int tmd_neighbor_csr_f64(const double* pos, const int64_t* batch, const double* box, int box_stride, int periodic,
                          int n, double cutoff_lower, double cutoff_upper, int loop, int transpose, int max_pairs,
-                         int* indptr, int* nbr_i, int* nbr_j, double* vec, double* dist, int* num_pairs, int* rev,
-                         int* workspace, void* stream);
+                         int max_cells, int* indptr, int* nbr_i, int* nbr_j, double* vec, double* dist, int* num_pairs,
+                         int* rev, int* workspace, void* stream);
 
 /* ---- a2: position gradient of the neighbour outputs -------------------------------------------------------
  * Replaces neighbor_grad_positions (extensions/neighbor_utils.py:11-46; two index_add_ with atomics).
@@ -162,8 +164,13 @@ int tmd_pair_chain(const float* pair_r, const int* num_unique, int max_pairs, co
 int tmd_pair_chain_tc(const float* pair_r, const int* num_unique, int max_pairs, const float* const* W_hi,
                       const float* const* W_lo, const float* const* bias, const int* dims, int n_layers, int act,
                       int mul_cutoff, const float* means, const float* betas, double alpha, double lo, double hi,
-                      float* act_a_hi, float* act_a_lo, float* act_b_hi, float* act_b_lo, float* out_f, float* out_fp,
-                      void* stream);
+                      const float* rbf_hi, const float* rbf_lo, float* act_a_hi, float* act_a_lo, float* act_b_hi,
+                      float* act_b_lo, float* out_f, float* out_fp, void* stream);
+/* layer-0 operand of tmd_pair_chain_tc: rows (value[, d/dr]) of ExpNormalSmearing(r_p), TF32 split, K padded to a multiple
+ * of 32.  Computed once per frame and shared by the embedding chain and every interaction layer (rbf_hi / rbf_lo). */
+int tmd_pair_rbf_split(const float* pair_r, const int* num_unique, int max_pairs, int R, int rows_per_pair,
+                       const float* means, const float* betas, double alpha, double lo, double hi, float* a_hi,
+                       float* a_lo, void* stream);
 int tmd_mp_pair_bwd(const float* YI, const float* YA, const float* YS, const float* dMI, const float* dMA,
                     const float* dMS, const float* f, const float* fp, const int* pid, const int* nbr_j,
                     const int* indptr, int n, int F, float* dYI, float* dYA, float* dYS, float* d_pair_r, void* stream);

@@ -21,8 +21,8 @@ P, I, D, LL = c_void_p, c_int, c_double, c_longlong
 
 # symbol -> (argtypes, number of CUDA kernels one call launches)
 SIGNATURES = {
-    "tmd_neighbor_csr_f32": ([P, P, P, I, I, I, D, D, I, I, I, P, P, P, P, P, P, P, P, P], 5),
-    "tmd_neighbor_csr_f64": ([P, P, P, I, I, I, D, D, I, I, I, P, P, P, P, P, P, P, P, P], 5),
+    "tmd_neighbor_csr_f32": ([P, P, P, I, I, I, D, D, I, I, I, I, P, P, P, P, P, P, P, P, P], 9),
+    "tmd_neighbor_csr_f64": ([P, P, P, I, I, I, D, D, I, I, I, I, P, P, P, P, P, P, P, P, P], 9),
     "tmd_neighbor_grad_csr_f32": ([P, P, P, I, I, P, P, P, P, P, P], 1),
     "tmd_neighbor_grad_csr_f64": ([P, P, P, I, I, P, P, P, P, P, P], 1),
     "tmd_neighbor_grad_coo_f32": ([P, LL, P, P, P, P, P, P], 1),
@@ -56,7 +56,8 @@ SIGNATURES = {
     "tmd_p3_bwd": ([P] * 4 + [P] * 3 + [P] * 6 + [I, I, P], 1),
     "tmd_pair_index": ([P, P, P, P, P, I, I, P, P, P, P, P, P, P, P], 3),
     "tmd_pair_chain": ([P, P, I, P, P, P, P, P, P, P, I, I, I, P, P, D, D, D, P, P, P], 1),
-    "tmd_pair_chain_tc": ([P, P, I, P, P, P, P, I, I, I, P, P, D, D, D, P, P, P, P, P, P, P], 4),
+    "tmd_pair_chain_tc": ([P, P, I, P, P, P, P, I, I, I, P, P, D, D, D, P, P, P, P, P, P, P, P, P], 3),
+    "tmd_pair_rbf_split": ([P, P, I, I, I, P, P, D, D, D, P, P, P], 1),
     "tmd_mp_pair_bwd": ([P] * 11 + [I, I] + [P] * 4 + [P], 1),
     "tmd_embed_fwd": ([P] * 8 + [D, D, I, I] + [P] * 3 + [P], 1),
     "tmd_embed_bwd": ([P] * 9 + [D, D, I, I] + [P] * 5 + [P], 1),

@@ -34,3 +34,25 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+
+// Transposing warp reduction: every lane holds V partial values; afterwards lane l (< V) returns the warp-wide total of
+// value l.  V-1 shuffles in total (instead of 5 per value) and no serial dependency between the values.
+template <int V>
+__device__ __forceinline__ float warp_reduce_transpose(float (&v)[V], int lane) {
+  static_assert(V == 32 || V == 16 || V == 8, "V must be 8, 16 or 32");
+#pragma unroll
+  for (int s = V / 2; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = upper ? v[i] : v[i + s];
+      const float keep = upper ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  // lanes >= V (when V < 32) hold a copy of lane (l mod V)'s total after the remaining full-warp steps
+  float r = v[0];
+#pragma unroll
+  for (int s = 16; s >= V; s >>= 1) r += __shfl_xor_sync(0xffffffffu, r, s);
+  return r;
+}

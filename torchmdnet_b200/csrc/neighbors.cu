@@ -8,7 +8,8 @@
 //     no host-side boolean-mask compaction, no separate COO->CSR pass.
 //   * candidates are restricted to the row's own `batch` segment (binary search when `batch`
 //     is sorted, which is how every caller builds it), so 8 x 5000-atom boxes cost 8 x 5000^2,
-//     not 40000^2.
+//     not 40000^2; for one rectangular periodic box they come from a cell grid (27 cells, O(N)),
+//     staged in shared memory and rank-sorted so the emitted rows are identical to the scan's.
 //   * arithmetic identical to the reference: canonical orientation (larger index first),
 //     delta = pos_a - pos_b, sequential z,y,x minimum-image rounding with roundf (ties away),
 //     separate roundings for every mul/sub (no FMA contraction), cut-offs compared squared.
@@ -49,66 +50,191 @@ __global__ void batch_segments_kernel(const int64_t* __restrict__ batch, int n, 
   }
 }
 
+template <typename T> struct BoxRow { T b00, b10, b11, b20, b21, b22; };
+
+// minimum-image delta of the directed pair (i, j) computed in the canonical orientation (larger index first) with the
+// reference's operation order; returns whether lo2 <= d2 < hi2
+template <typename T>
+__device__ __forceinline__ bool pair_delta(const T* __restrict__ pos, int i, int j, T xi, T yi, T zi, int periodic,
+                                           const BoxRow<T>& B, T lo2, T hi2, T& dx, T& dy, T& dz, T& d2) {
+  const bool fwd = i > j;
+  const T xj = pos[3 * j], yj = pos[3 * j + 1], zj = pos[3 * j + 2];
+  dx = fwd ? sub_rn(xi, xj) : sub_rn(xj, xi);
+  dy = fwd ? sub_rn(yi, yj) : sub_rn(yj, yi);
+  dz = fwd ? sub_rn(zi, zj) : sub_rn(zj, zi);
+  if (periodic) {
+    const T s3 = round_away(div_rn(dz, B.b22));
+    dx = sub_rn(dx, mul_rn(s3, B.b20)); dy = sub_rn(dy, mul_rn(s3, B.b21)); dz = sub_rn(dz, mul_rn(s3, B.b22));
+    const T s2 = round_away(div_rn(dy, B.b11));
+    dx = sub_rn(dx, mul_rn(s2, B.b10)); dy = sub_rn(dy, mul_rn(s2, B.b11));
+    const T s1 = round_away(div_rn(dx, B.b00));
+    dx = sub_rn(dx, mul_rn(s1, B.b00));
+  }
+  d2 = add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz));
+  const bool ok = (d2 < hi2) && (d2 >= lo2);
+  if (!fwd) { dx = -dx; dy = -dy; dz = -dz; }
+  return ok;
+}
+
+// ---- cell grid (single rectangular periodic box): header ints {nx, ny, nz, ok}
+__global__ void cell_setup_kernel(const float* boxf, const double* boxd, int box_stride, int periodic, double cutoff,
+                                  int max_cells, int* __restrict__ hdr) {
+  int ok = (periodic && box_stride == 0 && max_cells >= 27) ? 1 : 0;
+  double b[9];
+  for (int k = 0; k < 9; ++k) b[k] = ok ? (boxf ? (double)boxf[k] : boxd[k]) : 0.0;
+  if (ok && (b[3] != 0.0 || b[6] != 0.0 || b[7] != 0.0 || b[1] != 0.0 || b[2] != 0.0 || b[5] != 0.0)) ok = 0;  // rectangular only
+  int nc[3] = {1, 1, 1};
+  if (ok) {
+    const double L[3] = {b[0], b[4], b[8]};
+    for (int d = 0; d < 3; ++d) {
+      nc[d] = (int)floor(L[d] / (cutoff * 1.0001));   // cell edge strictly larger than the cutoff
+      if (nc[d] < 3) ok = 0;                           // 27 distinct neighbour cells needed
+    }
+    while (ok && (long long)nc[0] * nc[1] * nc[2] > max_cells) {  // coarsen the longest axis until it fits
+      int d = (nc[0] >= nc[1] && nc[0] >= nc[2]) ? 0 : (nc[1] >= nc[2] ? 1 : 2);
+      if (--nc[d] < 3) ok = 0;
+    }
+  }
+  hdr[0] = nc[0]; hdr[1] = nc[1]; hdr[2] = nc[2]; hdr[3] = ok;
+}
+template <typename T>
+__global__ void cell_assign_kernel(const T* __restrict__ pos, const T* __restrict__ box, int n, const int* __restrict__ hdr,
+                                   int* __restrict__ cell_of, int* __restrict__ cell_count) {
+  if (!hdr[3]) return;
+  const int nx = hdr[0], ny = hdr[1], nz = hdr[2];
+  const T L[3] = {box[0], box[4], box[8]};
+  const int nc[3] = {nx, ny, nz};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int c[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      T f = pos[3 * i + d] / L[d];
+      f -= floor(f);
+      int k = (int)(f * (T)nc[d]);
+      c[d] = k < 0 ? 0 : (k >= nc[d] ? nc[d] - 1 : k);
+    }
+    const int id = (c[0] * ny + c[1]) * nz + c[2];
+    cell_of[i] = id;
+    atomicAdd(cell_count + id, 1);
+  }
+}
+__global__ void cell_fill_kernel(int n, const int* __restrict__ hdr, const int* __restrict__ cell_of,
+                                 const int* __restrict__ cell_start, int* __restrict__ cursor, int* __restrict__ cell_atoms) {
+  if (!hdr[3]) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int c = cell_of[i];
+    cell_atoms[cell_start[c] + atomicAdd(cursor + c, 1)] = i;
+  }
+}
+
+constexpr int ROW_CAP = 192;  // neighbours of one atom staged in shared memory for the in-row sort (cell path)
+
+// One warp owns one row i.  Candidates come either from the row's batch segment in ascending order (brute, already sorted)
+// or from the 27 neighbouring cells (unordered -> staged in shared memory and rank-sorted by j, so the emitted row is
+// identical to the brute one).  FILL=false only counts.
 template <typename T, bool FILL>
 __global__ void __launch_bounds__(256) neighbor_rows_kernel(
     const T* __restrict__ pos, const int64_t* __restrict__ batch, const T* __restrict__ box, int box_stride,
     int periodic, int n, T lo2, T hi2, int loop, int transpose, const int* __restrict__ seg_lo,
     const int* __restrict__ seg_hi, const int* __restrict__ unsorted_flag, const int* __restrict__ indptr,
     int max_pairs, int* __restrict__ deg, int* __restrict__ out_i, int* __restrict__ out_j, T* __restrict__ out_vec,
-    T* __restrict__ out_dist) {
+    T* __restrict__ out_dist, const int* __restrict__ cell_hdr, const int* __restrict__ cell_of,
+    const int* __restrict__ cell_start, const int* __restrict__ cell_atoms) {
+  extern __shared__ unsigned char nb_smem[];
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
+  const int wid = threadIdx.x >> 5;
   const int nwarps = gridDim.x * warps_per_block;
   const bool unsorted = (*unsorted_flag) != 0;
-  for (int i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < n; i += nwarps) {
+  const bool use_cells = cell_hdr && cell_hdr[3] != 0;
+  // per-warp staging (cell path, FILL only): j[ROW_CAP], then dx, dy, dz, d2 as T
+  int* sj = reinterpret_cast<int*>(nb_smem) + wid * ROW_CAP;
+  T* sv = reinterpret_cast<T*>(nb_smem + (size_t)warps_per_block * ROW_CAP * sizeof(int)) + (size_t)wid * ROW_CAP * 4;
+  for (int i = blockIdx.x * warps_per_block + wid; i < n; i += nwarps) {
     const T xi = pos[3 * i], yi = pos[3 * i + 1], zi = pos[3 * i + 2];
     const int64_t bi = batch[i];
-    T b00 = 0, b10 = 0, b11 = 0, b20 = 0, b21 = 0, b22 = 0;
+    BoxRow<T> B = {0, 0, 0, 0, 0, 0};
     if (periodic) {
       const T* bx = box + (size_t)bi * box_stride;
-      b00 = bx[0]; b10 = bx[3]; b11 = bx[4]; b20 = bx[6]; b21 = bx[7]; b22 = bx[8];
+      B.b00 = bx[0]; B.b10 = bx[3]; B.b11 = bx[4]; B.b20 = bx[6]; B.b21 = bx[7]; B.b22 = bx[8];
     }
-    int jlo = unsorted ? 0 : seg_lo[i];
-    int jhi = unsorted ? n : seg_hi[i];
-    if (!transpose) jhi = min(jhi, i + 1);  // half list keeps only j <= i (the canonical orientation)
     const int base = FILL ? indptr[i] : 0;
     int count = 0;
-    for (int j0 = jlo; j0 < jhi; j0 += 32) {
-      const int j = j0 + lane;
-      bool ok = false;
-      T dx = 0, dy = 0, dz = 0, d2 = 0;
-      if (j < jhi && batch[j] == bi) {
-        if (j == i) {
-          ok = loop != 0;
-        } else {
-          const bool fwd = i > j;  // canonical orientation: larger index minus smaller index
-          const T xj = pos[3 * j], yj = pos[3 * j + 1], zj = pos[3 * j + 2];
-          dx = fwd ? sub_rn(xi, xj) : sub_rn(xj, xi);
-          dy = fwd ? sub_rn(yi, yj) : sub_rn(yj, yi);
-          dz = fwd ? sub_rn(zi, zj) : sub_rn(zj, zi);
-          if (periodic) {
-            const T s3 = round_away(div_rn(dz, b22));
-            dx = sub_rn(dx, mul_rn(s3, b20)); dy = sub_rn(dy, mul_rn(s3, b21)); dz = sub_rn(dz, mul_rn(s3, b22));
-            const T s2 = round_away(div_rn(dy, b11));
-            dx = sub_rn(dx, mul_rn(s2, b10)); dy = sub_rn(dy, mul_rn(s2, b11));
-            const T s1 = round_away(div_rn(dx, b00));
-            dx = sub_rn(dx, mul_rn(s1, b00));
+    bool row_done = false;
+    if (use_cells) {
+      // ------------------------------------------------------------------ cell path
+      const int nx = cell_hdr[0], ny = cell_hdr[1], nz = cell_hdr[2];
+      const int ci = cell_of[i];
+      const int cz = ci % nz, cy = (ci / nz) % ny, cx = ci / (nz * ny);
+      for (int nb = 0; nb < 27; ++nb) {
+        const int ax = (cx + nb / 9 - 1 + nx) % nx, ay = (cy + (nb / 3) % 3 - 1 + ny) % ny, az = (cz + nb % 3 - 1 + nz) % nz;
+        const int c2 = (ax * ny + ay) * nz + az;
+        const int s0 = cell_start[c2], s1 = cell_start[c2 + 1];
+        for (int t0 = s0; t0 < s1; t0 += 32) {
+          const int t = t0 + lane;
+          bool ok = false;
+          int j = -1;
+          T dx = 0, dy = 0, dz = 0, d2 = 0;
+          if (t < s1) {
+            j = cell_atoms[t];
+            if (batch[j] == bi && (transpose || j <= i)) {
+              if (j == i) ok = loop != 0;
+              else ok = pair_delta(pos, i, j, xi, yi, zi, periodic, B, lo2, hi2, dx, dy, dz, d2);
+            }
           }
-          d2 = add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz));
-          ok = (d2 < hi2) && (d2 >= lo2);
-          if (!fwd) { dx = -dx; dy = -dy; dz = -dz; }
+          const unsigned m = __ballot_sync(0xffffffffu, ok);
+          if (FILL && ok) {
+            const int k = count + __popc(m & ((1u << lane) - 1u));
+            if (k < ROW_CAP) { sj[k] = j; sv[4 * k] = dx; sv[4 * k + 1] = dy; sv[4 * k + 2] = dz; sv[4 * k + 3] = d2; }
+          }
+          count += __popc(m);
         }
       }
-      const unsigned m = __ballot_sync(0xffffffffu, ok);
-      if (FILL && ok) {
-        const int slot = base + count + __popc(m & ((1u << lane) - 1u));
-        if (slot < max_pairs) {
-          out_i[slot] = i; out_j[slot] = j;
-          out_vec[3 * (size_t)slot] = dx; out_vec[3 * (size_t)slot + 1] = dy; out_vec[3 * (size_t)slot + 2] = dz;
-          out_dist[slot] = sqrt_rn(d2);
+      if (!FILL) {
+        row_done = true;
+      } else if (count <= ROW_CAP) {
+        __syncwarp();
+        for (int e = lane; e < count; e += 32) {   // rank sort by j (unique within a row)
+          const int j = sj[e];
+          int rank = 0;
+          for (int u = 0; u < count; ++u) rank += (sj[u] < j);
+          const int slot = base + rank;
+          if (slot < max_pairs) {
+            out_i[slot] = i; out_j[slot] = j;
+            out_vec[3 * (size_t)slot] = sv[4 * e]; out_vec[3 * (size_t)slot + 1] = sv[4 * e + 1]; out_vec[3 * (size_t)slot + 2] = sv[4 * e + 2];
+            out_dist[slot] = sqrt_rn(sv[4 * e + 3]);
+          }
         }
+        __syncwarp();
+        row_done = true;
+      } else {
+        count = 0;  // very dense row: emit it with the ordered segment scan below
       }
-      count += __popc(m);
+    }
+    if (!row_done) {
+      // ------------------------------------------------------------------ ordered scan of the batch segment
+      int jlo = unsorted ? 0 : seg_lo[i];
+      int jhi = unsorted ? n : seg_hi[i];
+      if (!transpose) jhi = min(jhi, i + 1);  // half list keeps only j <= i (the canonical orientation)
+      for (int j0 = jlo; j0 < jhi; j0 += 32) {
+        const int j = j0 + lane;
+        bool ok = false;
+        T dx = 0, dy = 0, dz = 0, d2 = 0;
+        if (j < jhi && batch[j] == bi) {
+          if (j == i) ok = loop != 0;
+          else ok = pair_delta(pos, i, j, xi, yi, zi, periodic, B, lo2, hi2, dx, dy, dz, d2);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (FILL && ok) {
+          const int slot = base + count + __popc(m & ((1u << lane) - 1u));
+          if (slot < max_pairs) {
+            out_i[slot] = i; out_j[slot] = j;
+            out_vec[3 * (size_t)slot] = dx; out_vec[3 * (size_t)slot + 1] = dy; out_vec[3 * (size_t)slot + 2] = dz;
+            out_dist[slot] = sqrt_rn(d2);
+          }
+        }
+        count += __popc(m);
+      }
     }
     if (!FILL && lane == 0) deg[i] = count;
   }
@@ -247,26 +373,46 @@ __global__ void csr_sort_rows_kernel(const int* __restrict__ ei, int E, int n, c
 template <typename T>
 static int neighbor_csr_impl(const T* pos, const int64_t* batch, const T* box, int box_stride, int periodic, int n,
                              double cutoff_lower, double cutoff_upper, int loop, int transpose, int max_pairs,
-                             int* indptr, int* nbr_i, int* nbr_j, T* vec, T* dist, int* num_pairs, int* rev,
-                             int* workspace, cudaStream_t st) {
-  TMD_REQUIRE(n >= 0 && max_pairs >= 0, "neighbor_csr: negative size");
+                             int max_cells, int* indptr, int* nbr_i, int* nbr_j, T* vec, T* dist, int* num_pairs,
+                             int* rev, int* workspace, cudaStream_t st) {
+  TMD_REQUIRE(n >= 0 && max_pairs >= 0 && max_cells >= 0, "neighbor_csr: negative size");
   TMD_REQUIRE(pos && batch && indptr && nbr_i && nbr_j && vec && dist && num_pairs && workspace,
               "neighbor_csr: null pointer");
   TMD_REQUIRE(!periodic || box, "neighbor_csr: periodic without box");
   if (n == 0) { cudaMemsetAsync(num_pairs, 0, sizeof(int), st); cudaMemsetAsync(indptr, 0, sizeof(int), st); return tmd_check_launch("neighbor_csr(empty)"); }
+  // workspace (ints): seg_lo[n] seg_hi[n] deg[n] flag[1] | hdr[4] cell_of[n] cell_atoms[n] cell_count[C+1] cell_start[C+1] cursor[C+1]
   int* seg_lo = workspace; int* seg_hi = workspace + n; int* deg = workspace + 2 * n; int* flag = workspace + 3 * n;
-  cudaMemsetAsync(flag, 0, sizeof(int), st);
+  int* hdr = workspace + 3 * n + 1; int* cell_of = hdr + 4; int* cell_atoms = cell_of + n;
+  int* cell_count = cell_atoms + n; int* cell_start = cell_count + (max_cells + 1); int* cursor = cell_start + (max_cells + 1);
+  const bool cells = max_cells >= 27 && periodic && box_stride == 0;
+  cudaMemsetAsync(flag, 0, sizeof(int) * 5, st);  // flag + hdr (hdr.ok = 0 unless the setup kernel enables the grid)
   batch_segments_kernel<<<tmd_blocks_for(n, 256), 256, 0, st>>>(batch, n, seg_lo, seg_hi, flag);
+  if (cells) {
+    cudaMemsetAsync(cell_count, 0, sizeof(int) * 3 * (max_cells + 1), st);
+    const bool f32 = sizeof(T) == 4;
+    cell_setup_kernel<<<1, 1, 0, st>>>(f32 ? reinterpret_cast<const float*>(box) : nullptr,
+                                       f32 ? nullptr : reinterpret_cast<const double*>(box), box_stride, periodic,
+                                       cutoff_upper, max_cells, hdr);
+    cell_assign_kernel<T><<<tmd_blocks_for(n, 256), 256, 0, st>>>(pos, box, n, hdr, cell_of, cell_count);
+    exclusive_scan_kernel<<<1, 1024, 0, st>>>(cell_count, max_cells, cell_start, nullptr);
+    cell_fill_kernel<<<tmd_blocks_for(n, 256), 256, 0, st>>>(n, hdr, cell_of, cell_start, cursor, cell_atoms);
+  }
   // cut-offs are squared in double and rounded to T, like the reference's python-float kernel args
   const T lo2 = (T)(cutoff_lower * cutoff_lower), hi2 = (T)(cutoff_upper * cutoff_upper);
   const int blocks = tmd_blocks_for((long long)n * 32, 256, 148 * 8);
-  neighbor_rows_kernel<T, false><<<blocks, 256, 0, st>>>(pos, batch, box, box_stride, periodic, n, lo2, hi2, loop,
-                                                          transpose, seg_lo, seg_hi, flag, nullptr, max_pairs, deg,
-                                                          nullptr, nullptr, nullptr, nullptr);
+  const size_t smem = cells ? (size_t)8 * ROW_CAP * (sizeof(int) + 4 * sizeof(T)) : 0;
+  if (smem > 48 * 1024) {
+    cudaFuncSetAttribute(neighbor_rows_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(neighbor_rows_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
+  const int* chdr = cells ? hdr : nullptr;
+  neighbor_rows_kernel<T, false><<<blocks, 256, smem, st>>>(pos, batch, box, box_stride, periodic, n, lo2, hi2, loop,
+                                                             transpose, seg_lo, seg_hi, flag, nullptr, max_pairs, deg,
+                                                             nullptr, nullptr, nullptr, nullptr, chdr, cell_of, cell_start, cell_atoms);
   exclusive_scan_kernel<<<1, 1024, 0, st>>>(deg, n, indptr, num_pairs);
-  neighbor_rows_kernel<T, true><<<blocks, 256, 0, st>>>(pos, batch, box, box_stride, periodic, n, lo2, hi2, loop,
-                                                         transpose, seg_lo, seg_hi, flag, indptr, max_pairs, deg,
-                                                         nbr_i, nbr_j, vec, dist);
+  neighbor_rows_kernel<T, true><<<blocks, 256, smem, st>>>(pos, batch, box, box_stride, periodic, n, lo2, hi2, loop,
+                                                            transpose, seg_lo, seg_hi, flag, indptr, max_pairs, deg,
+                                                            nbr_i, nbr_j, vec, dist, chdr, cell_of, cell_start, cell_atoms);
   if (rev) reverse_edge_kernel<<<tmd_blocks_for(max_pairs, 256), 256, 0, st>>>(indptr, nbr_i, nbr_j, num_pairs, max_pairs, rev);
   return tmd_check_launch("neighbor_csr");
 }
@@ -275,19 +421,19 @@ extern "C" {
 
 int tmd_neighbor_csr_f32(const float* pos, const int64_t* batch, const float* box, int box_stride, int periodic,
                          int n, double cutoff_lower, double cutoff_upper, int loop, int transpose, int max_pairs,
-                         int* indptr, int* nbr_i, int* nbr_j, float* vec, float* dist, int* num_pairs, int* rev,
-                         int* workspace, void* stream) {
+                         int max_cells, int* indptr, int* nbr_i, int* nbr_j, float* vec, float* dist, int* num_pairs,
+                         int* rev, int* workspace, void* stream) {
   return neighbor_csr_impl<float>(pos, batch, box, box_stride, periodic, n, cutoff_lower, cutoff_upper, loop,
-                                  transpose, max_pairs, indptr, nbr_i, nbr_j, vec, dist, num_pairs, rev, workspace,
-                                  (cudaStream_t)stream);
+                                  transpose, max_pairs, max_cells, indptr, nbr_i, nbr_j, vec, dist, num_pairs, rev,
+                                  workspace, (cudaStream_t)stream);
 }
 int tmd_neighbor_csr_f64(const double* pos, const int64_t* batch, const double* box, int box_stride, int periodic,
                          int n, double cutoff_lower, double cutoff_upper, int loop, int transpose, int max_pairs,
-                         int* indptr, int* nbr_i, int* nbr_j, double* vec, double* dist, int* num_pairs, int* rev,
-                         int* workspace, void* stream) {
+                         int max_cells, int* indptr, int* nbr_i, int* nbr_j, double* vec, double* dist, int* num_pairs,
+                         int* rev, int* workspace, void* stream) {
   return neighbor_csr_impl<double>(pos, batch, box, box_stride, periodic, n, cutoff_lower, cutoff_upper, loop,
-                                   transpose, max_pairs, indptr, nbr_i, nbr_j, vec, dist, num_pairs, rev, workspace,
-                                   (cudaStream_t)stream);
+                                   transpose, max_pairs, max_cells, indptr, nbr_i, nbr_j, vec, dist, num_pairs, rev,
+                                   workspace, (cudaStream_t)stream);
 }
 
 int tmd_neighbor_grad_csr_f32(const int* indptr, const int* rev, const int* num_pairs, int max_pairs, int n,

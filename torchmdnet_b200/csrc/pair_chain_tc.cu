@@ -408,14 +408,29 @@ extern "C" {
 // Tensor-core radial chain on pairs (same contract as tmd_pair_chain, 3xTF32 on tcgen05).
 //   W_hi[l], W_lo[l] : TF32 split of the nn.Linear weight [N_l, K_l_pad] (row-major, K padded to a multiple of 32 with 0)
 //   dims = {R, N_0, N_1, N_2}; hidden widths must be multiples of 32, every N_l a multiple of 64
+//   rbf_hi/rbf_lo    : optional layer-0 operand from tmd_pair_rbf_split (shared by all chains of a frame), else NULL
 //   act_a_hi/lo, act_b_hi/lo : ping-pong workspaces, each >= rows_pad * max(K_l_pad) floats where
 //                              rows_pad = roundup(max_pairs * (out_fp ? 2 : 1), 128)
+int tmd_pair_rbf_split(const float* pair_r, const int* num_unique, int max_pairs, int R, int rows_per_pair,
+                       const float* means, const float* betas, double alpha, double lo, double hi, float* a_hi,
+                       float* a_lo, void* stream) {
+  TMD_REQUIRE(pair_r && num_unique && means && betas && a_hi && a_lo, "pair_rbf_split: null pointer");
+  TMD_REQUIRE(rows_per_pair == 1 || rows_per_pair == 2, "pair_rbf_split: rows_per_pair must be 1 or 2");
+  if (max_pairs == 0) return TMD_OK;
+  const int K0 = ((R + BK - 1) / BK) * BK;
+  const long long total = (long long)max_pairs * K0;
+  pair_rbf_split_kernel<<<tmd_blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      pair_r, num_unique, max_pairs, R, K0, rows_per_pair, means, betas, (float)alpha, (float)lo, (float)hi, a_hi, a_lo);
+  return tmd_check_launch("pair_rbf_split");
+}
+
 int tmd_pair_chain_tc(const float* pair_r, const int* num_unique, int max_pairs, const float* const* W_hi,
                       const float* const* W_lo, const float* const* bias, const int* dims, int n_layers, int act,
                       int mul_cutoff, const float* means, const float* betas, double alpha, double lo, double hi,
-                      float* act_a_hi, float* act_a_lo, float* act_b_hi, float* act_b_lo, float* out_f, float* out_fp,
-                      void* stream) {
+                      const float* rbf_hi, const float* rbf_lo, float* act_a_hi, float* act_a_lo, float* act_b_hi,
+                      float* act_b_lo, float* out_f, float* out_fp, void* stream) {
   TMD_REQUIRE(pair_r && num_unique && W_hi && W_lo && bias && dims && means && betas && out_f, "pair_chain_tc: null pointer");
+  TMD_REQUIRE((rbf_hi == nullptr) == (rbf_lo == nullptr), "pair_chain_tc: rbf_hi / rbf_lo must be given together");
   TMD_REQUIRE(act_a_hi && act_a_lo && act_b_hi && act_b_lo, "pair_chain_tc: null workspace");
   TMD_REQUIRE(n_layers >= 1 && n_layers <= 3, "pair_chain_tc: n_layers must be 1..3");
   if (max_pairs == 0) return TMD_OK;
@@ -424,12 +439,15 @@ int tmd_pair_chain_tc(const float* pair_r, const int* num_unique, int max_pairs,
   const int rows_pad = ((max_pairs * rpp + BM - 1) / BM) * BM;
   const int R = dims[0];
   const int K0 = ((R + BK - 1) / BK) * BK;
-  {
+  if (!rbf_hi) {  // layer-0 operand not precomputed by tmd_pair_rbf_split: build it into workspace A
     const long long total = (long long)max_pairs * K0;
     pair_rbf_split_kernel<<<tmd_blocks_for(total, 256), 256, 0, st>>>(pair_r, num_unique, max_pairs, R, K0, rpp, means, betas,
                                                                       (float)alpha, (float)lo, (float)hi, act_a_hi, act_a_lo);
   }
-  float* in_hi = act_a_hi; float* in_lo = act_a_lo; float* o_hi = act_b_hi; float* o_lo = act_b_lo;
+  const float* in_hi = rbf_hi ? rbf_hi : act_a_hi;
+  const float* in_lo = rbf_hi ? rbf_lo : act_a_lo;
+  float* o_hi = act_b_hi; float* o_lo = act_b_lo;
+  float* n_hi = act_a_hi; float* n_lo = act_a_lo;   // where the layer after this one writes
   int K = K0;
   for (int l = 0; l < n_layers; ++l) {
     const int N = dims[l + 1];
@@ -460,9 +478,10 @@ int tmd_pair_chain_tc(const float* pair_r, const int* num_unique, int max_pairs,
       gemm3x_tf32_kernel<2><<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
     }
     // next layer reads what this one wrote
+    in_hi = o_hi; in_lo = o_lo;
     float* t;
-    t = in_hi; in_hi = o_hi; o_hi = t;
-    t = in_lo; in_lo = o_lo; o_lo = t;
+    t = o_hi; o_hi = n_hi; n_hi = t;
+    t = o_lo; o_lo = n_lo; n_lo = t;
     K = N;
   }
   return tmd_check_launch("pair_chain_tc");

@@ -6,7 +6,7 @@ message passing is a single gather kernel that emits dE/dr per pair.  Training (
 using the autograd-composed ops of tensornet_ops.py.
 """
 import ctypes
-from typing import NamedTuple, Sequence
+from typing import NamedTuple, Optional, Sequence
 
 import torch
 from torch import Tensor
@@ -119,7 +119,29 @@ class RadialChain:
         return self._wt, self._b, self._dims
 
 
-def run_chain(chain: RadialChain, pair_r: Tensor, num_unique: Tensor, rbf_mod, lo: float, hi: float, want_tangent: bool):
+class RbfOperand(NamedTuple):
+    hi: Tensor
+    lo: Tensor
+    rows_per_pair: int
+
+
+def precompute_rbf(pair_r: Tensor, num_unique: Tensor, rbf_mod, lo: float, hi: float, want_tangent: bool) -> Optional[RbfOperand]:
+    """Layer-0 tensor-core operand (rbf and d rbf/dr, TF32 split), shared by all radial chains of one frame."""
+    P = pair_r.shape[0]
+    if not USE_TENSOR_CORES or P == 0:
+        return None
+    rpp = 2 if want_tangent else 1
+    R = rbf_mod.means.shape[0]
+    rows_pad = -(-(P * rpp) // 128) * 128
+    K0 = -(-R // 32) * 32
+    buf = torch.empty(2, rows_pad, K0, device=pair_r.device, dtype=torch.float32)
+    _lib.call("tmd_pair_rbf_split", p(pair_r), p(num_unique), P, R, rpp, p(rbf_mod.means.detach()), p(rbf_mod.betas.detach()),
+              float(rbf_mod.alpha), float(lo), float(hi), p(buf[0]), p(buf[1]), device=pair_r.device)
+    return RbfOperand(buf[0], buf[1], rpp)
+
+
+def run_chain(chain: RadialChain, pair_r: Tensor, num_unique: Tensor, rbf_mod, lo: float, hi: float, want_tangent: bool,
+              rbf_op: Optional[RbfOperand] = None):
     """-> (f [P,N_last], f' or None).  `rbf_mod` is the ExpNormalSmearing module (means/betas/alpha)."""
     wt, b, dims = chain.tensors()
     P = pair_r.shape[0]
@@ -131,11 +153,13 @@ def run_chain(chain: RadialChain, pair_r: Tensor, num_unique: Tensor, rbf_mod, l
         rows_pad = -(-(P * (2 if want_tangent else 1)) // 128) * 128
         width = max([his[0].shape[1]] + [w.shape[1] for w in wt[:-1]])
         ws = torch.empty(4, rows_pad, width, device=pair_r.device, dtype=torch.float32)
+        if rbf_op is not None and rbf_op.rows_per_pair != (2 if want_tangent else 1):
+            rbf_op = None
         _lib.call("tmd_pair_chain_tc", p(pair_r), p(num_unique), P, ctypes.cast(p_hi, ctypes.c_void_p),
                   ctypes.cast(p_lo, ctypes.c_void_p), ctypes.cast(p_b, ctypes.c_void_p), ctypes.cast(dims, ctypes.c_void_p),
                   len(wt), int(chain.act), int(chain.mul_cutoff), p(rbf_mod.means.detach()), p(rbf_mod.betas.detach()),
-                  float(rbf_mod.alpha), float(lo), float(hi), p(ws[0]), p(ws[1]), p(ws[2]), p(ws[3]), p(f), p(fp),
-                  device=pair_r.device)
+                  float(rbf_mod.alpha), float(lo), float(hi), p(rbf_op.hi) if rbf_op else None, p(rbf_op.lo) if rbf_op else None,
+                  p(ws[0]), p(ws[1]), p(ws[2]), p(ws[3]), p(f), p(fp), device=pair_r.device)
         return f, fp
     wt3 = wt + [None] * (3 - len(wt))
     b3 = b + [None] * (3 - len(b))
@@ -153,10 +177,10 @@ class _InteractionMP(torch.autograd.Function):
     """M = sum_e f(r_e) * Y_j with f = cutoff * MLP(rbf(r)) evaluated per pair (rows a6 + a7)."""
 
     @staticmethod
-    def forward(ctx, YI, YA, YS, pair_r, chain, rbf_mod, lo, hi, g, pidx):
+    def forward(ctx, YI, YA, YS, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op):
         YI, YA, YS = YI.contiguous(), YA.contiguous(), YS.contiguous()
         need = pair_r.requires_grad
-        f, fp = run_chain(chain, pair_r.detach(), pidx.num_unique, rbf_mod, lo, hi, need)
+        f, fp = run_chain(chain, pair_r.detach(), pidx.num_unique, rbf_mod, lo, hi, need, rbf_op)
         N, F = YI.shape[0], YI.shape[-1]
         M = _triple(N, F, YI.device)
         _lib.call("tmd_mp_fwd", p(YI), p(YA), p(YS), p(f), p(pidx.pid), p(g.nbr_j), p(g.indptr), N, F, p(M[0]), p(M[1]), p(M[2]),
@@ -175,20 +199,20 @@ class _InteractionMP(torch.autograd.Function):
         _lib.call("tmd_mp_pair_bwd", p(YI), p(YA), p(YS), p(dI.contiguous()), p(dA.contiguous()), p(dS.contiguous()), p(f),
                   p(fp) if ctx.has_fp else None, p(pid), p(nbr_j), p(indptr), N, F, p(dY[0]), p(dY[1]), p(dY[2]), p(d_r),
                   device=YI.device)
-        return dY[0], dY[1], dY[2], d_r, None, None, None, None, None, None
+        return dY[0], dY[1], dY[2], d_r, None, None, None, None, None, None, None
 
 
-def interaction_message_passing(Y, pair_r, chain, rbf_mod, lo, hi, g, pidx):
-    return _InteractionMP.apply(Y[0], Y[1], Y[2], pair_r, chain, rbf_mod, lo, hi, g, pidx)
+def interaction_message_passing(Y, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op=None):
+    return _InteractionMP.apply(Y[0], Y[1], Y[2], pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op)
 
 
 class _EmbeddingMP(torch.autograd.Function):
     """I/A/S of the TensorNet embedding from (dist, rhat) with w = C(r)(U_i+V_j)(W_k rbf + b_k) built in-kernel (row a5)."""
 
     @staticmethod
-    def forward(ctx, dist, rhat, U, V, pair_r, chain, rbf_mod, lo, hi, g, pidx):
+    def forward(ctx, dist, rhat, U, V, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op):
         need = dist.requires_grad or rhat.requires_grad
-        dp, dpp = run_chain(chain, pair_r.detach(), pidx.num_unique, rbf_mod, lo, hi, need)
+        dp, dpp = run_chain(chain, pair_r.detach(), pidx.num_unique, rbf_mod, lo, hi, need, rbf_op)
         dist_c, rhat_c, U, V = dist.detach().contiguous(), rhat.detach().contiguous(), U.contiguous(), V.contiguous()
         N, F = U.shape[0], U.shape[-1]
         out = _triple(N, F, U.device)
@@ -202,13 +226,13 @@ class _EmbeddingMP(torch.autograd.Function):
     def backward(ctx, dI, dA, dS):
         dist, rhat, dp, dpp, pid, nbr_j, indptr, U, V = ctx.saved_tensors
         if not ctx.has_tangent:
-            return (None,) * 11
+            return (None,) * 12
         N, F = U.shape[0], U.shape[-1]
         g_dist, g_rhat = torch.zeros_like(dist), torch.zeros_like(rhat)
         _lib.call("tmd_embed_bwd", p(rhat), p(dist), p(dp), p(dpp), p(pid), p(nbr_j), p(indptr), p(U), p(V), ctx.lo, ctx.hi,
                   N, F, p(dI.contiguous()), p(dA.contiguous()), p(dS.contiguous()), p(g_dist), p(g_rhat), device=U.device)
-        return g_dist, g_rhat, None, None, None, None, None, None, None, None, None
+        return g_dist, g_rhat, None, None, None, None, None, None, None, None, None, None
 
 
-def embedding_message_passing(dist, rhat, U, V, pair_r, chain, rbf_mod, lo, hi, g, pidx):
-    return _EmbeddingMP.apply(dist, rhat, U, V, pair_r, chain, rbf_mod, lo, hi, g, pidx)
+def embedding_message_passing(dist, rhat, U, V, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op=None):
+    return _EmbeddingMP.apply(dist, rhat, U, V, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op)

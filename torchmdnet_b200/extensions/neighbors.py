@@ -64,9 +64,11 @@ def _build(pos, batch, box, use_periodic, lo, hi, loop, transpose, max_pairs, wa
     if n == 0:
         indptr.zero_()
         return indptr, nbr_i, nbr_j, rev, num_pairs, vec, dist
-    ws = torch.empty(3 * n + 1, **i32)
+    # cell grid for one rectangular periodic box (decided on the device from the box tensor); otherwise segment scan
+    max_cells = min(4 * n + 64, 1 << 20) if (use_periodic and stride == 0 and n >= 512) else 0
+    ws = torch.empty(5 * n + 8 + 3 * (max_cells + 1), **i32)
     _lib.call("tmd_neighbor_csr_" + _suffix(pos.dtype), _lib.ptr(pos_c), _lib.ptr(batch_c), _lib.ptr(box_c), stride,
-              int(use_periodic), n, float(lo), float(hi), int(loop), int(transpose), int(max_pairs), _lib.ptr(indptr),
+              int(use_periodic), n, float(lo), float(hi), int(loop), int(transpose), int(max_pairs), max_cells, _lib.ptr(indptr),
               _lib.ptr(nbr_i), _lib.ptr(nbr_j), _lib.ptr(vec), _lib.ptr(dist), _lib.ptr(num_pairs), _lib.ptr(rev),
               _lib.ptr(ws), device=dev)
     return indptr, nbr_i, nbr_j, rev, num_pairs, vec, dist

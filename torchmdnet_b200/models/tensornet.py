@@ -77,9 +77,9 @@ class TensorEmbedding(nn.Module):
             Z = self.emb(z)
             U = torch.nn.functional.linear(Z, self.emb2.weight[:, :F_])
             V = torch.nn.functional.linear(Z, self.emb2.weight[:, F_:], self.emb2.bias)
-            dist, pair_r, pidx, rbf_mod = fast
+            dist, pair_r, pidx, rbf_mod, rbf_op = fast
             I, A, S = fused.embedding_message_passing(dist, rhat, U.detach(), V.detach(), pair_r, self.radial_chain(), rbf_mod,
-                                                      self.cutoff.cutoff_lower, self.cutoff.cutoff_upper, g, pidx)
+                                                      self.cutoff.cutoff_lower, self.cutoff.cutoff_upper, g, pidx, rbf_op)
         else:
             w = self.pair_weights(z, nbr_i, nbr_j, cut, rbf)
             I, A, S = ops.fn_radial_message_passing(rhat, w, None, g.indptr)
@@ -131,9 +131,9 @@ class Interaction(nn.Module):
         Y = (lt[0](Xn[0]), lt[1](Xn[1]), lt[2](Xn[2]))
         if fast is not None:
             # fused path: f (and df/dr) once per unordered pair, message passing reads it through the pair index
-            dist, pair_r, pidx, rbf_mod = fast
+            dist, pair_r, pidx, rbf_mod, rbf_op = fast
             M = fused.interaction_message_passing(Y, pair_r, self.radial_chain(), rbf_mod, self.cutoff.cutoff_lower,
-                                                  self.cutoff.cutoff_upper, g, pidx)
+                                                  self.cutoff.cutoff_upper, g, pidx, rbf_op)
         else:
             f = self.edge_weights(rbf, cut)
             # the neighbour list is symmetric and f depends on |r| only, so the CSC of the graph is
@@ -223,7 +223,10 @@ class TensorNet(nn.Module):
         rhat = vec / dist.masked_fill(dist == 0, 1).unsqueeze(1)
         if use_fused:
             pair_r = fused.pair_distances(dist, pidx, P)
-            fast = (dist, pair_r, pidx, self.distance_expansion)
+            # rbf(r) and d rbf/dr once per frame: the layer-0 tensor-core operand of every radial chain
+            rbf_op = fused.precompute_rbf(pair_r.detach(), pidx.num_unique, self.distance_expansion, self.cutoff_lower,
+                                          self.cutoff_upper, pair_r.requires_grad)
+            fast = (dist, pair_r, pidx, self.distance_expansion, rbf_op)
             X = self.tensor_embedding(z, g, None, None, None, rhat, None, fast=fast)
             for layer in self.layers:
                 X = layer(X, g, None, None, qf, fast=fast)
