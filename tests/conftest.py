@@ -2,6 +2,11 @@ import os
 import sys
 
 import pytest
+import torch
+
+# the CPU oracle is called from the GPU tests too: a fixed, small thread count keeps it fast on many-core hosts
+# (128 default threads oversubscribe on these tensor sizes and made one run take 12 minutes)
+torch.set_num_threads(min(8, os.cpu_count() or 1))
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "oracle")):

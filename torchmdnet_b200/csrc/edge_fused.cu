@@ -287,8 +287,11 @@ __global__ void __launch_bounds__(256, 2) mp_pair_bwd_kernel(CIrr Y, CIrr dM, co
     // ---- pass 2: canonical pairs (j <= b; rows are sorted so they come first): dE/dr_p.  Per-lane partials of up to 32
     // pairs are parked in shared memory ([pair][lane], padded) and reduced by a transposed read: no shuffle chains.
     if (fp) {
-      int kc = k0;
-      while (kc < k1 && nbr_j[kc] <= b) ++kc;  // canonical slots are [k0, kc)
+      int kc = 0;   // canonical slots are [k0, k0 + #{j <= b}) because the row is sorted by j
+      for (int k = k0 + lane; k < k1; k += 32) kc += (nbr_j[k] <= b) ? 1 : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) kc += __shfl_xor_sync(0xffffffffu, kc, o);
+      kc += k0;
       for (int kb = k0; kb < kc; kb += 32) {
         const int ne = min(32, kc - kb);
         for (int e = 0; e < ne; ++e) {
