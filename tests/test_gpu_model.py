@@ -142,3 +142,25 @@ def test_multi_molecule_batch_and_permutation():
         yk, fk = m(z[sel].to(dev), pos[sel].to(dev), torch.zeros(int(sel.sum()), dtype=torch.long, device=dev))
         assert abs(yk.item() - y[k].item()) < 1e-4 * max(1, abs(y[k].item()))
         assert (fk - f[sel.to(dev)]).abs().max() < 1e-4 * f.abs().max()
+
+
+def test_cuda_graph_force_field():
+    """reference tests/test_model.py:161-204 (test_cuda_graph_compatible): the whole model replays from a CUDA graph."""
+    from torchmdnet_b200.calculators import CUDAGraphForceField
+    fx = torch.load(os.path.join(GOLDEN, "box300_tensornet_L2.pt"), weights_only=False)
+    hp = dict(fx["hparams"]); hp["static_shapes"] = True
+    m = seeded_model(hp, fx["weight_seed"]).eval().to(dev)
+    for p_ in m.parameters():
+        p_.requires_grad_(False)
+    ff = CUDAGraphForceField(m, fx["z"].to(dev), fx["batch"].to(dev), box=fx["box"].to(dev), num_systems=1)
+    pos = fx["pos"].to(dev)
+    e, f = ff(pos)
+    torch.cuda.synchronize()
+    assert rel(e, fx["ref_E64"]) < TOL and relF(f, fx["ref_F64"]) < TOL
+    # new positions through the same graph == eager evaluation
+    pos2 = pos + 0.05 * torch.randn_like(pos)
+    e2, f2 = ff(pos2)
+    e2, f2 = e2.clone(), f2.clone()
+    y, g = m(fx["z"].to(dev), pos2.clone(), fx["batch"].to(dev), box=fx["box"].to(dev), num_systems=1)
+    assert rel(e2, y.double().cpu()) < 1e-6 and relF(f2, g.double().cpu()) < 1e-5
+    assert abs(e2.item() - e.item()) > 1e-6
