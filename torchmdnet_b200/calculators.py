@@ -48,7 +48,8 @@ class CUDAGraphForceField:
         return y, f
 
     def capture(self, pos: Tensor):
-        self.pos.copy_(pos)
+        with torch.no_grad():
+            self.pos.copy_(pos)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -64,6 +65,7 @@ class CUDAGraphForceField:
     def __call__(self, pos: Tensor) -> Tuple[Tensor, Tensor]:
         if self.graph is None:
             self.capture(pos)
-        self.pos.copy_(pos, non_blocking=True)
+        with torch.no_grad():
+            self.pos.copy_(pos, non_blocking=True)
         self.graph.replay()
         return self.energy, self.forces
