@@ -155,6 +155,7 @@ def test_cuda_graph_force_field():
     ff = CUDAGraphForceField(m, fx["z"].to(dev), fx["batch"].to(dev), box=fx["box"].to(dev), num_systems=1)
     pos = fx["pos"].to(dev)
     e, f = ff(pos)
+    e, f = e.clone(), f.clone()  # the graph's outputs are static buffers, overwritten by the next replay
     torch.cuda.synchronize()
     assert rel(e, fx["ref_E64"]) < TOL and relF(f, fx["ref_F64"]) < TOL
     # new positions through the same graph == eager evaluation

@@ -18,6 +18,7 @@
 //                                  (+ cutoff on the last layer), re-split to (hi, lo) or final fp32 f / f' to HBM;
 //                                  double-buffered accumulator (2 x 256 columns) overlaps it with the next item's MMAs
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -396,6 +397,10 @@ static int make_map(CUtensorMap* m, const float* base, int rows, int K, int box_
 }
 
 static int pick_bn(int N) {
+  // TMD_TC_BN (dev knob): preferred n-block; default = the widest of 256/192/128/64 that divides N
+  static int pref = -1;
+  if (pref < 0) { const char* e = getenv("TMD_TC_BN"); pref = e ? atoi(e) : 0; }
+  if (pref > 0 && pref <= 256 && pref % 16 == 0 && N % pref == 0) return pref;
   const int cands[] = {256, 192, 128, 64};
   for (int c : cands) if (N % c == 0) return c;
   return 0;
