@@ -1,10 +1,8 @@
 // a6 (+ the radial projections of a5) on the 5th-generation tensor cores: tcgen05 / TMEM / TMA.
 //
 // The radial chain  rbf(r) -> [Linear -> SiLU] x L -> (x cutoff)  with its d/dr tangent is evaluated for every
-// unordered atom pair as a sequence of GEMMs.  A tile is 128 pairs; its operand block holds the 128 VALUE rows followed
-// by the 128 TANGENT rows ([256, K] per tile), and the two halves are multiplied by the same weight tile into two TMEM
-// accumulators side by side (D_v | D_t), so the epilogue thread that owns pair m reads z and dz/dr of the same column
-// from its own TMEM lane -- the activation derivative needs no cross-lane traffic.
+// unordered atom pair as a sequence of GEMMs  D[2P, N] = A[2P, K] . W[N, K]^T  (row 2p = value of pair p, row 2p+1 =
+// its tangent, so the activation derivative needs only a lane^1 shuffle in the epilogue).
 //
 // fp32 parity (energies/forces to 1e-4 relative, reference noise ~3e-6) rules out single-pass TF32 (1e-3).  Each
 // operand is split into two TF32 terms, x = hi + lo (cvt.rna.tf32), and D accumulates lo.hi + hi.lo + hi.hi in the
@@ -12,15 +10,13 @@
 // peak, still ~5x the fp32 FFMA roofline.  The previous layer's epilogue writes its output already split (hi, lo),
 // so operands go HBM -> TMA (SWIZZLE_128B) -> SMEM -> tensor core with no conversion pass.
 //
-// Kernel anatomy (one CTA per SM, persistent over (m_tile, n_block) work items, 576 threads):
-//   warp 0      : TMA producer   - A_hi/A_lo [256 x 32] (value|tangent rows) and W_hi/W_lo [BN x 32] fp32 boxes per
-//                                  K-block into a 2-stage mbarrier ring
-//   warp 1      : MMA issuer     - allocates 512 TMEM columns; one elected lane issues 24 tcgen05.mma per K-block
-//                                  (4 K-steps of 8 x 3 split terms x {value, tangent}), tcgen05.commit frees the SMEM
-//                                  stage / publishes the accumulator pair
-//   warps 2..17 : epilogue       - tcgen05.ld 32x32b.x32 of z and t (thread = TMEM lane = pair), bias + SiLU + tangent
+// Kernel anatomy (one CTA per SM, persistent over (m_tile, n_block) work items, 192 threads):
+//   warp 0      : TMA producer   - A_hi/A_lo [128 x 32] and W_hi/W_lo [BN x 32] fp32 boxes per K-block, mbarrier ring
+//   warp 1      : MMA issuer     - allocates 512 TMEM columns, one elected lane issues 12 tcgen05.mma per K-block
+//                                  (4 K-steps of 8 x 3 split terms), tcgen05.commit frees the SMEM stage / publishes D
+//   warps 2..17 : epilogue       - tcgen05.ld 32x32b.x32 (thread = TMEM lane = output row), bias + SiLU + tangent
 //                                  (+ cutoff on the last layer), re-split to (hi, lo) or final fp32 f / f' to HBM;
-//                                  double-buffered accumulators overlap it with the next item's MMAs
+//                                  double-buffered accumulator (2 x 256 columns) overlaps it with the next item's MMAs
 #include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -115,8 +111,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -150,20 +146,17 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-B aligned operand ring
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const bool jvp = P.rows_per_pair == 2;
-  const int rows_per_tile = jvp ? 2 * BM : BM;          // [value rows | tangent rows]
-  const int a_tile_bytes = rows_per_tile * BK * 4;      // one of (hi, lo)
   const int b_tile_bytes = P.BN * BK * 4;
-  const int stage_bytes = 2 * a_tile_bytes + 2 * b_tile_bytes;
-  const int acc_stride = jvp ? 2 * P.BN : P.BN;         // TMEM columns of one accumulator stage (D_v | D_t)
+  const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[MAX_N];
   for (int i = threadIdx.x; i < P.N; i += TC_THREADS) bias_s[i] = P.bias[i];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_pairs = P.num_unique ? min(*P.num_unique, P.max_pairs) : P.max_pairs;
-  const int m_tiles = (n_pairs + BM - 1) / BM;
+  const int n_pairs = min(*P.num_unique, P.max_pairs);
+  const int rows_valid = n_pairs * P.rows_per_pair;
+  const int m_tiles = (rows_valid + BM - 1) / BM;
   const int n_blks = P.N / P.BN;
   const int total_items = m_tiles * n_blks;
   const int k_blocks = P.K / BK;
@@ -192,10 +185,10 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + (size_t)stage * stage_bytes;
           mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-          tma_load_2d(&map_a_hi, &full_bar[stage], st, kb * BK, m_tile * rows_per_tile);
-          tma_load_2d(&map_a_lo, &full_bar[stage], st + a_tile_bytes, kb * BK, m_tile * rows_per_tile);
-          tma_load_2d(&map_b_hi, &full_bar[stage], st + 2 * a_tile_bytes, kb * BK, n_blk * P.BN);
-          tma_load_2d(&map_b_lo, &full_bar[stage], st + 2 * a_tile_bytes + b_tile_bytes, kb * BK, n_blk * P.BN);
+          tma_load_2d(&map_a_hi, &full_bar[stage], st, kb * BK, m_tile * BM);
+          tma_load_2d(&map_a_lo, &full_bar[stage], st + A_TILE_BYTES, kb * BK, m_tile * BM);
+          tma_load_2d(&map_b_hi, &full_bar[stage], st + 2 * A_TILE_BYTES, kb * BK, n_blk * P.BN);
+          tma_load_2d(&map_b_lo, &full_bar[stage], st + 2 * A_TILE_BYTES + b_tile_bytes, kb * BK, n_blk * P.BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -207,28 +200,20 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
       tcgen05_fence_after();
-      const uint32_t d_v = tmem_base + (uint32_t)(acc * acc_stride);
-      const uint32_t d_t = d_v + (uint32_t)P.BN;
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + a_tile_bytes);
-          const uint64_t b_hi = make_desc_sw128(st + 2 * a_tile_bytes), b_lo = make_desc_sw128(st + 2 * a_tile_bytes + b_tile_bytes);
-          const uint64_t t_off = (uint64_t)(A_TILE_BYTES >> 4);  // tangent rows start 128 rows = 16 KB further
+          const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + A_TILE_BYTES);
+          const uint64_t b_hi = make_desc_sw128(st + 2 * A_TILE_BYTES), b_lo = make_desc_sw128(st + 2 * A_TILE_BYTES + b_tile_bytes);
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
             const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 8 tf32 = 32 B per K-step inside the 128 B swizzle row
-            const uint32_t accum = (kb | k) != 0;
-            umma_tf32(d_v, a_lo + adv, b_hi + adv, idesc, accum);
-            umma_tf32(d_v, a_hi + adv, b_lo + adv, idesc, 1);
-            umma_tf32(d_v, a_hi + adv, b_hi + adv, idesc, 1);
-            if (jvp) {
-              umma_tf32(d_t, a_lo + t_off + adv, b_hi + adv, idesc, accum);
-              umma_tf32(d_t, a_hi + t_off + adv, b_lo + adv, idesc, 1);
-              umma_tf32(d_t, a_hi + t_off + adv, b_hi + adv, idesc, 1);
-            }
+            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
           }
         }
         __syncwarp();
@@ -236,20 +221,26 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (elect_one()) umma_commit(&tmem_full_bar[acc]);         // accumulators complete -> epilogue
+      if (elect_one()) umma_commit(&tmem_full_bar[acc]);         // accumulator complete -> epilogue
       __syncwarp();
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..17; TMEM lane quarter = warp & 3)
+    // jvp: lanes (2m, 2m+1) hold the value / tangent rows of pair m.  They swap halves of the 32-column chunk so that
+    // each lane evaluates the activation ONCE for 16 columns and produces both h and dh for them.
     const int q = warp & 3;
     const int sub = (warp - 2) >> 2;  // which of the round-robin 32-column chunks this warp drains
-    const int pair_in_tile = q * 32 + lane;
+    const int row_in_tile = q * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
+    const bool jvp = P.rows_per_pair == 2;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int m_tile = item / n_blks, n_blk = item - m_tile * n_blks;
-      const int pair = m_tile * BM + pair_in_tile;
-      const bool valid = pair < n_pairs;
+      const int row = m_tile * BM + row_in_tile;
+      const bool tangent = jvp && (row & 1);
+      const int row_v = jvp ? (row & ~1) : row;          // the value row of this lane's pair
+      const bool valid = row_v < rows_valid;
+      const int pair = jvp ? (row >> 1) : row;
       float cut = 1.f, dcut = 0.f;
       if (P.final_layer && P.mul_cutoff) {
         const float r = valid ? __ldg(P.pair_r + pair) : 0.f;
@@ -257,57 +248,80 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride);
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
       for (int c0 = sub * 32; c0 < P.BN; c0 += 32 * (EPI_WARPS / 4)) {
-        uint32_t v[32], t[32];
+        uint32_t v[32];
         tmem_ld32(t_row + (uint32_t)c0, v);
-        if (jvp) tmem_ld32(t_row + (uint32_t)(P.BN + c0), t);
-        tmem_ld_wait();
         const int col0 = n_blk * P.BN + c0;
-        float* h = reinterpret_cast<float*>(v);   // results overwrite the accumulator registers in place
-        float* dh = reinterpret_cast<float*>(t);
+        if (jvp) {
+          const int cb = col0 + (tangent ? 16 : 0);        // this lane's 16 columns
+          float h[16], dh[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float z = __uint_as_float(v[i]) + bias_s[col0 + i];
-          float hh = z, dd = jvp ? __uint_as_float(t[i]) : 0.f;
-          if (P.act) {
-            // sigmoid on the SFU (ex2 + rcp): ~1e-7 relative, far inside the 3xTF32 error budget
-            const float sg = __fdividef(1.f, 1.f + __expf(-z));
-            hh = z * sg;
-            if (jvp) dd = sg * fmaf(z, 1.f - sg, 1.f) * dd;
+          for (int i = 0; i < 16; ++i) {
+            const float send = __uint_as_float(tangent ? v[i] : v[16 + i]);
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            const float z = (tangent ? recv : __uint_as_float(v[i])) + bias_s[cb + i];
+            const float t = tangent ? __uint_as_float(v[16 + i]) : recv;
+            float hh = z, dd = t;
+            if (P.act) {
+              // sigmoid on the SFU (ex2 + rcp): ~1e-7 relative, far inside the 3xTF32 error budget
+              const float sg = __fdividef(1.f, 1.f + __expf(-z));
+              hh = z * sg;
+              dd = sg * fmaf(z, 1.f - sg, 1.f) * t;
+            }
+            if (P.final_layer && P.mul_cutoff) { dd = fmaf(dd, cut, hh * dcut); hh *= cut; }
+            h[i] = hh; dh[i] = dd;
           }
-          if (P.final_layer && P.mul_cutoff) { if (jvp) dd = fmaf(dd, cut, hh * dcut); hh *= cut; }
-          h[i] = hh; dh[i] = dd;
-        }
-        if (valid) {
-          if (P.final_layer) {
-            float* d0 = P.out_f + (size_t)pair * P.N + col0;
+          if (valid) {
+            if (P.final_layer) {
+              float* d0 = P.out_f + (size_t)pair * P.N + cb;
+              float* d1 = P.out_fp + (size_t)pair * P.N + cb;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) st4(d0 + i, make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]));
-            if (jvp) {
-              float* d1 = P.out_fp + (size_t)pair * P.N + col0;
+              for (int i = 0; i < 16; i += 4) {
+                st4(d0 + i, make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]));
+                st4(d1 + i, make_float4(dh[i], dh[i + 1], dh[i + 2], dh[i + 3]));
+              }
+            } else {
+              const size_t o0 = (size_t)row_v * P.N + cb, o1 = o0 + P.N;
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) st4(d1 + i, make_float4(dh[i], dh[i + 1], dh[i + 2], dh[i + 3]));
+              for (int i = 0; i < 16; i += 4) {
+                float a[4], b[4], c[4], d[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  a[u] = tf32_rna(h[i + u]);  b[u] = tf32_rna(h[i + u] - a[u]);
+                  c[u] = tf32_rna(dh[i + u]); d[u] = tf32_rna(dh[i + u] - c[u]);
+                }
+                st4(P.out_hi + o0 + i, make_float4(a[0], a[1], a[2], a[3]));
+                st4(P.out_lo + o0 + i, make_float4(b[0], b[1], b[2], b[3]));
+                st4(P.out_hi + o1 + i, make_float4(c[0], c[1], c[2], c[3]));
+                st4(P.out_lo + o1 + i, make_float4(d[0], d[1], d[2], d[3]));
+              }
             }
-          } else {
-            const size_t o0 = ((size_t)m_tile * rows_per_tile + pair_in_tile) * P.N + col0;  // value row of this pair
+          }
+        } else {
+          float o[32];
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float a[4], b[4];
+          for (int i = 0; i < 32; ++i) {
+            const float z = __uint_as_float(v[i]) + bias_s[col0 + i];
+            float res = P.act ? z * __fdividef(1.f, 1.f + __expf(-z)) : z;
+            if (P.final_layer && P.mul_cutoff) res *= cut;
+            o[i] = res;
+          }
+          if (valid) {
+            if (P.final_layer) {
+              float* dst = P.out_f + (size_t)pair * P.N + col0;
 #pragma unroll
-              for (int u = 0; u < 4; ++u) { a[u] = tf32_rna(h[i + u]); b[u] = tf32_rna(h[i + u] - a[u]); }
-              st4(P.out_hi + o0 + i, make_float4(a[0], a[1], a[2], a[3]));
-              st4(P.out_lo + o0 + i, make_float4(b[0], b[1], b[2], b[3]));
-            }
-            if (jvp) {
-              const size_t o1 = o0 + (size_t)BM * P.N;                                       // its tangent row
+              for (int i = 0; i < 32; i += 4) st4(dst + i, make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]));
+            } else {
+              float* dhp = P.out_hi + (size_t)row * P.N + col0;
+              float* dlp = P.out_lo + (size_t)row * P.N + col0;
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
-                float a[4], b[4];
+                float hi4[4], lo4[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { a[u] = tf32_rna(dh[i + u]); b[u] = tf32_rna(dh[i + u] - a[u]); }
-                st4(P.out_hi + o1 + i, make_float4(a[0], a[1], a[2], a[3]));
-                st4(P.out_lo + o1 + i, make_float4(b[0], b[1], b[2], b[3]));
+                for (int u = 0; u < 4; ++u) { hi4[u] = tf32_rna(o[i + u]); lo4[u] = tf32_rna(o[i + u] - hi4[u]); }
+                st4(dhp + i, make_float4(hi4[0], hi4[1], hi4[2], hi4[3]));
+                st4(dlp + i, make_float4(lo4[0], lo4[1], lo4[2], lo4[3]));
               }
             }
           }
@@ -328,8 +342,7 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   }
 }
 
-// layer-0 operand in the tile-block layout: tile m = pairs [128m, 128m+128): value rows first, tangent rows after
-// (rows_per_pair == 2), each (rbf(r_p) | d rbf/dr) split into (hi, lo), K padded to K_pad with zeros
+// layer-0 operand: rows (2p, 2p+1) = (rbf(r_p), d rbf/dr) split into (hi, lo), K padded to K_pad with zeros
 __global__ void pair_rbf_split_kernel(const float* __restrict__ pair_r, const int* __restrict__ num_unique, int max_pairs,
                                       int R, int K_pad, int rows_per_pair, const float* __restrict__ means,
                                       const float* __restrict__ betas, float alpha, float lo, float hi,
@@ -346,10 +359,10 @@ __global__ void pair_rbf_split_kernel(const float* __restrict__ pair_r, const in
       const float u = expf(alpha * (lo - r));
       tn::expnorm_rbf(u, alpha, c0, dc0, means[k], betas[k], &v, &dv);
     }
-    const size_t r0 = ((size_t)(p / BM) * (rows_per_pair * BM) + (p % BM)) * K_pad + k;
+    const size_t r0 = (size_t)p * rows_per_pair * K_pad + k;
     float h = tf32_rna(v);
     a_hi[r0] = h; a_lo[r0] = tf32_rna(v - h);
-    if (rows_per_pair == 2) { h = tf32_rna(dv); a_hi[r0 + (size_t)BM * K_pad] = h; a_lo[r0 + (size_t)BM * K_pad] = tf32_rna(dv - h); }
+    if (rows_per_pair == 2) { h = tf32_rna(dv); a_hi[r0 + K_pad] = h; a_lo[r0 + K_pad] = tf32_rna(dv - h); }
   }
 }
 
@@ -383,14 +396,13 @@ static int make_map(CUtensorMap* m, const float* base, int rows, int K, int box_
   return TMD_OK;
 }
 
-static int pick_bn(int N, bool jvp) {
+static int pick_bn(int N) {
   // TMD_TC_BN (dev knob): preferred n-block; default = the widest of 256/192/128/64 that divides N
   static int pref = -1;
   if (pref < 0) { const char* e = getenv("TMD_TC_BN"); pref = e ? atoi(e) : 0; }
-  const int cap = jvp ? 128 : 256;  // two accumulator stages of (D_v | D_t) must fit the 512 TMEM columns
-  if (pref > 0 && pref <= cap && pref % 16 == 0 && N % pref == 0) return pref;
+  if (pref > 0 && pref <= 256 && pref % 16 == 0 && N % pref == 0) return pref;
   const int cands[] = {256, 192, 128, 64};
-  for (int c : cands) if (c <= cap && N % c == 0) return c;
+  for (int c : cands) if (N % c == 0) return c;
   return 0;
 }
 
@@ -403,7 +415,7 @@ extern "C" {
 //   dims = {R, N_0, N_1, N_2}; hidden widths must be multiples of 32, every N_l a multiple of 64
 //   rbf_hi/rbf_lo    : optional layer-0 operand from tmd_pair_rbf_split (shared by all chains of a frame), else NULL
 //   act_a_hi/lo, act_b_hi/lo : ping-pong workspaces, each >= rows_pad * max(K_l_pad) floats where
-//                              rows_pad = roundup(max_pairs, 128) * (out_fp ? 2 : 1)
+//                              rows_pad = roundup(max_pairs * (out_fp ? 2 : 1), 128)
 int tmd_pair_rbf_split(const float* pair_r, const int* num_unique, int max_pairs, int R, int rows_per_pair,
                        const float* means, const float* betas, double alpha, double lo, double hi, float* a_hi,
                        float* a_lo, void* stream) {
@@ -429,7 +441,7 @@ int tmd_pair_chain_tc(const float* pair_r, const int* num_unique, int max_pairs,
   if (max_pairs == 0) return TMD_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int rpp = out_fp ? 2 : 1;
-  const int rows_pad = ((max_pairs + BM - 1) / BM) * BM * rpp;   // tile-block layout: 128 (x2) rows per 128 pairs
+  const int rows_pad = ((max_pairs * rpp + BM - 1) / BM) * BM;
   const int R = dims[0];
   const int K0 = ((R + BK - 1) / BK) * BK;
   if (!rbf_hi) {  // layer-0 operand not precomputed by tmd_pair_rbf_split: build it into workspace A
@@ -444,22 +456,22 @@ int tmd_pair_chain_tc(const float* pair_r, const int* num_unique, int max_pairs,
   int K = K0;
   for (int l = 0; l < n_layers; ++l) {
     const int N = dims[l + 1];
-    const int BN = pick_bn(N, rpp == 2);
+    const int BN = pick_bn(N);
     TMD_REQUIRE(BN > 0, "pair_chain_tc: layer widths must be multiples of 64");
     TMD_REQUIRE(l == n_layers - 1 || N % BK == 0, "pair_chain_tc: hidden widths must be multiples of 32");
     TMD_REQUIRE(N <= MAX_N, "pair_chain_tc: layer wider than 1024");
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
-    if ((rc = make_map(&ma_hi, in_hi, rows_pad, K, BM * rpp))) return rc;
-    if ((rc = make_map(&ma_lo, in_lo, rows_pad, K, BM * rpp))) return rc;
+    if ((rc = make_map(&ma_hi, in_hi, rows_pad, K, BM))) return rc;
+    if ((rc = make_map(&ma_lo, in_lo, rows_pad, K, BM))) return rc;
     if ((rc = make_map(&mb_hi, W_hi[l], N, K, BN))) return rc;
     if ((rc = make_map(&mb_lo, W_lo[l], N, K, BN))) return rc;
     GemmParams P;
     P.K = K; P.N = N; P.BN = BN; P.rows_per_pair = rpp; P.act = act; P.final_layer = (l == n_layers - 1);
     P.mul_cutoff = mul_cutoff; P.lo = (float)lo; P.hi = (float)hi; P.bias = bias[l]; P.pair_r = pair_r;
     P.num_unique = num_unique; P.max_pairs = max_pairs; P.out_hi = o_hi; P.out_lo = o_lo; P.out_f = out_f; P.out_fp = out_fp;
-    const int stage_bytes = 2 * A_TILE_BYTES * rpp + 2 * BN * BK * 4;
-    const int max_items = ((max_pairs + BM - 1) / BM) * (N / BN);
+    const int stage_bytes = 2 * A_TILE_BYTES + 2 * BN * BK * 4;
+    const int max_items = (rows_pad / BM) * (N / BN);
     const int grid = max_items < 148 ? max_items : 148;
     if (stage_bytes * 3 + 1024 <= 200 * 1024) {
       const int smem = stage_bytes * 3 + 1024;

@@ -132,7 +132,7 @@ def precompute_rbf(pair_r: Tensor, num_unique: Tensor, rbf_mod, lo: float, hi: f
         return None
     rpp = 2 if want_tangent else 1
     R = rbf_mod.means.shape[0]
-    rows_pad = -(-P // 128) * 128 * rpp   # tile-block layout: [128 value rows | 128 tangent rows] per 128 pairs
+    rows_pad = -(-(P * rpp) // 128) * 128
     K0 = -(-R // 32) * 32
     buf = torch.empty(2, rows_pad, K0, device=pair_r.device, dtype=torch.float32)
     _lib.call("tmd_pair_rbf_split", p(pair_r), p(num_unique), P, R, rpp, p(rbf_mod.means.detach()), p(rbf_mod.betas.detach()),
@@ -150,7 +150,7 @@ def run_chain(chain: RadialChain, pair_r: Tensor, num_unique: Tensor, rbf_mod, l
     fp = torch.empty_like(f) if want_tangent else None
     if USE_TENSOR_CORES and chain.supported_tc() and P > 0:
         his, los, p_hi, p_lo, p_b = chain.tc_tensors()
-        rows_pad = -(-P // 128) * 128 * (2 if want_tangent else 1)
+        rows_pad = -(-(P * (2 if want_tangent else 1)) // 128) * 128
         width = max([his[0].shape[1]] + [w.shape[1] for w in wt[:-1]])
         ws = torch.empty(4, rows_pad, width, device=pair_r.device, dtype=torch.float32)
         if rbf_op is not None and rbf_op.rows_per_pair != (2 if want_tangent else 1):
