@@ -113,6 +113,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// 256-bit global store (STG.E.256 on sm_100a): one full 32-byte sector per lane and instruction
+__device__ __forceinline__ void st8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -276,25 +281,20 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             if (P.final_layer) {
               float* d0 = P.out_f + (size_t)pair * P.N + cb;
               float* d1 = P.out_fp + (size_t)pair * P.N + cb;
-#pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                st4(d0 + i, make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]));
-                st4(d1 + i, make_float4(dh[i], dh[i + 1], dh[i + 2], dh[i + 3]));
-              }
+              st8(d0, h); st8(d0 + 8, h + 8);
+              st8(d1, dh); st8(d1 + 8, dh + 8);
             } else {
               const size_t o0 = (size_t)row_v * P.N + cb, o1 = o0 + P.N;
 #pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                float a[4], b[4], c[4], d[4];
+              for (int i = 0; i < 16; i += 8) {
+                float a[8], b[8], c[8], d[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 8; ++u) {
                   a[u] = tf32_rna(h[i + u]);  b[u] = tf32_rna(h[i + u] - a[u]);
                   c[u] = tf32_rna(dh[i + u]); d[u] = tf32_rna(dh[i + u] - c[u]);
                 }
-                st4(P.out_hi + o0 + i, make_float4(a[0], a[1], a[2], a[3]));
-                st4(P.out_lo + o0 + i, make_float4(b[0], b[1], b[2], b[3]));
-                st4(P.out_hi + o1 + i, make_float4(c[0], c[1], c[2], c[3]));
-                st4(P.out_lo + o1 + i, make_float4(d[0], d[1], d[2], d[3]));
+                st8(P.out_hi + o0 + i, a); st8(P.out_lo + o0 + i, b);
+                st8(P.out_hi + o1 + i, c); st8(P.out_lo + o1 + i, d);
               }
             }
           }
