@@ -49,6 +49,14 @@ def workload(name, seed=0):
         hp = systems.tensornet_hparams(num_layers=2, F=128, R=32, cutoff=5.0, max_nb=128)
         z, pos, batch, box = systems.random_box(1000, seed=seed)
         desc = "C2: TensorNet 2-layer F=128 R=32 rc=5.0, 1000-atom random periodic box L=21.54A, energy+forces"
+    elif name == "c3":
+        hp = systems.et_hparams()
+        z, pos, batch, box = systems.molecule_batch(n_mol=256, seed=seed)
+        desc = "C3: ET-SPICE (5 layers, F=128, H=8, R=64, rc=10), 256 molecules x 20-40 atoms, energy+forces"
+    elif name == "c5":
+        hp = systems.tensornet_hparams(num_layers=2, F=128, R=32, cutoff=5.0, max_nb=128)
+        z, pos, batch, box = systems.random_box(5000, seed=seed, n_boxes=8)
+        desc = "C5 (per GPU): TensorNet-ANI2X config (2 layers, F=128), 8 x 5000-atom periodic boxes, energy+forces"
     else:
         raise ValueError(name)
     return hp, z, pos, batch, box, desc
@@ -162,7 +170,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c4", choices=["c4", "c2"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch the ~250 kernels of a frame from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
@@ -189,11 +197,13 @@ def main():
     _lib.library()  # fail loudly if the extension is missing
 
     hp, z, pos, batch, box, desc = workload(args.workload, seed=rank)
-    hp["static_shapes"] = not args.eager   # capacity-sized buffers + device counters: the frame is CUDA-graph capturable
+    hp["static_shapes"] = (not args.eager) and hp["model"] == "tensornet"   # capacity-sized buffers + device counters: the frame is CUDA-graph capturable
     model = seeded_model(hp).to(dev)
     for p_ in model.parameters():
         p_.requires_grad_(False)
-    zd, bd, boxd = z.to(dev), batch.to(dev), box.to(dev)
+    zd, bd, boxd = z.to(dev), batch.to(dev), (None if box is None else box.to(dev))
+    n_sys = int(batch.max()) + 1
+    is_tn = hp["model"] == "tensornet"
     pos_d = pos.to(dev)
 
     def barrier():
@@ -202,12 +212,12 @@ def main():
         torch.cuda.synchronize()
 
     ff = None
-    if not args.eager:
+    if not args.eager and is_tn:  # (the ET module reads the pair counter on the host: eager only)
         from torchmdnet_b200.calculators import CUDAGraphForceField
-        ff = CUDAGraphForceField(model, zd, bd, box=boxd, num_systems=1).capture(pos_d)
+        ff = CUDAGraphForceField(model, zd, bd, box=boxd, num_systems=n_sys).capture(pos_d)
 
     def frame(p):
-        y, f = ff(p) if ff is not None else model(zd, p, bd, box=boxd, num_systems=1)
+        y, f = ff(p) if ff is not None else model(zd, p, bd, box=boxd, num_systems=n_sys)
         if dist_on:  # the single collective of the path: total energy over all boxes
             tot = y.sum()
             dist.all_reduce(tot)
@@ -218,7 +228,7 @@ def main():
     barrier()
     launches_per_frame = None
     if ff is not None:  # count this library's launches in one frame with an eager evaluation (the graph replays the same nodes)
-        l_a = _lib.launches(); model(zd, pos_d.clone(), bd, box=boxd, num_systems=1); launches_per_frame = _lib.launches() - l_a
+        l_a = _lib.launches(); model(zd, pos_d.clone(), bd, box=boxd, num_systems=n_sys); launches_per_frame = _lib.launches() - l_a
         barrier()
     l0 = _lib.launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -238,9 +248,9 @@ def main():
 
     # ---- e2e: host buffers, H2D of the inputs + D2H of energy and forces inside the timed region ----
     pin = lambda x: x.clone().pin_memory()
-    h_z, h_pos, h_batch, h_box = pin(z), pin(pos), pin(batch), pin(box)
+    h_z, h_pos, h_batch, h_box = pin(z), pin(pos), pin(batch), pin(box if box is not None else torch.zeros(3, 3))
     h_f = torch.empty(pos.shape, dtype=torch.float32).pin_memory()
-    h_e = torch.empty(1, 1, dtype=torch.float32).pin_memory()
+    h_e = torch.empty(n_sys, 1, dtype=torch.float32).pin_memory()
     h2d = sum(x.numel() * x.element_size() for x in (h_z, h_pos, h_batch, h_box))
     d2h = h_f.numel() * 4 + h_e.numel() * 4
 
@@ -269,67 +279,73 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant hand-written kernel: the tcgen05 radial chain of one interaction layer (a6) ----
-    from torchmdnet_b200.extensions import tensornet_ops as ops
-    from torchmdnet_b200.extensions import fused
-    rep = model.representation_model
-    g = rep.distance.graph(pos_d, bd, boxd)
-    pidx = fused.build_pair_index(g)
-    E, Pn = torch.cat([g.num_pairs, pidx.num_unique]).tolist()
-    N = z.numel(); F = hp["embedding_dimension"]; R = hp["num_rbf"]
-    pair_r = pidx.pair_r[:Pn].contiguous()
-    chain = rep.layers[0].radial_chain()
-    run = lambda: fused.run_chain(chain, pair_r, pidx.num_unique, rep.distance_expansion, 0.0, hp["cutoff_upper"], True)
-    for _ in range(3):
-        run()
-    torch.cuda.synchronize()
-    reps = 10
-    ev0.record()
-    for _ in range(reps):
-        run()
-    ev1.record(); torch.cuda.synchronize()
-    c_ms = ev0.elapsed_time(ev1) / reps
-    hbm_peak, tc_peak, how = measured_peaks()
-    # algorithmic flops of one chain call: value + d/dr rows (2 per pair) through R->F->2F->3F (2(RF+2F^2+6F^2)
-    # = 270 336 flop per evaluated row at F=128, R=32); the 3xTF32 split executes 3x this on the tensor pipe
-    flops = 2 * Pn * 2 * (R * F + F * 2 * F + 2 * F * 3 * F)
-    ach_tf = flops / (c_ms * 1e-3) / 1e12
-    roofline = {"kernel": "gemm3x_tf32_kernel x3 (+ pair_rbf_split): tcgen05 radial chain of one interaction layer, value + d/dr on unique pairs",
-                "bound": "tensor", "achieved": ach_tf, "peak": tc_peak, "peak_source": how + " dense bf16 burst", "unit": "TFLOP/s",
-                "frac": ach_tf / tc_peak, "frac_of_3xtf32_ceiling": ach_tf / (tc_peak / 6.0),
-                "note": "fp32-parity path: TF32 runs at 1/2 the bf16 rate and each product needs 3 split MMAs, so the ceiling for this kernel is peak/6",
-                "traffic": 4.257e9, "traffic_source": "ncu --set full r01 (dram read+write summed over the 3 GEMM launches of one chain call, profiles/r01_gemm3x_ncu.md)",
-                "algorithmic_flops": flops, "kernel_ms": c_ms, "pairs": Pn}
-    # ---- secondary: interaction message passing forward (a7), HBM/L2-gather bound ----
-    I_, A_, S_ = (torch.randn(N, k, F, device=dev) for k in (1, 3, 5))
-    w = torch.randn(E, 3, F, device=dev)
-    for _ in range(3):
-        ops.fn_message_passing(I_, A_, S_, w, None, g.nbr_j, g.indptr, g.rev, g.nbr_j, g.indptr)
-    torch.cuda.synchronize()
-    ev0.record()
-    for _ in range(reps):
-        ops.fn_message_passing(I_, A_, S_, w, None, g.nbr_j, g.indptr, g.rev, g.nbr_j, g.indptr)
-    ev1.record(); torch.cuda.synchronize()
-    k_ms = ev0.elapsed_time(ev1) / reps
-    alg_bytes = 4 * (3 * E * F + 2 * 9 * N * F) + 4 * (2 * E + N + 1)  # edge weights + node in/out + CSR
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    roofline2 = {"kernel": "mp_fwd_kernel (interaction message passing fwd, one layer)", "bound": "hbm", "achieved": achieved,
-                 "peak": hbm_peak, "peak_source": how, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                 "algorithmic_bytes": alg_bytes, "kernel_ms": k_ms, "edges": E}
+    roofline = roofline2 = None
+    N = z.numel()
+    if is_tn:
+        # ---- roofline of the dominant hand-written kernel: the tcgen05 radial chain of one interaction layer (a6) ----
+        from torchmdnet_b200.extensions import tensornet_ops as ops
+        from torchmdnet_b200.extensions import fused
+        rep = model.representation_model
+        g = rep.distance.graph(pos_d, bd, boxd)
+        pidx = fused.build_pair_index(g)
+        E, Pn = torch.cat([g.num_pairs, pidx.num_unique]).tolist()
+        N = z.numel(); F = hp["embedding_dimension"]; R = hp["num_rbf"]
+        pair_r = pidx.pair_r[:Pn].contiguous()
+        chain = rep.layers[0].radial_chain()
+        run = lambda: fused.run_chain(chain, pair_r, pidx.num_unique, rep.distance_expansion, 0.0, hp["cutoff_upper"], True)
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        reps = 10
+        ev0.record()
+        for _ in range(reps):
+            run()
+        ev1.record(); torch.cuda.synchronize()
+        c_ms = ev0.elapsed_time(ev1) / reps
+        hbm_peak, tc_peak, how = measured_peaks()
+        # algorithmic flops of one chain call: value + d/dr rows (2 per pair) through R->F->2F->3F (2(RF+2F^2+6F^2)
+        # = 270 336 flop per evaluated row at F=128, R=32); the 3xTF32 split executes 3x this on the tensor pipe
+        flops = 2 * Pn * 2 * (R * F + F * 2 * F + 2 * F * 3 * F)
+        ach_tf = flops / (c_ms * 1e-3) / 1e12
+        roofline = {"kernel": "gemm3x_tf32_kernel x3 (+ pair_rbf_split): tcgen05 radial chain of one interaction layer, value + d/dr on unique pairs",
+                    "bound": "tensor", "achieved": ach_tf, "peak": tc_peak, "peak_source": how + " dense bf16 burst", "unit": "TFLOP/s",
+                    "frac": ach_tf / tc_peak, "frac_of_3xtf32_ceiling": ach_tf / (tc_peak / 6.0),
+                    "note": "fp32-parity path: TF32 runs at 1/2 the bf16 rate and each product needs 3 split MMAs, so the ceiling for this kernel is peak/6",
+                    "traffic": 4.257e9, "traffic_source": "ncu --set full r01 (dram read+write summed over the 3 GEMM launches of one chain call, profiles/r01_gemm3x_ncu.md)",
+                    "algorithmic_flops": flops, "kernel_ms": c_ms, "pairs": Pn}
+        # ---- secondary: interaction message passing forward (a7), HBM/L2-gather bound ----
+        I_, A_, S_ = (torch.randn(N, k, F, device=dev) for k in (1, 3, 5))
+        w = torch.randn(E, 3, F, device=dev)
+        for _ in range(3):
+            ops.fn_message_passing(I_, A_, S_, w, None, g.nbr_j, g.indptr, g.rev, g.nbr_j, g.indptr)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(reps):
+            ops.fn_message_passing(I_, A_, S_, w, None, g.nbr_j, g.indptr, g.rev, g.nbr_j, g.indptr)
+        ev1.record(); torch.cuda.synchronize()
+        k_ms = ev0.elapsed_time(ev1) / reps
+        alg_bytes = 4 * (3 * E * F + 2 * 9 * N * F) + 4 * (2 * E + N + 1)  # edge weights + node in/out + CSR
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        roofline2 = {"kernel": "mp_fwd_kernel (interaction message passing fwd, one layer)", "bound": "hbm", "achieved": achieved,
+                     "peak": hbm_peak, "peak_source": how, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                     "algorithmic_bytes": alg_bytes, "kernel_ms": k_ms, "edges": E}
 
     cpu = None
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_side = 6 if args.workload == "c4" else 4
+        if not (is_tn and box is not None and box.dim() == 2):
+            raise SystemExit("cpu baseline sampling is defined for the single-box TensorNet workloads; use --no-cpu-baseline")
         fps, n_sample, tt, cores = cpu_oracle_frames_per_s(hp, n_side, 46.42 * n_side / 15, 2, cores, N)
         cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{n_sample}-atom sub-box of the same water system, {tt:.2f} s/frame on {cores} threads, scaled by atoms ratio"}
 
     value = world * args.steps / (ms * 1e-3)
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+    metric = METRIC if args.workload == "c4" else f"frames_per_sec_energy_forces_{args.workload}"
+    out = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic",
-           "config": {"workload": desc, "atoms_per_gpu": N, "edges_per_gpu": E, "boxes": world, "parallelism": f"dp{world} (one box per GPU, one scalar all-reduce)",
+           "config": {"workload": desc, "atoms_per_gpu": N, "edges_per_gpu": int(model.representation_model.distance.graph(pos_d, bd, boxd).num_pairs.item()), "boxes": world, "parallelism": f"dp{world} (one box per GPU, one scalar all-reduce)",
                       "l2": "per-frame working set ~4 GB >> 126 MB L2; no explicit flush",
                       "cuda_graph": ff is not None},
            "clocks": clocks.summary(),

@@ -64,7 +64,7 @@ def test_golden_energy_forces(name, path):
     m = build(fx)
     if fx["hparams"]["model"] == "tensornet":
         m.representation_model.fused_edge_path = None if path == "fused" else False
-        if path == "fused" and fx["hparams"]["embedding_dimension"] <= 128:
+        if path == "fused":
             assert m.representation_model._fused_path_ok()
     elif path == "composed":
         pytest.skip("single path")

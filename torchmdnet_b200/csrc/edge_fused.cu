@@ -509,7 +509,7 @@ int tmd_mp_pair_bwd(const float* YI, const float* YA, const float* YS, const flo
   if (n == 0) return TMD_OK;
   const int chunks = (F + 127) / 128;
   const size_t smem = (size_t)8 * 18 * chunks * 32 * sizeof(float4) + (size_t)8 * 32 * 33 * sizeof(float);
-  TMD_REQUIRE(smem <= 110 * 1024, "mp_pair_bwd: F too large for the per-warp staging buffer");
+  TMD_REQUIRE(smem <= 200 * 1024, "mp_pair_bwd: F too large for the per-warp staging buffer (F <= 256)");
   cudaFuncSetAttribute(mp_pair_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   mp_pair_bwd_kernel<<<tmd_blocks_for((long long)n * 32, 256), 256, smem, (cudaStream_t)stream>>>(
       CIrr{YI, YA, YS}, CIrr{dMI, dMA, dMS}, f, fp, pid, nbr_j, indptr, n, F, MIrr{dYI, dYA, dYS}, d_pair_r);

@@ -73,15 +73,19 @@ class RadialChain:
         self.layers, self.act, self.mul_cutoff = [list(l) for l in layers], act, mul_cutoff
         self._key, self._wt, self._b, self._dims = None, None, None, None
 
-    def supported(self) -> bool:
+    def supported_ffma(self) -> bool:
+        """fp32 CUDA-core chain kernel: widths % 32 == 0 and <= 384."""
         widths = [sum(m.out_features for m in l) for l in self.layers]
         R = self.layers[0][0].in_features
         return R % 4 == 0 and len(widths) <= 3 and all(w % 32 == 0 and w <= 384 for w in widths)
 
+    def supported(self) -> bool:
+        return (USE_TENSOR_CORES and self.supported_tc()) or self.supported_ffma()
+
     def supported_tc(self) -> bool:
         """tcgen05 path: hidden widths % 32 == 0, every output width % 64 == 0."""
         widths = [sum(m.out_features for m in l) for l in self.layers]
-        return len(widths) <= 3 and all(w % 64 == 0 for w in widths) and all(w % 32 == 0 for w in widths[:-1])
+        return len(widths) <= 3 and all(w % 64 == 0 and w <= 1024 for w in widths) and all(w % 32 == 0 for w in widths[:-1])
 
     def tc_tensors(self):
         """TF32 (round-to-nearest-away, = cvt.rna.tf32.f32) hi/lo split of every weight, K of layer 0 zero-padded to a
@@ -161,6 +165,8 @@ def run_chain(chain: RadialChain, pair_r: Tensor, num_unique: Tensor, rbf_mod, l
                   float(rbf_mod.alpha), float(lo), float(hi), p(rbf_op.hi) if rbf_op else None, p(rbf_op.lo) if rbf_op else None,
                   p(ws[0]), p(ws[1]), p(ws[2]), p(ws[3]), p(f), p(fp), device=pair_r.device)
         return f, fp
+    if not chain.supported_ffma():
+        raise RuntimeError("radial chain widths are supported by neither the tcgen05 nor the fp32 chain kernel")
     wt3 = wt + [None] * (3 - len(wt))
     b3 = b + [None] * (3 - len(b))
     _lib.call("tmd_pair_chain", p(pair_r), p(num_unique), P, p(wt3[0]), p(b3[0]), p(wt3[1]), p(b3[1]), p(wt3[2]), p(b3[2]),
