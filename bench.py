@@ -197,6 +197,8 @@ def main():
     _lib.library()  # fail loudly if the extension is missing
 
     hp, z, pos, batch, box, desc = workload(args.workload, seed=rank)
+    if args.workload == "c5":
+        args.eager = True  # 40k atoms at max_num_neighbors=128: exact-size (dynamic) buffers instead of 2.4x capacity ones
     hp["static_shapes"] = (not args.eager) and hp["model"] == "tensornet"   # capacity-sized buffers + device counters: the frame is CUDA-graph capturable
     model = seeded_model(hp).to(dev)
     for p_ in model.parameters():

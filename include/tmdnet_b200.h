@@ -181,6 +181,21 @@ int tmd_embed_bwd(const float* rhat, const float* dist, const float* dp, const f
                   const int* nbr_j, const int* indptr, const float* U, const float* V, double lo, double hi, int n,
                   int F, const float* dI, const float* dA, const float* dS, float* g_dist, float* g_rhat, void* stream);
 
+/* ---- a14: Equivariant-Transformer attention message --------------------------------------------------------------------
+ * Replaces EquivariantMultiHeadAttention.propagate/message/aggregate (models/torchmd_et.py:355-426: 4 index_select gathers,
+ * ~10 elementwise launches on [E,H,3hd] tensors, 2 scatter-adds).  One warp per target atom of the sorted symmetric CSR;
+ * q, kk [N,F], v [N,3F] (per head: a|b|c), vec [N,3,F]; dkv [P,4F] = SiLU(dk_proj(rbf)) [F] | SiLU(dv_proj(rbf)) [3F] per
+ * unordered pair (from tmd_pair_chain_tc), dkvp its d/dr.  Outputs xagg [N,F], vagg [N,3,F]; backward returns the node
+ * gradients and dE/d dist[E], dE/d rhat[E,3].  F <= 128, head_dim % 4 == 0, head_dim/4 a power of two. */
+int tmd_et_msg_fwd(const float* q, const float* kk, const float* v, const float* vec, const float* dkv, const int* pid,
+                   const int* nbr_j, const int* indptr, const float* dist, const float* rhat, double lo, double hi,
+                   int vector_cutoff, int n, int F, int head_dim, float* xagg, float* vagg, void* stream);
+int tmd_et_msg_bwd(const float* q, const float* kk, const float* v, const float* vec, const float* dkv,
+                   const float* dkvp, const float* gx, const float* gv, const int* pid, const int* nbr_j,
+                   const int* indptr, const float* dist, const float* rhat, double lo, double hi, int vector_cutoff, int n,
+                   int F, int head_dim, float* gq, float* gk, float* gv_out, float* gvec, float* g_dist, float* g_rhat,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

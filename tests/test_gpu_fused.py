@@ -145,3 +145,53 @@ def test_fused_embedding():
     (g1,) = torch.autograd.grad(sum((a * w_).sum() for a, w_ in zip(out, ws)), [pos], retain_graph=True)
     (g2,) = torch.autograd.grad(sum((a * w_).sum() for a, w_ in zip(ref, ws)), [pos], retain_graph=True)
     assert (g1 - g2).abs().max() < 2e-4 * (1 + g2.abs().max()), (g1 - g2).abs().max()
+
+
+@pytest.mark.parametrize("vcut", [True, False])
+def test_et_attention_message(vcut):
+    """fused ET message kernel (tmd_et_msg_fwd/bwd) vs the reference formulas (models/torchmd_et.py:355-426) in torch."""
+    from torchmdnet_b200.extensions import fused
+    from torchmdnet_b200.models.utils import ExpNormalSmearing, CosineCutoff
+    torch.manual_seed(3)
+    R, F, H = 32, 64, 4
+    hd = F // H
+    z, pos, g = graph_for(n=90, seed=6)
+    n = z.numel()
+    pidx = fused.build_pair_index(g)
+    E, P = int(g.num_pairs), int(pidx.num_unique)
+    rbf = ExpNormalSmearing(0.0, 5.0, R, trainable=False).to(dev)
+    dk_proj, dv_proj = torch.nn.Linear(R, F).to(dev), torch.nn.Linear(R, 3 * F).to(dev)
+    chain = fused.RadialChain([[dk_proj, dv_proj]], act=True, mul_cutoff=False)
+    q, k = (torch.randn(n, F, device=dev, requires_grad=True) for _ in range(2))
+    v = torch.randn(n, 3 * F, device=dev, requires_grad=True)
+    vec = torch.randn(n, 3, F, device=dev, requires_grad=True)
+    dist, dvec = g.dist[:E], g.vec[:E]
+    rhat = dvec / dist.masked_fill(dist == 0, 1).unsqueeze(1)
+    pair_r = fused.pair_distances(dist, pidx, P)
+    xa, va = fused.et_message(q, k, v, vec, dist, rhat, pair_r, chain, rbf, 0.0, 5.0, vcut, hd, g, pidx)
+    # reference: edge (e0 = source, e1 = target); our slot (row t, nbr s) is the edge (s -> t) with d_ij = -rhat
+    t_idx, s_idx = g.nbr_i[:E].long(), g.nbr_j[:E].long()
+    f_ij = rbf(dist)
+    cutoff = CosineCutoff(0.0, 5.0)(dist)
+    dk = torch.nn.functional.silu(dk_proj(f_ij)).view(-1, H, hd)
+    dv = torch.nn.functional.silu(dv_proj(f_ij)).view(-1, H, 3 * hd)
+    q_i, k_j, v_j = q.view(-1, H, hd)[t_idx], k.view(-1, H, hd)[s_idx], v.view(-1, H, 3 * hd)[s_idx]
+    vec_j = vec.view(-1, 3, H, hd)[s_idx]
+    attn = torch.nn.functional.silu((q_i * k_j * dk).sum(-1))
+    if vcut:
+        v_j = v_j * cutoff.view(-1, 1, 1)
+    else:
+        attn = attn * cutoff.unsqueeze(1)
+    v_j = v_j * dv
+    xs, m1, m2 = torch.split(v_j, hd, dim=2)
+    xs = xs * attn.unsqueeze(2)
+    vm = vec_j * m1.unsqueeze(1) + m2.unsqueeze(1) * (-rhat).unsqueeze(2).unsqueeze(3)
+    xref = torch.zeros(n, H, hd, device=dev).index_add(0, t_idx, xs).view(n, F)
+    vref = torch.zeros(n, 3, H, hd, device=dev).index_add(0, t_idx, vm).view(n, 3, F)
+    assert (xa - xref).abs().max() < 5e-5 * (1 + xref.abs().max())
+    assert (va - vref).abs().max() < 5e-5 * (1 + vref.abs().max())
+    wx, wv = torch.randn_like(xref), torch.randn_like(vref)
+    g1 = torch.autograd.grad((xa * wx).sum() + (va * wv).sum(), [q, k, v, vec, pos], retain_graph=True)
+    g2 = torch.autograd.grad((xref * wx).sum() + (vref * wv).sum(), [q, k, v, vec, pos], retain_graph=True)
+    for name, a, b in zip("q k v vec pos".split(), g1, g2):
+        assert (a - b).abs().max() < 2e-4 * (1 + b.abs().max()), (name, (a - b).abs().max().item())

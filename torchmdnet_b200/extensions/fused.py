@@ -242,3 +242,42 @@ class _EmbeddingMP(torch.autograd.Function):
 
 def embedding_message_passing(dist, rhat, U, V, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op=None):
     return _EmbeddingMP.apply(dist, rhat, U, V, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op)
+
+
+class _ETMessage(torch.autograd.Function):
+    """Fused ET attention message + aggregation (row a14): see csrc/et_attention.cu."""
+
+    @staticmethod
+    def forward(ctx, q, kk, v, vec, dist, rhat, pair_r, chain, rbf_mod, lo, hi, vcut, head_dim, g, pidx, rbf_op):
+        need = dist.requires_grad or rhat.requires_grad
+        dkv, dkvp = run_chain(chain, pair_r.detach(), pidx.num_unique, rbf_mod, lo, hi, need, rbf_op)
+        q, kk, v, vec = q.contiguous(), kk.contiguous(), v.contiguous(), vec.contiguous()
+        dist_c, rhat_c = dist.detach().contiguous(), rhat.detach().contiguous()
+        N, F = q.shape[0], q.shape[-1]
+        xagg = torch.empty(N, F, device=q.device, dtype=torch.float32)
+        vagg = torch.empty(N, 3, F, device=q.device, dtype=torch.float32)
+        _lib.call("tmd_et_msg_fwd", p(q), p(kk), p(v), p(vec), p(dkv), p(pidx.pid), p(g.nbr_j), p(g.indptr), p(dist_c), p(rhat_c),
+                  float(lo), float(hi), int(vcut), N, F, int(head_dim), p(xagg), p(vagg), device=q.device)
+        ctx.save_for_backward(q, kk, v, vec, dkv, dkvp if dkvp is not None else dkv, pidx.pid, g.nbr_j, g.indptr, dist_c, rhat_c)
+        ctx.cfg = (float(lo), float(hi), int(vcut), int(head_dim), dkvp is not None)
+        return xagg, vagg
+
+    @staticmethod
+    def backward(ctx, gx, gv):
+        q, kk, v, vec, dkv, dkvp, pid, nbr_j, indptr, dist, rhat = ctx.saved_tensors
+        lo, hi, vcut, hd, has_t = ctx.cfg
+        if not has_t:
+            raise RuntimeError("ET fused message was evaluated without tangents (positions did not require grad)")
+        N, F = q.shape[0], q.shape[-1]
+        gq, gk = torch.empty_like(q), torch.empty_like(kk)
+        gvo, gvec = torch.empty_like(v), torch.empty_like(vec)
+        g_dist, g_rhat = torch.zeros_like(dist), torch.zeros_like(rhat)
+        _lib.call("tmd_et_msg_bwd", p(q), p(kk), p(v), p(vec), p(dkv), p(dkvp), p(gx.contiguous()), p(gv.contiguous()), p(pid),
+                  p(nbr_j), p(indptr), p(dist), p(rhat), lo, hi, vcut, N, F, hd, p(gq), p(gk), p(gvo), p(gvec), p(g_dist),
+                  p(g_rhat), device=q.device)
+        return (gq, gk, gvo, gvec, g_dist, g_rhat) + (None,) * 10
+
+
+def et_message(q, kk, v, vec, dist, rhat, pair_r, chain, rbf_mod, lo, hi, vector_cutoff, head_dim, g, pidx, rbf_op=None):
+    """(x_agg [N,F], vec_agg [N,3,F]) of one ET attention layer; q, kk [N,F], v [N,3F], vec [N,3,F]."""
+    return _ETMessage.apply(q, kk, v, vec, dist, rhat, pair_r, chain, rbf_mod, lo, hi, vector_cutoff, head_dim, g, pidx, rbf_op)

@@ -207,7 +207,8 @@ class TensorNet(nn.Module):
         nbr_i, nbr_j, dist, vec = g.nbr_i, g.nbr_j, g.dist, g.vec
         use_fused = self._fused_path_ok()
         pidx = fused.build_pair_index(g) if use_fused else None
-        P = dist.shape[0]
+        # capacity of the unique-pair arrays: every pair but the self loops is listed twice, so P_u <= (E + N) / 2
+        P = min(dist.shape[0], (dist.shape[0] + z.shape[0]) // 2 + 1)
         if not self.static_shapes:
             # dynamic shapes: one host read of the pair counters, then exact-size views (the reference pays a
             # boolean-mask compaction here, models/utils.py:303-307)

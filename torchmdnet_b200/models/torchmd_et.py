@@ -12,6 +12,7 @@ import torch
 from torch import Tensor, nn
 
 from .utils import CosineCutoff, NeighborEmbedding, OptimizedDistance, act_class_mapping, rbf_class_mapping
+from ..extensions import fused
 
 __all__ = ["TorchMD_ET"]
 
@@ -51,6 +52,25 @@ class EquivariantMultiHeadAttention(nn.Module):
             if lin is not None:
                 nn.init.xavier_uniform_(lin.weight)
                 lin.bias.data.fill_(0)
+
+    def radial_chain(self) -> "fused.RadialChain":
+        if getattr(self, "_chain", None) is None:
+            self._chain = fused.RadialChain([[self.dk_proj, self.dv_proj]], act=True, mul_cutoff=False)
+        return self._chain
+
+    def forward_fused(self, x, vec, fast):
+        """Same layer with the gather/message/scatter part in one kernel (csrc/et_attention.cu) and dk, dv evaluated
+        once per unordered pair on the tensor cores."""
+        dist, rhat, pair_r, g, pidx, rbf_mod, rbf_op = fast
+        F_ = self.hidden_channels
+        xl = self.layernorm(x)
+        q, k, v = self.q_proj(xl), self.k_proj(xl), self.v_proj(xl)
+        vec1, vec2, vec3 = torch.split(self.vec_proj(vec), F_, dim=-1)
+        vec_dot = (vec1 * vec2).sum(dim=1)
+        xa, va = fused.et_message(q, k, v, vec, dist, rhat, pair_r, self.radial_chain(), rbf_mod, self.cutoff.cutoff_lower,
+                                  self.cutoff.cutoff_upper, self.vector_cutoff, self.head_dim, g, pidx, rbf_op)
+        o1, o2, o3 = torch.split(self.o_proj(xa), F_, dim=1)
+        return vec_dot * o2 + o3, vec3 * o1.unsqueeze(1) + va
 
     def forward(self, x, vec, src, dst, cut, f_ij, d_ij):
         """src = edge_index[0] (key/value atom), dst = edge_index[1] (query atom, aggregation target)."""
@@ -111,7 +131,26 @@ class TorchMD_ET(nn.Module):
             for _ in range(num_layers)])
         self.out_norm = nn.LayerNorm(hidden_channels, dtype=dtype)
         self.cutoff = CosineCutoff(cutoff_lower, cutoff_upper)
+        self.fused_edge_path = None  # None: automatic; False: force the torch-op message path
         self.reset_parameters()
+
+    def _fused_path_ok(self) -> bool:
+        """Fused attention kernels differentiate w.r.t. geometry and node features only (not dk/dv weights): used in
+        eval mode or with frozen parameters, for the configuration they implement."""
+        if self.fused_edge_path is False or self.rbf_type != "expnorm" or self.distance_influence != "both":
+            return False
+        if self.activation != "silu" or self.attn_activation != "silu" or not fused.USE_TENSOR_CORES:
+            return False
+        F_, hd = self.hidden_channels, self.hidden_channels // self.num_heads
+        lph = hd // 4
+        if F_ > 128 or F_ % 4 or hd % 4 or lph & (lph - 1):
+            return False
+        chains = [l.radial_chain() for l in self.attention_layers]
+        if not all(c.supported_tc() for c in chains):
+            return False
+        rbf_frozen = not any(t.requires_grad for t in (self.distance_expansion.means, self.distance_expansion.betas))
+        frozen = rbf_frozen and all(c.frozen() for c in chains)
+        return frozen or not (self.training and torch.is_grad_enabled())
 
     def reset_parameters(self):
         self.embedding.reset_parameters()
@@ -126,7 +165,13 @@ class TorchMD_ET(nn.Module):
                 s: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
         x = self.embedding(z)
         g = self.distance.graph(pos, batch, box)
-        E = min(int(g.num_pairs.item()), g.dist.shape[0])
+        use_fused = self._fused_path_ok()
+        if use_fused:
+            pidx = fused.build_pair_index(g)
+            E, P = torch.cat([g.num_pairs, pidx.num_unique]).tolist()
+            E, P = min(E, g.dist.shape[0]), min(P, g.dist.shape[0])
+        else:
+            E = min(int(g.num_pairs.item()), g.dist.shape[0])
         a, b = g.nbr_i[:E].long(), g.nbr_j[:E].long()
         dist, vec = g.dist[:E], g.vec[:E]
         edge_attr = self.distance_expansion(dist)
@@ -137,8 +182,13 @@ class TorchMD_ET(nn.Module):
         v = torch.zeros(x.size(0), 3, x.size(1), device=x.device, dtype=x.dtype)
         # the list is symmetric, so pairing (src, dst) = (a, b) covers exactly the reference's edge set
         # {(edge_index[0], edge_index[1])}; vec = pos_a - pos_b is the reference's d_ij for that edge
+        if use_fused:
+            pair_r = fused.pair_distances(dist, pidx, P)
+            rbf_op = fused.precompute_rbf(pair_r.detach(), pidx.num_unique, self.distance_expansion, self.cutoff_lower,
+                                          self.cutoff_upper, pair_r.requires_grad)
+            fast = (dist, d_ij, pair_r, g, pidx, self.distance_expansion, rbf_op)
         for attn in self.attention_layers:
-            dx, dv = attn(x, v, a, b, cut, edge_attr, d_ij)
+            dx, dv = attn.forward_fused(x, v, fast) if use_fused else attn(x, v, a, b, cut, edge_attr, d_ij)
             x = x + dx
             v = v + dv
         return self.out_norm(x), v, z, pos, batch
