@@ -313,7 +313,7 @@ def main():
                     "bound": "tensor", "achieved": ach_tf, "peak": tc_peak, "peak_source": how + " dense bf16 burst", "unit": "TFLOP/s",
                     "frac": ach_tf / tc_peak, "frac_of_3xtf32_ceiling": ach_tf / (tc_peak / 6.0),
                     "note": "fp32-parity path: TF32 runs at 1/2 the bf16 rate and each product needs 3 split MMAs, so the ceiling for this kernel is peak/6",
-                    "traffic": 4.257e9, "traffic_source": "ncu --set full r01 (dram read+write summed over the 3 GEMM launches of one chain call, profiles/r01_gemm3x_ncu.md)",
+                    "traffic": 4.240e9, "traffic_source": "ncu --set full r01 (dram read+write summed over the 3 GEMM launches of one chain call, profiles/r01_gemm3x_ncu.md)",
                     "algorithmic_flops": flops, "kernel_ms": c_ms, "pairs": Pn}
         # ---- secondary: interaction message passing forward (a7), HBM/L2-gather bound ----
         I_, A_, S_ = (torch.randn(N, k, F, device=dev) for k in (1, 3, 5))

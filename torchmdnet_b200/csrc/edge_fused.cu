@@ -245,7 +245,6 @@ __global__ void __launch_bounds__(256, 2) mp_pair_bwd_kernel(CIrr Y, CIrr dM, co
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wid = threadIdx.x >> 5;
   const int chunks = (F + 127) / 128;            // channel chunks of 128 (one float4 per lane)
   float4* myb = sm4 + (size_t)wid * 18 * chunks * 32;  // [chunk][18][32 lanes]
-  float* red = reinterpret_cast<float*>(sm4 + (size_t)wpb * 18 * chunks * 32) + wid * 32 * 33;  // [32 pairs][33]
   for (int b = blockIdx.x * wpb + wid; b < n; b += gridDim.x * wpb) {
     const int k0 = indptr[b], k1 = indptr[b + 1];
     __syncwarp();
@@ -284,56 +283,40 @@ __global__ void __launch_bounds__(256, 2) mp_pair_bwd_kernel(CIrr Y, CIrr dM, co
       }
       st9(dY, b, F, h, acc);
     }
-    // ---- pass 2: canonical pairs (j <= b; rows are sorted so they come first): dE/dr_p.  Per-lane partials of up to 32
-    // pairs are parked in shared memory ([pair][lane], padded) and reduced by a transposed read: no shuffle chains.
+    // ---- pass 2: canonical pairs (j <= b; rows are sorted so they come first): dE/dr_p
     if (fp) {
-      int kc = 0;   // canonical slots are [k0, k0 + #{j <= b}) because the row is sorted by j
-      for (int k = k0 + lane; k < k1; k += 32) kc += (nbr_j[k] <= b) ? 1 : 0;
+      for (int k = k0; k < k1; ++k) {
+        const long long j = nbr_j[k];
+        if (j > b) break;
+        const long long p = pid[k];
+        const float sym = (j == b) ? 0.f : 1.f;  // a self loop is a single directed edge
+        const float4 s4 = make_float4(sym, sym, sym, sym);
+        float s = 0.f;
+        for (int ch = 0; ch < chunks; ++ch) {
+          const int h = ch * 128 + lane * 4;
+          if (h >= F) continue;
+          const float4* yb = myb + (ch * 18) * 32 + lane;
+          const float4* db = myb + (ch * 18 + 9) * 32 + lane;
+          const float* fpe = fp + p * 3 * (long long)F + h;
+          float4 g = fma4(s4, mul4(ldg4(dM.I + j * F + h), yb[0]), mul4(db[0], ldg4(Y.I + j * F + h)));
+          s += dot4(ldg4(fpe), g);
+          g = zero4();
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) kc += __shfl_xor_sync(0xffffffffu, kc, o);
-      kc += k0;
-      for (int kb = k0; kb < kc; kb += 32) {
-        const int ne = min(32, kc - kb);
-        for (int e = 0; e < ne; ++e) {
-          const int k = kb + e;
-          const long long j = nbr_j[k];
-          const long long p = pid[k];
-          const float sym = (j == b) ? 0.f : 1.f;  // a self loop is a single directed edge
-          const float4 s4 = make_float4(sym, sym, sym, sym);
-          float s = 0.f;
-          for (int ch = 0; ch < chunks; ++ch) {
-            const int h = ch * 128 + lane * 4;
-            if (h >= F) continue;
-            const float4* yb = myb + (ch * 18) * 32 + lane;
-            const float4* db = myb + (ch * 18 + 9) * 32 + lane;
-            const float* fpe = fp + p * 3 * (long long)F + h;
-            float4 g = fma4(s4, mul4(ldg4(dM.I + j * F + h), yb[0]), mul4(db[0], ldg4(Y.I + j * F + h)));
-            s += dot4(ldg4(fpe), g);
-            g = zero4();
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              g = fma4(db[(1 + c) * 32], ldg4(Y.A + (j * 3 + c) * F + h), g);
-              g = fma4(s4, mul4(ldg4(dM.A + (j * 3 + c) * F + h), yb[(1 + c) * 32]), g);
-            }
-            s += dot4(ldg4(fpe + F), g);
-            g = zero4();
-#pragma unroll
-            for (int c = 0; c < 5; ++c) {
-              g = fma4(db[(4 + c) * 32], ldg4(Y.S + (j * 5 + c) * F + h), g);
-              g = fma4(s4, mul4(ldg4(dM.S + (j * 5 + c) * F + h), yb[(4 + c) * 32]), g);
-            }
-            s += dot4(ldg4(fpe + 2 * F), g);
+          for (int c = 0; c < 3; ++c) {
+            g = fma4(db[(1 + c) * 32], ldg4(Y.A + (j * 3 + c) * F + h), g);
+            g = fma4(s4, mul4(ldg4(dM.A + (j * 3 + c) * F + h), yb[(1 + c) * 32]), g);
           }
-          red[e * 33 + lane] = s;
+          s += dot4(ldg4(fpe + F), g);
+          g = zero4();
+#pragma unroll
+          for (int c = 0; c < 5; ++c) {
+            g = fma4(db[(4 + c) * 32], ldg4(Y.S + (j * 5 + c) * F + h), g);
+            g = fma4(s4, mul4(ldg4(dM.S + (j * 5 + c) * F + h), yb[(4 + c) * 32]), g);
+          }
+          s += dot4(ldg4(fpe + 2 * F), g);
         }
-        __syncwarp();
-        if (lane < ne) {
-          float tot = 0.f;
-#pragma unroll 8
-          for (int l = 0; l < 32; ++l) tot += red[lane * 33 + l];
-          d_pair_r[pid[kb + lane]] = tot;
-        }
-        __syncwarp();
+        s = warp_sum(s);
+        if (lane == 0) d_pair_r[p] = s;
       }
     }
   }
@@ -384,59 +367,49 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict_
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < n; b += gridDim.x * wpb) {
     const int k0 = indptr[b], k1 = indptr[b + 1];
-    for (int kb = k0; kb < k1; kb += 8) {
-      float part[32];  // [edge 0..7][gd, gr0, gr1, gr2]
+    for (int k = k0; k < k1; ++k) {
+      const long long j = nbr_j[k], p = pid[k];
+      const float r[3] = {__ldg(rhat + 3 * k), __ldg(rhat + 3 * k + 1), __ldg(rhat + 3 * k + 2)};
+      float cut, dcut;
+      tn::cosine_cutoff(__ldg(dist + k), lo, hi, &cut, &dcut);
+      float a[3], s[5];
+      tn::skew_compact(r, a); tn::sym_basis(r, s);
+      float gr[3] = {0.f, 0.f, 0.f};
+      float gd = 0.f;
+      for (int h = lane * 4; h < F; h += 128) {
+        float4 d[9];
+        ld9(dout, b, F, h, d);
+        const float4 z = add4(ldg4(U + (long long)b * F + h), ldg4(V + j * F + h));
+        const float* de = dp + p * 3 * (long long)F + h;
+        const float* dde = dpp + p * 3 * (long long)F + h;
+        const float4 q1 = ldg4(de), q2 = ldg4(de + F), q3 = ldg4(de + 2 * F);
+        // dL/dw_k
+        float4 g2 = zero4(), g3 = zero4();
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        part[4 * e] = part[4 * e + 1] = part[4 * e + 2] = part[4 * e + 3] = 0.f;
-        const int k = kb + e;
-        if (k >= k1) continue;
-        const long long j = nbr_j[k], p = pid[k];
-        const float r[3] = {__ldg(rhat + 3 * k), __ldg(rhat + 3 * k + 1), __ldg(rhat + 3 * k + 2)};
-        float cut, dcut;
-        tn::cosine_cutoff(__ldg(dist + k), lo, hi, &cut, &dcut);
-        float a[3], s[5];
-        tn::skew_compact(r, a); tn::sym_basis(r, s);
-        float gr[3] = {0.f, 0.f, 0.f};
-        float gd = 0.f;
-        for (int h = lane * 4; h < F; h += 128) {
-          float4 d[9];
-          ld9(dout, b, F, h, d);
-          const float4 z = add4(ldg4(U + (long long)b * F + h), ldg4(V + j * F + h));
-          const float* de = dp + p * 3 * (long long)F + h;
-          const float* dde = dpp + p * 3 * (long long)F + h;
-          const float4 q1 = ldg4(de), q2 = ldg4(de + F), q3 = ldg4(de + 2 * F);
-          float4 g2 = zero4(), g3 = zero4();
+        for (int c = 0; c < 3; ++c) g2 = fma4(make_float4(a[c], a[c], a[c], a[c]), d[1 + c], g2);
 #pragma unroll
-          for (int c = 0; c < 3; ++c) g2 = fma4(make_float4(a[c], a[c], a[c], a[c]), d[1 + c], g2);
+        for (int c = 0; c < 5; ++c) g3 = fma4(make_float4(s[c], s[c], s[c], s[c]), d[4 + c], g3);
+        // w_k = cut * z * q_k  ->  dw_k/dr = dcut * z * q_k + cut * z * q'_k
+        const float4 t1 = fma4(make_float4(dcut, dcut, dcut, dcut), q1, mul4(make_float4(cut, cut, cut, cut), ldg4(dde)));
+        const float4 t2 = fma4(make_float4(dcut, dcut, dcut, dcut), q2, mul4(make_float4(cut, cut, cut, cut), ldg4(dde + F)));
+        const float4 t3 = fma4(make_float4(dcut, dcut, dcut, dcut), q3, mul4(make_float4(cut, cut, cut, cut), ldg4(dde + 2 * F)));
+        gd += dot4(mul4(z, t1), d[0]) + dot4(mul4(z, t2), g2) + dot4(mul4(z, t3), g3);
+        // d/d rhat through skew and the symmetric-traceless basis
+        const float4 w2 = mul4(make_float4(cut, cut, cut, cut), mul4(z, q2));
+        const float4 w3 = mul4(make_float4(cut, cut, cut, cut), mul4(z, q3));
+        gr[0] -= dot4(w2, d[3]); gr[1] += dot4(w2, d[2]); gr[2] -= dot4(w2, d[1]);
+        const float w3v[4] = {w3.x, w3.y, w3.z, w3.w};
+        const float dSv[5][4] = {{d[4].x, d[4].y, d[4].z, d[4].w}, {d[5].x, d[5].y, d[5].z, d[5].w},
+                                 {d[6].x, d[6].y, d[6].z, d[6].w}, {d[7].x, d[7].y, d[7].z, d[7].w},
+                                 {d[8].x, d[8].y, d[8].z, d[8].w}};
 #pragma unroll
-          for (int c = 0; c < 5; ++c) g3 = fma4(make_float4(s[c], s[c], s[c], s[c]), d[4 + c], g3);
-          // w_k = cut * z * q_k  ->  dw_k/dr = dcut * z * q_k + cut * z * q'_k
-          const float4 c4 = make_float4(cut, cut, cut, cut), dc4 = make_float4(dcut, dcut, dcut, dcut);
-          const float4 t1 = fma4(dc4, q1, mul4(c4, ldg4(dde)));
-          const float4 t2 = fma4(dc4, q2, mul4(c4, ldg4(dde + F)));
-          const float4 t3 = fma4(dc4, q3, mul4(c4, ldg4(dde + 2 * F)));
-          gd += dot4(mul4(z, t1), d[0]) + dot4(mul4(z, t2), g2) + dot4(mul4(z, t3), g3);
-          const float4 w2 = mul4(c4, mul4(z, q2));
-          const float4 w3 = mul4(c4, mul4(z, q3));
-          gr[0] -= dot4(w2, d[3]); gr[1] += dot4(w2, d[2]); gr[2] -= dot4(w2, d[1]);
-          const float w3v[4] = {w3.x, w3.y, w3.z, w3.w};
-          const float dSv[5][4] = {{d[4].x, d[4].y, d[4].z, d[4].w}, {d[5].x, d[5].y, d[5].z, d[5].w},
-                                   {d[6].x, d[6].y, d[6].z, d[6].w}, {d[7].x, d[7].y, d[7].z, d[7].w},
-                                   {d[8].x, d[8].y, d[8].z, d[8].w}};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float dS[5] = {dSv[0][q], dSv[1][q], dSv[2][q], dSv[3][q], dSv[4][q]};
-            tn::sym_basis_bwd_acc(r, dS, w3v[q], gr);
-          }
+        for (int q = 0; q < 4; ++q) {
+          const float dS[5] = {dSv[0][q], dSv[1][q], dSv[2][q], dSv[3][q], dSv[4][q]};
+          tn::sym_basis_bwd_acc(r, dS, w3v[q], gr);
         }
-        part[4 * e] = gd; part[4 * e + 1] = gr[0]; part[4 * e + 2] = gr[1]; part[4 * e + 3] = gr[2];
       }
-      const float tot = warp_reduce_transpose<32>(part, lane);
-      const int k = kb + (lane >> 2), c = lane & 3;
-      if (k < k1) {
-        if (c == 0) g_dist[k] = tot; else g_rhat[3 * k + (c - 1)] = tot;
-      }
+      gd = warp_sum(gd); gr[0] = warp_sum(gr[0]); gr[1] = warp_sum(gr[1]); gr[2] = warp_sum(gr[2]);
+      if (lane == 0) { g_dist[k] = gd; g_rhat[3 * k] = gr[0]; g_rhat[3 * k + 1] = gr[1]; g_rhat[3 * k + 2] = gr[2]; }
     }
   }
 }
@@ -508,7 +481,7 @@ int tmd_mp_pair_bwd(const float* YI, const float* YA, const float* YS, const flo
   TMD_REQUIRE(!fp || d_pair_r, "mp_pair_bwd: fp given without d_pair_r");
   if (n == 0) return TMD_OK;
   const int chunks = (F + 127) / 128;
-  const size_t smem = (size_t)8 * 18 * chunks * 32 * sizeof(float4) + (size_t)8 * 32 * 33 * sizeof(float);
+  const size_t smem = (size_t)8 * 18 * chunks * 32 * sizeof(float4);
   TMD_REQUIRE(smem <= 200 * 1024, "mp_pair_bwd: F too large for the per-warp staging buffer (F <= 256)");
   cudaFuncSetAttribute(mp_pair_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   mp_pair_bwd_kernel<<<tmd_blocks_for((long long)n * 32, 256), 256, smem, (cudaStream_t)stream>>>(
