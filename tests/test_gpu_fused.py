@@ -195,3 +195,24 @@ def test_et_attention_message(vcut):
     g2 = torch.autograd.grad((xref * wx).sum() + (vref * wv).sum(), [q, k, v, vec, pos], retain_graph=True)
     for name, a, b in zip("q k v vec pos".split(), g1, g2):
         assert (a - b).abs().max() < 2e-4 * (1 + b.abs().max()), (name, (a - b).abs().max().item())
+
+
+@pytest.mark.parametrize("F", [64, 128, 256])
+def test_irreps_linear_tensor_cores(F):
+    """grouped 3xTF32 node linears (tmd_irreps_linear_tc) vs three fp64 nn.Linear, forward and input gradients."""
+    from torchmdnet_b200.extensions import fused
+    torch.manual_seed(0)
+    n = 300 + 37  # segments not multiples of 128
+    lins = [torch.nn.Linear(F, F, bias=False).to(dev) for _ in range(3)]
+    w = fused.IrrepsLinearWeights(lins)
+    assert w.supported()
+    X = [torch.randn(n, k, F, device=dev, requires_grad=True) for k in (1, 3, 5)]
+    out = fused.irreps_linear(X, w)
+    ref = [torch.nn.functional.linear(x.double(), l.weight.double()) for x, l in zip(X, lins)]
+    for a, b in zip(out, ref):
+        assert a.shape == b.shape and (a.double() - b).abs().max() < 3e-6 * (1 + b.abs().max())
+    ws = [torch.randn_like(o) for o in out]
+    g1 = torch.autograd.grad(sum((o * w_).sum() for o, w_ in zip(out, ws)), X)
+    g2 = torch.autograd.grad(sum((r * w_.double()).sum() for r, w_ in zip(ref, ws)), X)
+    for a, b in zip(g1, g2):
+        assert (a.double() - b.double()).abs().max() < 3e-6 * (1 + b.abs().max())

@@ -141,6 +141,8 @@ struct GemmParams {
   float* out_lo;
   float* out_f;    // final: [P, N]
   float* out_fp;   // final, rows_per_pair == 2
+  int seg_t1, seg_t2;   // grouped GEMM: m-tiles [0,t1) use weight block 0, [t1,t2) block 1, [t2,..) block 2
+  int b_seg_rows;       // rows of one weight block in the stacked B tensor map
 };
 
 template <int STAGES>
@@ -159,7 +161,7 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   for (int i = threadIdx.x; i < P.N; i += TC_THREADS) bias_s[i] = P.bias[i];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_pairs = min(*P.num_unique, P.max_pairs);
+  const int n_pairs = P.num_unique ? min(*P.num_unique, P.max_pairs) : P.max_pairs;
   const int rows_valid = n_pairs * P.rows_per_pair;
   const int m_tiles = (rows_valid + BM - 1) / BM;
   const int n_blks = P.N / P.BN;
@@ -186,14 +188,15 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const int m_tile = item / n_blks, n_blk = item - m_tile * n_blks;
+        const int b_row = n_blk * P.BN + ((m_tile >= P.seg_t1) + (m_tile >= P.seg_t2)) * P.b_seg_rows;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + (size_t)stage * stage_bytes;
           mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
           tma_load_2d(&map_a_hi, &full_bar[stage], st, kb * BK, m_tile * BM);
           tma_load_2d(&map_a_lo, &full_bar[stage], st + A_TILE_BYTES, kb * BK, m_tile * BM);
-          tma_load_2d(&map_b_hi, &full_bar[stage], st + 2 * A_TILE_BYTES, kb * BK, n_blk * P.BN);
-          tma_load_2d(&map_b_lo, &full_bar[stage], st + 2 * A_TILE_BYTES + b_tile_bytes, kb * BK, n_blk * P.BN);
+          tma_load_2d(&map_b_hi, &full_bar[stage], st + 2 * A_TILE_BYTES, kb * BK, b_row);
+          tma_load_2d(&map_b_lo, &full_bar[stage], st + 2 * A_TILE_BYTES + b_tile_bytes, kb * BK, b_row);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -366,6 +369,22 @@ __global__ void pair_rbf_split_kernel(const float* __restrict__ pair_r, const in
   }
 }
 
+// (I [N,1,F], A [N,3,F], S [N,5,F]) -> TF32 (hi, lo) in one row-segmented buffer [R_tot, F]; segment starts 0, r1, r2
+__global__ void irreps_split_kernel(const float* __restrict__ I, const float* __restrict__ A, const float* __restrict__ S,
+                                    int N, int F, int r1, int r2, float* __restrict__ hi, float* __restrict__ lo) {
+  const long long total = 9LL * N * F;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / F;
+    const int c = (int)(idx - row * F);
+    float x; long long orow;
+    if (row < N) { x = I[row * F + c]; orow = row; }
+    else if (row < 4LL * N) { x = A[(row - N) * F + c]; orow = r1 + (row - N); }
+    else { x = S[(row - 4LL * N) * F + c]; orow = r2 + (row - 4LL * N); }
+    const float h = tf32_rna(x);
+    hi[orow * F + c] = h; lo[orow * F + c] = tf32_rna(x - h);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -470,6 +489,7 @@ int tmd_pair_chain_tc(const float* pair_r, const int* num_unique, int max_pairs,
     P.K = K; P.N = N; P.BN = BN; P.rows_per_pair = rpp; P.act = act; P.final_layer = (l == n_layers - 1);
     P.mul_cutoff = mul_cutoff; P.lo = (float)lo; P.hi = (float)hi; P.bias = bias[l]; P.pair_r = pair_r;
     P.num_unique = num_unique; P.max_pairs = max_pairs; P.out_hi = o_hi; P.out_lo = o_lo; P.out_f = out_f; P.out_fp = out_fp;
+    P.seg_t1 = P.seg_t2 = 0x7fffffff; P.b_seg_rows = 0;
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * BN * BK * 4;
     const int max_items = (rows_pad / BM) * (N / BN);
     const int grid = max_items < 148 ? max_items : 148;
@@ -490,6 +510,45 @@ int tmd_pair_chain_tc(const float* pair_r, const int* num_unique, int max_pairs,
     K = N;
   }
   return tmd_check_launch("pair_chain_tc");
+}
+
+// a9: the three bias-free F x F node linears of TensorNet (I, A, S rows each with its own weight) as ONE grouped 3xTF32
+// GEMM on tcgen05.  W_hi / W_lo: TF32 split of the stacked weights [3F, F] (rows 0..F-1 act on I, F..2F-1 on A, 2F..3F-1 on S).
+// Row-segmented buffers of R_tot = r128(N) + r128(3N) + r128(5N) rows: ws_hi, ws_lo (operands) and out (fp32 result);
+// the I / A / S blocks of `out` start at rows 0, r128(N), r128(N) + r128(3N).  zero_bias: F zeros.
+int tmd_irreps_linear_tc(const float* I, const float* A, const float* S, int N, int F, const float* W_hi, const float* W_lo,
+                         const float* zero_bias, float* ws_hi, float* ws_lo, float* out, void* stream) {
+  TMD_REQUIRE(I && A && S && W_hi && W_lo && zero_bias && ws_hi && ws_lo && out, "irreps_linear_tc: null pointer");
+  TMD_REQUIRE(F % 64 == 0 && F <= 256, "irreps_linear_tc: F must be a multiple of 64, <= 256");
+  if (N == 0) return TMD_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  auto r128 = [](long long x) { return (int)(((x + BM - 1) / BM) * BM); };
+  const int r1 = r128(N), r2 = r1 + r128(3LL * N), rtot = r2 + r128(5LL * N);
+  irreps_split_kernel<<<tmd_blocks_for(9LL * N * F, 256), 256, 0, st>>>(I, A, S, N, F, r1, r2, ws_hi, ws_lo);
+  const int BN = pick_bn(F);
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  if ((rc = make_map(&ma_hi, ws_hi, rtot, F, BM))) return rc;
+  if ((rc = make_map(&ma_lo, ws_lo, rtot, F, BM))) return rc;
+  if ((rc = make_map(&mb_hi, W_hi, 3 * F, F, BN))) return rc;
+  if ((rc = make_map(&mb_lo, W_lo, 3 * F, F, BN))) return rc;
+  GemmParams P;
+  P.K = F; P.N = F; P.BN = BN; P.rows_per_pair = 1; P.act = 0; P.final_layer = 1; P.mul_cutoff = 0; P.lo = 0.f; P.hi = 1.f;
+  P.bias = zero_bias; P.pair_r = nullptr; P.num_unique = nullptr; P.max_pairs = rtot; P.out_hi = nullptr; P.out_lo = nullptr;
+  P.out_f = out; P.out_fp = nullptr; P.seg_t1 = r1 / BM; P.seg_t2 = r2 / BM; P.b_seg_rows = F;
+  const int stage_bytes = 2 * A_TILE_BYTES + 2 * BN * BK * 4;
+  const int items = (rtot / BM) * (F / BN);
+  const int grid = items < 148 ? items : 148;
+  if (stage_bytes * 3 + 1024 <= 200 * 1024) {
+    const int smem = stage_bytes * 3 + 1024;
+    cudaFuncSetAttribute(gemm3x_tf32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    gemm3x_tf32_kernel<3><<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
+  } else {
+    const int smem = stage_bytes * 2 + 1024;
+    cudaFuncSetAttribute(gemm3x_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    gemm3x_tf32_kernel<2><<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
+  }
+  return tmd_check_launch("irreps_linear_tc");
 }
 
 }  // extern "C"

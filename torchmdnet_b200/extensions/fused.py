@@ -281,3 +281,67 @@ class _ETMessage(torch.autograd.Function):
 def et_message(q, kk, v, vec, dist, rhat, pair_r, chain, rbf_mod, lo, hi, vector_cutoff, head_dim, g, pidx, rbf_op=None):
     """(x_agg [N,F], vec_agg [N,3,F]) of one ET attention layer; q, kk [N,F], v [N,3F], vec [N,3,F]."""
     return _ETMessage.apply(q, kk, v, vec, dist, rhat, pair_r, chain, rbf_mod, lo, hi, vector_cutoff, head_dim, g, pidx, rbf_op)
+
+
+# ------------------------------------------------------------------------------------------ node linears on tensor cores
+def _tf32_split(w: Tensor):
+    b = w.contiguous().view(torch.int32)
+    hi = ((b + 0x1000) & -8192).view(torch.float32)
+    lo = w - hi
+    lo = ((lo.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+    return hi.contiguous(), lo.contiguous()
+
+
+class IrrepsLinearWeights:
+    """TF32-split, stacked copies of three bias-free nn.Linear(F, F) (forward: W, backward: W^T), cached per weight version."""
+
+    def __init__(self, linears: Sequence[torch.nn.Linear]):
+        self.linears = list(linears)
+        self._key = None
+
+    def supported(self) -> bool:
+        F = self.linears[0].in_features
+        return (USE_TENSOR_CORES and F % 64 == 0 and F <= 256 and
+                all(l.bias is None and l.in_features == F and l.out_features == F for l in self.linears))
+
+    def frozen(self) -> bool:
+        return not any(l.weight.requires_grad for l in self.linears)
+
+    def tensors(self):
+        key = tuple((l.weight.data_ptr(), l.weight._version) for l in self.linears)
+        if key != self._key:
+            W = torch.cat([l.weight.detach() for l in self.linears], 0)              # [3F, F]: out = x W_k^T  ->  B[n, k] = W_k
+            Wt = torch.cat([l.weight.detach().t() for l in self.linears], 0)        # backward: dx = dy W_k   ->  B[n, k] = W_k^T
+            self._fwd, self._bwd = _tf32_split(W), _tf32_split(Wt.contiguous())
+            self._zero = torch.zeros(W.shape[1], device=W.device, dtype=torch.float32)
+            self._key = key
+        return self._fwd, self._bwd, self._zero
+
+
+def _irreps_gemm(I, A, S, w_hi, w_lo, zero):
+    I, A, S = I.contiguous(), A.contiguous(), S.contiguous()
+    N, F = I.shape[0], I.shape[-1]
+    r128 = lambda x: -(-x // 128) * 128
+    r1 = r128(N); r2 = r1 + r128(3 * N); rtot = r2 + r128(5 * N)
+    ws = torch.empty(2, rtot, F, device=I.device, dtype=torch.float32)
+    out = torch.empty(rtot, F, device=I.device, dtype=torch.float32)
+    _lib.call("tmd_irreps_linear_tc", p(I), p(A), p(S), N, F, p(w_hi), p(w_lo), p(zero), p(ws[0]), p(ws[1]), p(out), device=I.device)
+    return out[:N].view(N, 1, F), out[r1:r1 + 3 * N].view(N, 3, F), out[r2:r2 + 5 * N].view(N, 5, F)
+
+
+class _IrrepsLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, I, A, S, weights):
+        fwd, bwd, zero = weights.tensors()
+        ctx.bwd, ctx.zero = bwd, zero
+        return _irreps_gemm(I, A, S, fwd[0], fwd[1], zero)
+
+    @staticmethod
+    def backward(ctx, dI, dA, dS):
+        gI, gA, gS = _irreps_gemm(dI, dA, dS, ctx.bwd[0], ctx.bwd[1], ctx.zero)
+        return gI, gA, gS, None
+
+
+def irreps_linear(X, weights: IrrepsLinearWeights):
+    """(W0 I, W1 A, W2 S) as one grouped tensor-core GEMM (row a9); gradients flow to I/A/S only (frozen weights)."""
+    return _IrrepsLinear.apply(X[0], X[1], X[2], weights)

@@ -70,6 +70,11 @@ class TensorEmbedding(nn.Module):
                                             mul_cutoff=False)
         return self._chain
 
+    def node_linear(self) -> "fused.IrrepsLinearWeights":
+        if getattr(self, "_nl", None) is None:
+            self._nl = fused.IrrepsLinearWeights(self.linears_tensor)
+        return self._nl
+
     def forward(self, z, g, nbr_i, nbr_j, cut, rhat, rbf, fast=None):
         if fast is not None:
             # fused path: U/V per atom, radial projections per pair (with d/dr), w assembled inside the kernel
@@ -86,9 +91,12 @@ class TensorEmbedding(nn.Module):
         norm = self.init_norm(ops.norm2_compact(I, A, S))
         for lin in self.linears_scalar:
             norm = self.act(lin(norm))
-        I = self.linears_tensor[0](I)
-        A = self.linears_tensor[1](A)
-        S = self.linears_tensor[2](S)
+        if fast is not None and self.node_linear().supported() and self.node_linear().frozen():
+            I, A, S = fused.irreps_linear((I, A, S), self.node_linear())
+        else:
+            I = self.linears_tensor[0](I)
+            A = self.linears_tensor[1](A)
+            S = self.linears_tensor[2](S)
         return ops.gate_compact(I, A, S, norm.view(-1, 3, self.hidden_channels))
 
 
@@ -125,10 +133,16 @@ class Interaction(nn.Module):
             self._chain = fused.RadialChain([[l] for l in self.linears_scalar], act=True, mul_cutoff=True)
         return self._chain
 
+    def node_linear(self, which: int) -> "fused.IrrepsLinearWeights":
+        if getattr(self, "_nl", None) is None:
+            self._nl = (fused.IrrepsLinearWeights(self.linears_tensor[0:3]), fused.IrrepsLinearWeights(self.linears_tensor[3:6]))
+        return self._nl[which]
+
     def forward(self, X, g, rbf, cut, qf, fast=None):
         lt = self.linears_tensor
+        tc_lin = fast is not None and all(self.node_linear(k).supported() and self.node_linear(k).frozen() for k in (0, 1))
         Xn = ops.interaction_normalize(*X)
-        Y = (lt[0](Xn[0]), lt[1](Xn[1]), lt[2](Xn[2]))
+        Y = fused.irreps_linear(Xn, self.node_linear(0)) if tc_lin else (lt[0](Xn[0]), lt[1](Xn[1]), lt[2](Xn[2]))
         if fast is not None:
             # fused path: f (and df/dr) once per unordered pair, message passing reads it through the pair index
             dist, pair_r, pidx, rbf_mod, rbf_op = fast
@@ -140,7 +154,7 @@ class Interaction(nn.Module):
             # (indptr, nbr_j, rev): the transposed edge of slot k in row b lives at rev[k]
             M = ops.fn_message_passing(Y[0], Y[1], Y[2], f, None, g.nbr_j, g.indptr, g.rev, g.nbr_j, g.indptr)
         Cn = ops.interaction_product(Y[0], Y[1], Y[2], M[0], M[1], M[2], qf, self.equivariance_invariance_group == "O(3)")
-        dX = (lt[3](Cn[0]), lt[4](Cn[1]), lt[5](Cn[2]))
+        dX = fused.irreps_linear(Cn, self.node_linear(1)) if tc_lin else (lt[3](Cn[0]), lt[4](Cn[1]), lt[5](Cn[2]))
         return ops.interaction_update(Xn[0], Xn[1], Xn[2], dX[0], dX[1], dX[2], qf)
 
 
