@@ -50,6 +50,20 @@ def test_operator_surface_matches_reference():
     assert list(fwd.parameters) == ["self", "z", "pos", "batch", "box", "q", "s", "extra_args", "num_systems"]
 
 
+def test_op_registry_names():
+    """the reference's torch.library names are registered by extensions/registry.py (CUDA only)."""
+    import torch
+    from torchmdnet_b200.extensions import registry
+    want = ["torchmdnet::warp_neighbor_brute_fwd", "torchmdnet::warp_neighbor_cell_fwd", "nvtnet::count_row_col_primitive",
+            "nvtnet::convert_to_sparse_primitive"]
+    for op in ["compose_tensor", "decompose_tensor", "tensor_matmul_o3_3x3", "tensor_matmul_so3_3x3", "tensor_norm3",
+               "message_passing", "radial_message_passing"]:
+        want += [f"tensornet::{op}_fwd_primitive", f"tensornet::{op}_bwd_primitive"]
+    assert sorted(want) == sorted(registry.REGISTERED)
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        torch.ops.tensornet.tensor_norm3_fwd_primitive(torch.rand(2, 3, 3, 8))  # no CPU kernel registered
+
+
 def test_no_cpu_fallback(lib):
     from torchmdnet_b200.extensions.ops import get_neighbor_pairs_kernel
     from torchmdnet_b200.extensions import tensornet_ops as t

@@ -165,3 +165,20 @@ def test_cuda_graph_force_field():
     y, g = m(fx["z"].to(dev), pos2.clone(), fx["batch"].to(dev), box=fx["box"].to(dev), num_systems=1)
     assert rel(e2, y.double().cpu()) < 1e-6 and relF(f2, g.double().cpu()) < 1e-5
     assert abs(e2.item() - e.item()) > 1e-6
+
+
+@pytest.mark.parametrize("kind", ["tensornet", "et"])
+def test_rotation_invariance_and_force_equivariance(kind):
+    """reference tests/test_equivariance.py:10-53: E(R x) = E(x), F(R x) = R F(x) (random rotation, incl. an improper one for O(3))."""
+    hp = systems.tensornet_hparams(num_layers=2, F=64, R=32, max_nb=64) if kind == "tensornet" else \
+        systems.et_hparams(num_layers=2, F=64, R=32, H=4, cutoff=5.0, max_nb=64)
+    m = seeded_model(hp, 11).eval().to(dev)
+    z, pos, batch, _ = systems.molecule_batch(n_mol=3, seed=9)
+    g = torch.Generator().manual_seed(0)
+    Q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g, dtype=torch.float64))
+    for R in (Q if torch.det(Q) > 0 else -Q, -(Q if torch.det(Q) > 0 else -Q)):   # proper, then improper
+        R = R.float().to(dev)
+        y1, f1 = m(z.to(dev), pos.to(dev), batch.to(dev))
+        y2, f2 = m(z.to(dev), (pos.to(dev) @ R.T).contiguous(), batch.to(dev))
+        assert (y1 - y2).abs().max() < 2e-5 * (1 + y1.abs().max())
+        assert (f1 @ R.T - f2).abs().max() < 5e-5 * (1 + f1.abs().max())
