@@ -160,12 +160,16 @@ int tmd_pair_chain(const float* pair_r, const int* num_unique, int max_pairs, co
 /* Tensor-core version of tmd_pair_chain: every layer is a 3xTF32 GEMM on tcgen05 (TMA-fed, TMEM accumulators).
  * W_hi/W_lo[l]: TF32 (cvt.rna) split of the Linear weight [N_l, K_l] with K_0 zero-padded to a multiple of 32;
  * hidden widths % 32 == 0, every N_l % 64 == 0.  Workspaces act_{a,b}_{hi,lo}: >= roundup(max_pairs*(out_fp?2:1),128)
- * x max(K_l) floats each.  Same outputs as tmd_pair_chain to ~1e-6 relative. */
+ * x max(K_l) floats each.  Same outputs as tmd_pair_chain to ~1e-6 relative.
+ * use_f16 = 1: the split terms are fp16 instead of tf32 (same 11-bit significands, half the bytes, twice the MMA rate;
+ * W_hi/W_lo and the workspaces then hold __half, K padded to multiples of 64, hidden widths % 64 == 0).  fp16 has a
+ * 5-bit exponent: the caller must bound |activations| and |d/dr| below 65504 (extensions/fused.py does, from the weight
+ * norms, and falls back to tf32 otherwise). */
 int tmd_pair_chain_tc(const float* pair_r, const int* num_unique, int max_pairs, const float* const* W_hi,
                       const float* const* W_lo, const float* const* bias, const int* dims, int n_layers, int act,
                       int mul_cutoff, const float* means, const float* betas, double alpha, double lo, double hi,
                       const float* rbf_hi, const float* rbf_lo, float* act_a_hi, float* act_a_lo, float* act_b_hi,
-                      float* act_b_lo, float* out_f, float* out_fp, void* stream);
+                      float* act_b_lo, float* out_f, float* out_fp, int use_f16, void* stream);
 /* ---- a9: node linears -----------------------------------------------------------------------------------------------
  * Replaces the three bias-free nn.Linear(F,F) that TensorNet applies to I / A / S (models/tensornet.py:752-754, :808-810,
  * :607-615; cuBLAS SGEMMs in the reference) by one grouped 3xTF32 tcgen05 GEMM.  W_hi/W_lo: TF32 split of the stacked
@@ -177,7 +181,7 @@ int tmd_irreps_linear_tc(const float* I, const float* A, const float* S, int N, 
  * of 32.  Computed once per frame and shared by the embedding chain and every interaction layer (rbf_hi / rbf_lo). */
 int tmd_pair_rbf_split(const float* pair_r, const int* num_unique, int max_pairs, int R, int rows_per_pair,
                        const float* means, const float* betas, double alpha, double lo, double hi, float* a_hi,
-                       float* a_lo, void* stream);
+                       float* a_lo, int use_f16, void* stream);
 int tmd_mp_pair_bwd(const float* YI, const float* YA, const float* YS, const float* dMI, const float* dMA,
                     const float* dMS, const float* f, const float* fp, const int* pid, const int* nbr_j,
                     const int* indptr, int n, int F, float* dYI, float* dYA, float* dYS, float* d_pair_r, void* stream);

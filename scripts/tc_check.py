@@ -34,8 +34,9 @@ for name, (lins, act, cut, concat) in cfgs.items():
         ref = x * CosineCutoff(0.0, 5.0)(rd).unsqueeze(-1)
     w = torch.randn_like(ref)
     (gref,) = torch.autograd.grad((ref * w).sum(), rd)
-    for tc in (False, True):
+    for tc, f16 in ((False, False), (True, False), (True, True)):
         fused.USE_TENSOR_CORES = tc
+        fused.USE_F16_SPLIT = f16
         f, fp = fused.run_chain(chain, r.float(), nu, rbf, 0.0, 5.0, True)
         torch.cuda.synchronize()
         ev = (f.double() - ref).abs().max().item() / ref.abs().max().item()
@@ -44,4 +45,4 @@ for name, (lins, act, cut, concat) in cfgs.items():
         for _ in range(5):
             fused.run_chain(chain, r.float(), nu, rbf, 0.0, 5.0, True)
         torch.cuda.synchronize()
-        print(f"{name:12s} tc={tc}: rel err value {ev:.2e} tangent {et:.2e}  time {1e3 * (time.perf_counter() - t0) / 5:.3f} ms (P={P})", flush=True)
+        print(f"{name:12s} tc={tc} f16={f16}: rel err value {ev:.2e} tangent {et:.2e}  time {1e3 * (time.perf_counter() - t0) / 5:.3f} ms (P={P})", flush=True)

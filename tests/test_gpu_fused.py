@@ -36,12 +36,13 @@ def test_pair_index():
     assert torch.equal(pidx.pair_r[:P], g.dist[:E][ce])
 
 
-@pytest.mark.parametrize("tc", [True, False])
+@pytest.mark.parametrize("tc", ["f16", "tf32", False])
 @pytest.mark.parametrize("cfg", ["interaction", "embedding", "single_act"])
 def test_pair_chain_value_and_tangent(cfg, tc, monkeypatch):
-    """tc=True: tcgen05 3xTF32 GEMM chain (tmd_pair_chain_tc); tc=False: fp32 CUDA-core chain (tmd_pair_chain)."""
+    """tc='f16'/'tf32': tcgen05 GEMM chain with fp16 / tf32 split terms (tmd_pair_chain_tc); False: fp32 CUDA-core chain."""
     from torchmdnet_b200.extensions import fused
-    monkeypatch.setattr(fused, "USE_TENSOR_CORES", tc)
+    monkeypatch.setattr(fused, "USE_TENSOR_CORES", bool(tc))
+    monkeypatch.setattr(fused, "USE_F16_SPLIT", tc == "f16")
     from torchmdnet_b200.models.utils import ExpNormalSmearing, CosineCutoff
     torch.manual_seed(0)
     R, F = 32, 128

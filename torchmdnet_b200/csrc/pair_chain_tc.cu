@@ -18,6 +18,7 @@
 //                                  (+ cutoff on the last layer), re-split to (hi, lo) or final fp32 f / f' to HBM;
 //                                  double-buffered accumulator (2 x 256 columns) overlaps it with the next item's MMAs
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "common.cuh"
 
@@ -101,6 +102,19 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
 __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with A = B = F16 (format 0): kind::f16, K = 16 per instruction
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -141,6 +155,7 @@ struct GemmParams {
   float* out_lo;
   float* out_f;    // final: [P, N]
   float* out_fp;   // final, rows_per_pair == 2
+  int f16;              // operands are fp16 (hi, lo) pairs (K-block = 64 elements) instead of tf32 (32 elements)
   int seg_t1, seg_t2;   // grouped GEMM: m-tiles [0,t1) use weight block 0, [t1,t2) block 1, [t2,..) block 2
   int b_seg_rows;       // rows of one weight block in the stacked B tensor map
 };
@@ -166,7 +181,8 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   const int m_tiles = (rows_valid + BM - 1) / BM;
   const int n_blks = P.N / P.BN;
   const int total_items = m_tiles * n_blks;
-  const int k_blocks = P.K / BK;
+  const int bk_el = P.f16 ? 2 * BK : BK;   // elements per 128-byte K-block
+  const int k_blocks = P.K / bk_el;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -193,17 +209,18 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + (size_t)stage * stage_bytes;
           mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-          tma_load_2d(&map_a_hi, &full_bar[stage], st, kb * BK, m_tile * BM);
-          tma_load_2d(&map_a_lo, &full_bar[stage], st + A_TILE_BYTES, kb * BK, m_tile * BM);
-          tma_load_2d(&map_b_hi, &full_bar[stage], st + 2 * A_TILE_BYTES, kb * BK, b_row);
-          tma_load_2d(&map_b_lo, &full_bar[stage], st + 2 * A_TILE_BYTES + b_tile_bytes, kb * BK, b_row);
+          tma_load_2d(&map_a_hi, &full_bar[stage], st, kb * bk_el, m_tile * BM);
+          tma_load_2d(&map_a_lo, &full_bar[stage], st + A_TILE_BYTES, kb * bk_el, m_tile * BM);
+          tma_load_2d(&map_b_hi, &full_bar[stage], st + 2 * A_TILE_BYTES, kb * bk_el, b_row);
+          tma_load_2d(&map_b_lo, &full_bar[stage], st + 2 * A_TILE_BYTES + b_tile_bytes, kb * bk_el, b_row);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = make_idesc_tf32(BM, P.BN);
+    const uint32_t idesc = P.f16 ? make_idesc_f16(BM, P.BN) : make_idesc_tf32(BM, P.BN);
+    const bool f16 = P.f16 != 0;
     int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -218,10 +235,16 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           const uint64_t b_hi = make_desc_sw128(st + 2 * A_TILE_BYTES), b_lo = make_desc_sw128(st + 2 * A_TILE_BYTES + b_tile_bytes);
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
-            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 8 tf32 = 32 B per K-step inside the 128 B swizzle row
-            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
-            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
-            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);  // 8 tf32 / 16 f16 = 32 B per K-step inside the 128 B swizzle row
+            if (f16) {
+              umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+              umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+              umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+            } else {
+              umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+              umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+              umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+            }
           }
         }
         __syncwarp();
@@ -288,6 +311,27 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
               st8(d1, dh); st8(d1 + 8, dh + 8);
             } else {
               const size_t o0 = (size_t)row_v * P.N + cb, o1 = o0 + P.N;
+              if (P.f16) {
+                // fp16 (hi, lo): 16 columns = 32 bytes = one 256-bit store per (row, array)
+                __half* oh = reinterpret_cast<__half*>(P.out_hi);
+                __half* ol = reinterpret_cast<__half*>(P.out_lo);
+                float a[8], b[8], c[8], d[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  const __half2 hh = __floats2half2_rn(h[2 * u], h[2 * u + 1]);
+                  const float2 hf = __half22float2(hh);
+                  const __half2 hl = __floats2half2_rn(h[2 * u] - hf.x, h[2 * u + 1] - hf.y);
+                  const __half2 dh2 = __floats2half2_rn(dh[2 * u], dh[2 * u + 1]);
+                  const float2 df = __half22float2(dh2);
+                  const __half2 dl = __floats2half2_rn(dh[2 * u] - df.x, dh[2 * u + 1] - df.y);
+                  a[u] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&hh));
+                  b[u] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&hl));
+                  c[u] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&dh2));
+                  d[u] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&dl));
+                }
+                st8(reinterpret_cast<float*>(oh + o0), a); st8(reinterpret_cast<float*>(ol + o0), b);
+                st8(reinterpret_cast<float*>(oh + o1), c); st8(reinterpret_cast<float*>(ol + o1), d);
+              } else
 #pragma unroll
               for (int i = 0; i < 16; i += 8) {
                 float a[8], b[8], c[8], d[8];
@@ -316,6 +360,23 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 #pragma unroll
               for (int i = 0; i < 32; i += 4) st4(dst + i, make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]));
             } else {
+              if (P.f16) {
+                __half* oh = reinterpret_cast<__half*>(P.out_hi) + (size_t)row * P.N + col0;
+                __half* ol = reinterpret_cast<__half*>(P.out_lo) + (size_t)row * P.N + col0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 16) {
+                  float a[8], b[8];
+#pragma unroll
+                  for (int u = 0; u < 8; ++u) {
+                    const __half2 hh = __floats2half2_rn(o[i + 2 * u], o[i + 2 * u + 1]);
+                    const float2 hf = __half22float2(hh);
+                    const __half2 hl = __floats2half2_rn(o[i + 2 * u] - hf.x, o[i + 2 * u + 1] - hf.y);
+                    a[u] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&hh));
+                    b[u] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&hl));
+                  }
+                  st8(reinterpret_cast<float*>(oh + i), a); st8(reinterpret_cast<float*>(ol + i), b);
+                }
+              } else {
               float* dhp = P.out_hi + (size_t)row * P.N + col0;
               float* dlp = P.out_lo + (size_t)row * P.N + col0;
 #pragma unroll
@@ -325,6 +386,7 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 for (int u = 0; u < 4; ++u) { hi4[u] = tf32_rna(o[i + u]); lo4[u] = tf32_rna(o[i + u] - hi4[u]); }
                 st4(dhp + i, make_float4(hi4[0], hi4[1], hi4[2], hi4[3]));
                 st4(dlp + i, make_float4(lo4[0], lo4[1], lo4[2], lo4[3]));
+              }
               }
             }
           }
@@ -349,7 +411,7 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 __global__ void pair_rbf_split_kernel(const float* __restrict__ pair_r, const int* __restrict__ num_unique, int max_pairs,
                                       int R, int K_pad, int rows_per_pair, const float* __restrict__ means,
                                       const float* __restrict__ betas, float alpha, float lo, float hi,
-                                      float* __restrict__ a_hi, float* __restrict__ a_lo) {
+                                      float* __restrict__ a_hi, float* __restrict__ a_lo, int f16) {
   const int n_pairs = min(*num_unique, max_pairs);
   const long long total = (long long)n_pairs * K_pad;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -363,6 +425,13 @@ __global__ void pair_rbf_split_kernel(const float* __restrict__ pair_r, const in
       tn::expnorm_rbf(u, alpha, c0, dc0, means[k], betas[k], &v, &dv);
     }
     const size_t r0 = (size_t)p * rows_per_pair * K_pad + k;
+    if (f16) {
+      __half* hh = reinterpret_cast<__half*>(a_hi); __half* hl = reinterpret_cast<__half*>(a_lo);
+      __half x = __float2half_rn(v);
+      hh[r0] = x; hl[r0] = __float2half_rn(v - __half2float(x));
+      if (rows_per_pair == 2) { x = __float2half_rn(dv); hh[r0 + K_pad] = x; hl[r0 + K_pad] = __float2half_rn(dv - __half2float(x)); }
+      continue;
+    }
     float h = tf32_rna(v);
     a_hi[r0] = h; a_lo[r0] = tf32_rna(v - h);
     if (rows_per_pair == 2) { h = tf32_rna(dv); a_hi[r0 + K_pad] = h; a_lo[r0 + K_pad] = tf32_rna(dv - h); }
@@ -401,14 +470,14 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // [rows, K] fp32 row-major, box = [box_rows, 32 cols], 128 B swizzle
-static int make_map(CUtensorMap* m, const float* base, int rows, int K, int box_rows) {
+static int make_map(CUtensorMap* m, const float* base, int rows, int K, int box_rows, int f16 = 0) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { tmd_set_error("cuTensorMapEncodeTiled unavailable"); return TMD_ERR_CUDA; }
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)K * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)K * (f16 ? 2 : 4)};
+  cuuint32_t box[2] = {(cuuint32_t)(f16 ? 2 * BK : BK), (cuuint32_t)box_rows};   // 128 bytes of K per row
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+  CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { tmd_set_error("cuTensorMapEncodeTiled failed"); return TMD_ERR_CUDA; }
@@ -437,14 +506,15 @@ extern "C" {
 //                              rows_pad = roundup(max_pairs * (out_fp ? 2 : 1), 128)
 int tmd_pair_rbf_split(const float* pair_r, const int* num_unique, int max_pairs, int R, int rows_per_pair,
                        const float* means, const float* betas, double alpha, double lo, double hi, float* a_hi,
-                       float* a_lo, void* stream) {
+                       float* a_lo, int use_f16, void* stream) {
   TMD_REQUIRE(pair_r && num_unique && means && betas && a_hi && a_lo, "pair_rbf_split: null pointer");
   TMD_REQUIRE(rows_per_pair == 1 || rows_per_pair == 2, "pair_rbf_split: rows_per_pair must be 1 or 2");
   if (max_pairs == 0) return TMD_OK;
-  const int K0 = ((R + BK - 1) / BK) * BK;
+  const int bk = use_f16 ? 2 * BK : BK;
+  const int K0 = ((R + bk - 1) / bk) * bk;
   const long long total = (long long)max_pairs * K0;
   pair_rbf_split_kernel<<<tmd_blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      pair_r, num_unique, max_pairs, R, K0, rows_per_pair, means, betas, (float)alpha, (float)lo, (float)hi, a_hi, a_lo);
+      pair_r, num_unique, max_pairs, R, K0, rows_per_pair, means, betas, (float)alpha, (float)lo, (float)hi, a_hi, a_lo, use_f16);
   return tmd_check_launch("pair_rbf_split");
 }
 
@@ -452,7 +522,7 @@ int tmd_pair_chain_tc(const float* pair_r, const int* num_unique, int max_pairs,
                       const float* const* W_lo, const float* const* bias, const int* dims, int n_layers, int act,
                       int mul_cutoff, const float* means, const float* betas, double alpha, double lo, double hi,
                       const float* rbf_hi, const float* rbf_lo, float* act_a_hi, float* act_a_lo, float* act_b_hi,
-                      float* act_b_lo, float* out_f, float* out_fp, void* stream) {
+                      float* act_b_lo, float* out_f, float* out_fp, int use_f16, void* stream) {
   TMD_REQUIRE(pair_r && num_unique && W_hi && W_lo && bias && dims && means && betas && out_f, "pair_chain_tc: null pointer");
   TMD_REQUIRE((rbf_hi == nullptr) == (rbf_lo == nullptr), "pair_chain_tc: rbf_hi / rbf_lo must be given together");
   TMD_REQUIRE(act_a_hi && act_a_lo && act_b_hi && act_b_lo, "pair_chain_tc: null workspace");
@@ -462,11 +532,12 @@ int tmd_pair_chain_tc(const float* pair_r, const int* num_unique, int max_pairs,
   const int rpp = out_fp ? 2 : 1;
   const int rows_pad = ((max_pairs * rpp + BM - 1) / BM) * BM;
   const int R = dims[0];
-  const int K0 = ((R + BK - 1) / BK) * BK;
+  const int bk = use_f16 ? 2 * BK : BK;
+  const int K0 = ((R + bk - 1) / bk) * bk;
   if (!rbf_hi) {  // layer-0 operand not precomputed by tmd_pair_rbf_split: build it into workspace A
     const long long total = (long long)max_pairs * K0;
     pair_rbf_split_kernel<<<tmd_blocks_for(total, 256), 256, 0, st>>>(pair_r, num_unique, max_pairs, R, K0, rpp, means, betas,
-                                                                      (float)alpha, (float)lo, (float)hi, act_a_hi, act_a_lo);
+                                                                      (float)alpha, (float)lo, (float)hi, act_a_hi, act_a_lo, use_f16);
   }
   const float* in_hi = rbf_hi ? rbf_hi : act_a_hi;
   const float* in_lo = rbf_hi ? rbf_lo : act_a_lo;
@@ -477,19 +548,19 @@ int tmd_pair_chain_tc(const float* pair_r, const int* num_unique, int max_pairs,
     const int N = dims[l + 1];
     const int BN = pick_bn(N);
     TMD_REQUIRE(BN > 0, "pair_chain_tc: layer widths must be multiples of 64");
-    TMD_REQUIRE(l == n_layers - 1 || N % BK == 0, "pair_chain_tc: hidden widths must be multiples of 32");
+    TMD_REQUIRE(l == n_layers - 1 || N % bk == 0, "pair_chain_tc: hidden widths must be multiples of 32 (tf32) / 64 (f16)");
     TMD_REQUIRE(N <= MAX_N, "pair_chain_tc: layer wider than 1024");
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
-    if ((rc = make_map(&ma_hi, in_hi, rows_pad, K, BM))) return rc;
-    if ((rc = make_map(&ma_lo, in_lo, rows_pad, K, BM))) return rc;
-    if ((rc = make_map(&mb_hi, W_hi[l], N, K, BN))) return rc;
-    if ((rc = make_map(&mb_lo, W_lo[l], N, K, BN))) return rc;
+    if ((rc = make_map(&ma_hi, in_hi, rows_pad, K, BM, use_f16))) return rc;
+    if ((rc = make_map(&ma_lo, in_lo, rows_pad, K, BM, use_f16))) return rc;
+    if ((rc = make_map(&mb_hi, W_hi[l], N, K, BN, use_f16))) return rc;
+    if ((rc = make_map(&mb_lo, W_lo[l], N, K, BN, use_f16))) return rc;
     GemmParams P;
     P.K = K; P.N = N; P.BN = BN; P.rows_per_pair = rpp; P.act = act; P.final_layer = (l == n_layers - 1);
     P.mul_cutoff = mul_cutoff; P.lo = (float)lo; P.hi = (float)hi; P.bias = bias[l]; P.pair_r = pair_r;
     P.num_unique = num_unique; P.max_pairs = max_pairs; P.out_hi = o_hi; P.out_lo = o_lo; P.out_f = out_f; P.out_fp = out_fp;
-    P.seg_t1 = P.seg_t2 = 0x7fffffff; P.b_seg_rows = 0;
+    P.seg_t1 = P.seg_t2 = 0x7fffffff; P.b_seg_rows = 0; P.f16 = use_f16;
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * BN * BK * 4;
     const int max_items = (rows_pad / BM) * (N / BN);
     const int grid = max_items < 148 ? max_items : 148;
@@ -535,7 +606,7 @@ int tmd_irreps_linear_tc(const float* I, const float* A, const float* S, int N, 
   GemmParams P;
   P.K = F; P.N = F; P.BN = BN; P.rows_per_pair = 1; P.act = 0; P.final_layer = 1; P.mul_cutoff = 0; P.lo = 0.f; P.hi = 1.f;
   P.bias = zero_bias; P.pair_r = nullptr; P.num_unique = nullptr; P.max_pairs = rtot; P.out_hi = nullptr; P.out_lo = nullptr;
-  P.out_f = out; P.out_fp = nullptr; P.seg_t1 = r1 / BM; P.seg_t2 = r2 / BM; P.b_seg_rows = F;
+  P.out_f = out; P.out_fp = nullptr; P.seg_t1 = r1 / BM; P.seg_t2 = r2 / BM; P.b_seg_rows = F; P.f16 = 0;
   const int stage_bytes = 2 * A_TILE_BYTES + 2 * BN * BK * 4;
   const int items = (rtot / BM) * (F / BN);
   const int grid = items < 148 ? items : 148;

@@ -18,6 +18,8 @@ p = _lib.ptr
 
 # tcgen05 (3xTF32) radial chain; False selects the fp32 CUDA-core chain kernel (kept as the arbiter in tests)
 USE_TENSOR_CORES = True
+# fp16 (hi, lo) split terms instead of tf32 ones when a host-side bound proves every hidden activation / tangent fits fp16
+USE_F16_SPLIT = True
 
 
 class PairIndex(NamedTuple):
@@ -87,10 +89,25 @@ class RadialChain:
         widths = [sum(m.out_features for m in l) for l in self.layers]
         return len(widths) <= 3 and all(w % 64 == 0 and w <= 1024 for w in widths) and all(w % 32 == 0 for w in widths[:-1])
 
-    def tc_tensors(self):
-        """TF32 (round-to-nearest-away, = cvt.rna.tf32.f32) hi/lo split of every weight, K of layer 0 zero-padded to a
-        multiple of 32, plus the pointer tables the C ABI takes."""
+    def tc_tensors(self, f16: bool = False):
+        """hi/lo split of every weight -- TF32 (round-to-nearest-away, = cvt.rna.tf32.f32) or fp16 -- with K of layer 0
+        zero-padded to a multiple of 32 (64 for fp16), plus the pointer tables the C ABI takes."""
         self.tensors()
+        if f16:
+            if getattr(self, "_tc16_key", None) != self._key:
+                his, los = [], []
+                for wt in self._wt:
+                    w = wt.t().contiguous()
+                    kpad = (-w.shape[1]) % 64
+                    if kpad:
+                        w = torch.nn.functional.pad(w, (0, kpad))
+                    hi = w.half()
+                    his.append(hi.contiguous()); los.append((w - hi.float()).half().contiguous())
+                n = len(his)
+                mk = lambda ts: (ctypes.c_void_p * 3)(*([t.data_ptr() for t in ts] + [None] * (3 - n)))
+                self._tc16 = (his, los, mk(his), mk(los), mk(self._b))
+                self._tc16_key = self._key
+            return self._tc16
         if getattr(self, "_tc_key", None) != self._key:
             def rna(x):
                 b = x.contiguous().view(torch.int32)
@@ -108,6 +125,34 @@ class RadialChain:
             self._tc = (his, los, mk(his), mk(los), mk(self._b))
             self._tc_key = self._key
         return self._tc
+
+    def f16_safe(self, rbf_mod, lo: float, hi: float) -> bool:
+        """Conservative bound on |hidden activations| and |d/dr| of the chain (infinity-norm of each weight, |SiLU'| <= 1.1):
+        fp16 operands are used only if everything stays below 3e4 and hidden widths are multiples of 64."""
+        if not USE_F16_SPLIT:
+            return False
+        self.tensors()
+        key = (self._key, float(lo), float(hi), rbf_mod.means.data_ptr(), rbf_mod.means._version, rbf_mod.betas._version)
+        if getattr(self, "_f16_key", None) != key:
+            widths = [w.shape[1] for w in self._wt]
+            ok = all(w % 64 == 0 for w in widths[:-1])
+            if ok:
+                with torch.no_grad():
+                    r = torch.linspace(0.0, float(hi), 4097, device=self._wt[0].device, dtype=torch.float64)
+                    alpha = float(rbf_mod.alpha)
+                    c0 = 0.5 * (torch.cos(r * 3.141592653589793 / float(hi)) + 1.0)
+                    xd = c0[:, None] * torch.exp(-rbf_mod.betas.double() * (torch.exp(alpha * (float(lo) - r))[:, None] - rbf_mod.means.double()) ** 2)
+                    # |d rbf_k / dr| bound: finite differences on the fine grid are enough for a 2x-margin check
+                    t = float(((xd[1:] - xd[:-1]).abs().max() / (float(hi) / 4096)).item()) * 2.0
+                    v = 1.0
+                    ok = ok and t < 3e4
+                    for wt, b in zip(self._wt[:-1], self._b[:-1]):
+                        nrm = float(wt.abs().sum(0).max().item())        # wt is [K, N]: max over outputs of sum_k |W|
+                        v = nrm * v + float(b.abs().max().item())
+                        t = 1.1 * nrm * t
+                        ok = ok and v < 3e4 and t < 3e4
+            self._f16_ok, self._f16_key = bool(ok), key
+        return self._f16_ok
 
     def frozen(self) -> bool:
         return not any(t.requires_grad for l in self.layers for m in l for t in (m.weight, m.bias))
@@ -127,10 +172,12 @@ class RbfOperand(NamedTuple):
     hi: Tensor
     lo: Tensor
     rows_per_pair: int
+    f16: bool
 
 
-def precompute_rbf(pair_r: Tensor, num_unique: Tensor, rbf_mod, lo: float, hi: float, want_tangent: bool) -> Optional[RbfOperand]:
-    """Layer-0 tensor-core operand (rbf and d rbf/dr, TF32 split), shared by all radial chains of one frame."""
+def precompute_rbf(pair_r: Tensor, num_unique: Tensor, rbf_mod, lo: float, hi: float, want_tangent: bool,
+                   f16: bool = False) -> Optional[RbfOperand]:
+    """Layer-0 tensor-core operand (rbf and d rbf/dr, split into tf32 or fp16 terms), shared by all radial chains of a frame."""
     P = pair_r.shape[0]
     if not USE_TENSOR_CORES or P == 0:
         return None
@@ -140,8 +187,18 @@ def precompute_rbf(pair_r: Tensor, num_unique: Tensor, rbf_mod, lo: float, hi: f
     K0 = -(-R // 32) * 32
     buf = torch.empty(2, rows_pad, K0, device=pair_r.device, dtype=torch.float32)
     _lib.call("tmd_pair_rbf_split", p(pair_r), p(num_unique), P, R, rpp, p(rbf_mod.means.detach()), p(rbf_mod.betas.detach()),
-              float(rbf_mod.alpha), float(lo), float(hi), p(buf[0]), p(buf[1]), device=pair_r.device)
-    return RbfOperand(buf[0], buf[1], rpp)
+              float(rbf_mod.alpha), float(lo), float(hi), p(buf[0]), p(buf[1]), int(f16), device=pair_r.device)
+    return RbfOperand(buf[0], buf[1], rpp, bool(f16))
+
+
+def shared_rbf_operand(chains, pair_r: Tensor, num_unique: Tensor, rbf_mod, lo: float, hi: float, want_tangent: bool):
+    """One layer-0 operand for all radial chains of a frame when they agree on the operand type (fp16 / tf32)."""
+    if not USE_TENSOR_CORES or not all(c.supported_tc() for c in chains):
+        return None
+    modes = {c.f16_safe(rbf_mod, lo, hi) for c in chains}
+    if len(modes) != 1:
+        return None
+    return precompute_rbf(pair_r, num_unique, rbf_mod, lo, hi, want_tangent, f16=modes.pop())
 
 
 def run_chain(chain: RadialChain, pair_r: Tensor, num_unique: Tensor, rbf_mod, lo: float, hi: float, want_tangent: bool,
@@ -153,17 +210,18 @@ def run_chain(chain: RadialChain, pair_r: Tensor, num_unique: Tensor, rbf_mod, l
     f = torch.empty(P, n_last, device=pair_r.device, dtype=torch.float32)
     fp = torch.empty_like(f) if want_tangent else None
     if USE_TENSOR_CORES and chain.supported_tc() and P > 0:
-        his, los, p_hi, p_lo, p_b = chain.tc_tensors()
+        f16 = chain.f16_safe(rbf_mod, lo, hi)
+        his, los, p_hi, p_lo, p_b = chain.tc_tensors(f16)
         rows_pad = -(-(P * (2 if want_tangent else 1)) // 128) * 128
         width = max([his[0].shape[1]] + [w.shape[1] for w in wt[:-1]])
         ws = torch.empty(4, rows_pad, width, device=pair_r.device, dtype=torch.float32)
-        if rbf_op is not None and rbf_op.rows_per_pair != (2 if want_tangent else 1):
+        if rbf_op is not None and (rbf_op.rows_per_pair != (2 if want_tangent else 1) or rbf_op.f16 != f16):
             rbf_op = None
         _lib.call("tmd_pair_chain_tc", p(pair_r), p(num_unique), P, ctypes.cast(p_hi, ctypes.c_void_p),
                   ctypes.cast(p_lo, ctypes.c_void_p), ctypes.cast(p_b, ctypes.c_void_p), ctypes.cast(dims, ctypes.c_void_p),
                   len(wt), int(chain.act), int(chain.mul_cutoff), p(rbf_mod.means.detach()), p(rbf_mod.betas.detach()),
                   float(rbf_mod.alpha), float(lo), float(hi), p(rbf_op.hi) if rbf_op else None, p(rbf_op.lo) if rbf_op else None,
-                  p(ws[0]), p(ws[1]), p(ws[2]), p(ws[3]), p(f), p(fp), device=pair_r.device)
+                  p(ws[0]), p(ws[1]), p(ws[2]), p(ws[3]), p(f), p(fp), int(f16), device=pair_r.device)
         return f, fp
     if not chain.supported_ffma():
         raise RuntimeError("radial chain widths are supported by neither the tcgen05 nor the fp32 chain kernel")

@@ -239,8 +239,9 @@ class TensorNet(nn.Module):
         if use_fused:
             pair_r = fused.pair_distances(dist, pidx, P)
             # rbf(r) and d rbf/dr once per frame: the layer-0 tensor-core operand of every radial chain
-            rbf_op = fused.precompute_rbf(pair_r.detach(), pidx.num_unique, self.distance_expansion, self.cutoff_lower,
-                                          self.cutoff_upper, pair_r.requires_grad)
+            chains = [self.tensor_embedding.radial_chain()] + [l.radial_chain() for l in self.layers]
+            rbf_op = fused.shared_rbf_operand(chains, pair_r.detach(), pidx.num_unique, self.distance_expansion,
+                                              self.cutoff_lower, self.cutoff_upper, pair_r.requires_grad)
             fast = (dist, pair_r, pidx, self.distance_expansion, rbf_op)
             X = self.tensor_embedding(z, g, None, None, None, rhat, None, fast=fast)
             for layer in self.layers:
