@@ -309,11 +309,14 @@ def main():
         # = 270 336 flop per evaluated row at F=128, R=32); the 3xTF32 split executes 3x this on the tensor pipe
         flops = 2 * Pn * 2 * (R * F + F * 2 * F + 2 * F * 3 * F)
         ach_tf = flops / (c_ms * 1e-3) / 1e12
-        roofline = {"kernel": "gemm3x_tf32_kernel x3 (+ pair_rbf_split): tcgen05 radial chain of one interaction layer, value + d/dr on unique pairs",
+        f16_mode = bool(chain.supported_tc() and chain.f16_safe(rep.distance_expansion, 0.0, hp["cutoff_upper"]))
+        split_div = 3.0 if f16_mode else 6.0   # 3 split MMAs per product; tf32 additionally runs at half the 16-bit rate
+        roofline = {"kernel": "gemm3x_tf32_kernel x3: tcgen05 radial chain of one interaction layer (3 split-term GEMMs), value + d/dr on unique pairs",
                     "bound": "tensor", "achieved": ach_tf, "peak": tc_peak, "peak_source": how + " dense bf16 burst", "unit": "TFLOP/s",
-                    "frac": ach_tf / tc_peak, "frac_of_3xtf32_ceiling": ach_tf / (tc_peak / 6.0),
-                    "note": "fp32-parity path: TF32 runs at 1/2 the bf16 rate and each product needs 3 split MMAs, so the ceiling for this kernel is peak/6",
-                    "traffic": 4.240e9, "traffic_source": "ncu --set full r01 (dram read+write summed over the 3 GEMM launches of one chain call, profiles/r01_gemm3x_ncu.md)",
+                    "frac": ach_tf / tc_peak, "frac_of_split_ceiling": ach_tf / (tc_peak / split_div),
+                    "operands": "fp16 (hi, lo) split terms" if f16_mode else "tf32 (hi, lo) split terms",
+                    "note": f"fp32-parity path: every product needs 3 split MMAs (lo.hi + hi.lo + hi.hi), so the tensor ceiling of this kernel is peak/{split_div:.0f}",
+                    "traffic": (2.56e9 if f16_mode else 4.240e9), "traffic_source": "ncu --set full r01 (dram read+write summed over the 3 GEMM launches of one chain call, profiles/r01_gemm3x_ncu.md)",
                     "algorithmic_flops": flops, "kernel_ms": c_ms, "pairs": Pn}
         # ---- secondary: interaction message passing forward (a7), HBM/L2-gather bound ----
         I_, A_, S_ = (torch.randn(N, k, F, device=dev) for k in (1, 3, 5))
