@@ -316,7 +316,7 @@ def main():
                     "frac": ach_tf / tc_peak, "frac_of_split_ceiling": ach_tf / (tc_peak / split_div),
                     "operands": "fp16 (hi, lo) split terms" if f16_mode else "tf32 (hi, lo) split terms",
                     "note": f"fp32-parity path: every product needs 3 split MMAs (lo.hi + hi.lo + hi.hi), so the tensor ceiling of this kernel is peak/{split_div:.0f}",
-                    "traffic": (2.56e9 if f16_mode else 4.240e9), "traffic_source": "ncu --set full r01 (dram read+write summed over the 3 GEMM launches of one chain call, profiles/r01_gemm3x_ncu.md)",
+                    "traffic": (2.53e9 if f16_mode else 4.240e9), "traffic_source": "ncu --set full r01 (dram read+write summed over the 3 GEMM launches of one chain call, profiles/r01_gemm3x_ncu.md)",
                     "algorithmic_flops": flops, "kernel_ms": c_ms, "pairs": Pn}
         # ---- secondary: interaction message passing forward (a7), HBM/L2-gather bound ----
         I_, A_, S_ = (torch.randn(N, k, F, device=dev) for k in (1, 3, 5))
