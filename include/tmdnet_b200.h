@@ -185,6 +185,11 @@ int tmd_pair_rbf_split(const float* pair_r, const int* num_unique, int max_pairs
 int tmd_mp_pair_bwd(const float* YI, const float* YA, const float* YS, const float* dMI, const float* dMA,
                     const float* dMS, const float* f, const float* fp, const int* pid, const int* nbr_j,
                     const int* indptr, int n, int F, float* dYI, float* dYA, float* dYS, float* d_pair_r, void* stream);
+/* single-pass variant: the radial gradient is emitted per DIRECTED slot, g_dist[k] = <f'_p, dM_j * Y_b> for k = (b, j); the two
+ * slots of a pair together carry dE/dr_p (the position-gradient kernel combines them).  Gathers only dM_j. */
+int tmd_mp_edge_bwd(const float* YI, const float* YA, const float* YS, const float* dMI, const float* dMA,
+                    const float* dMS, const float* f, const float* fp, const int* pid, const int* nbr_j,
+                    const int* indptr, int n, int F, float* dYI, float* dYA, float* dYS, float* g_dist, void* stream);
 int tmd_embed_fwd(const float* rhat, const float* dist, const float* dp, const int* pid, const int* nbr_j,
                   const int* indptr, const float* U, const float* V, double lo, double hi, int n, int F, float* oI,
                   float* oA, float* oS, void* stream);

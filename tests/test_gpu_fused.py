@@ -101,7 +101,7 @@ def test_fused_interaction_message_passing():
     Y = [torch.randn(n, k, F, device=dev, requires_grad=True) for k in (1, 3, 5)]
     dist = g.dist[:E]
     pair_r = fused.pair_distances(dist, pidx, P)
-    M = fused.interaction_message_passing(Y, pair_r, chain, rbf, 0.0, 5.0, g, pidx)
+    M = fused.interaction_message_passing(Y, dist, pair_r.detach(), chain, rbf, 0.0, 5.0, g, pidx)
     # reference: per directed edge
     x = rbf(dist)
     for l in lins:

@@ -322,6 +322,112 @@ __global__ void __launch_bounds__(256, 2) mp_pair_bwd_kernel(CIrr Y, CIrr dM, co
   }
 }
 
+// Single-pass variant of the backward above, emitting the radial gradient per DIRECTED slot instead of per pair:
+//   dY_b = sum_k f_p dM_j     and     g_dist[k] = < f'_p , dM_j * Y_b >     for slot k = (b, j)
+// g_dist[k] is the contribution of the transposed edge (j <- b) to dE/dr_p; the position-gradient kernel combines
+// g_dist[k] and g_dist[rev k] (g_e - g_rev(e) with opposite unit vectors), which sums the two halves of the pair.
+// Only dM_j is gathered (Y_j is not needed at all): half the gather traffic of mp_pair_bwd_kernel.
+__global__ void __launch_bounds__(256, 2) mp_edge_bwd_kernel(CIrr Y, CIrr dM, const float* __restrict__ f,
+                                                             const float* __restrict__ fp, const int* __restrict__ pid,
+                                                             const int* __restrict__ nbr_j, const int* __restrict__ indptr,
+                                                             int n, int F, MIrr dY, float* __restrict__ g_dist) {
+  extern __shared__ float4 sm4[];
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wid = threadIdx.x >> 5;
+  const int chunks = (F + 127) / 128;
+  float4* myb = sm4 + (size_t)wid * 9 * chunks * 32;   // own Y_b: [chunk][9][32 lanes]
+  for (int b = blockIdx.x * wpb + wid; b < n; b += gridDim.x * wpb) {
+    const int k0 = indptr[b], k1 = indptr[b + 1];
+    __syncwarp();
+    for (int ch = 0; ch < chunks; ++ch) {
+      const int h = ch * 128 + lane * 4;
+      if (h < F) {
+        float4 t[9];
+        ld9(Y, b, F, h, t);
+#pragma unroll
+        for (int c = 0; c < 9; ++c) myb[(ch * 9 + c) * 32 + lane] = t[c];
+      }
+    }
+    __syncwarp();
+    if (chunks == 1) {
+      const int h = lane * 4;
+      const bool on = h < F;
+      const float4* yb = myb + lane;
+      float4 acc[9];
+#pragma unroll
+      for (int c = 0; c < 9; ++c) acc[c] = zero4();
+#pragma unroll 2
+      for (int k = k0; k < k1; ++k) {
+        const long long j = nbr_j[k], p = pid[k];
+        float t = 0.f;
+        if (on) {
+          const float* fe = f + p * 3 * (long long)F + h;
+          const float4 w1 = ldg4(fe), w2 = ldg4(fe + F), w3 = ldg4(fe + 2 * F);
+          float4 dj[9];
+          ld9(dM, j, F, h, dj);
+          acc[0] = fma4(w1, dj[0], acc[0]);
+          float4 g2 = zero4(), g3 = zero4();
+#pragma unroll
+          for (int c = 1; c < 4; ++c) { acc[c] = fma4(w2, dj[c], acc[c]); g2 = fma4(dj[c], yb[c * 32], g2); }
+#pragma unroll
+          for (int c = 4; c < 9; ++c) { acc[c] = fma4(w3, dj[c], acc[c]); g3 = fma4(dj[c], yb[c * 32], g3); }
+          if (fp) {
+            const float* fpe = fp + p * 3 * (long long)F + h;
+            t = dot4(ldg4(fpe), mul4(dj[0], yb[0])) + dot4(ldg4(fpe + F), g2) + dot4(ldg4(fpe + 2 * F), g3);
+          }
+        }
+        if (fp) {
+          t = warp_sum(t);
+          if (lane == 0) g_dist[k] = (j == b) ? 0.f : t;
+        }
+      }
+      if (on) st9(dY, b, F, h, acc);
+    } else {
+      for (int ch = 0; ch < chunks; ++ch) {
+        const int h = ch * 128 + lane * 4;
+        if (h >= F) continue;
+        float4 acc[9];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) acc[c] = zero4();
+        for (int k = k0; k < k1; ++k) {
+          const long long j = nbr_j[k], p = pid[k];
+          const float* fe = f + p * 3 * (long long)F + h;
+          const float4 w1 = ldg4(fe), w2 = ldg4(fe + F), w3 = ldg4(fe + 2 * F);
+          float4 dj[9];
+          ld9(dM, j, F, h, dj);
+          acc[0] = fma4(w1, dj[0], acc[0]);
+#pragma unroll
+          for (int c = 1; c < 4; ++c) acc[c] = fma4(w2, dj[c], acc[c]);
+#pragma unroll
+          for (int c = 4; c < 9; ++c) acc[c] = fma4(w3, dj[c], acc[c]);
+        }
+        st9(dY, b, F, h, acc);
+      }
+      if (fp) {
+        for (int k = k0; k < k1; ++k) {
+          const long long j = nbr_j[k], p = pid[k];
+          float t = 0.f;
+          for (int ch = 0; ch < chunks; ++ch) {
+            const int h = ch * 128 + lane * 4;
+            if (h >= F) continue;
+            const float4* yb = myb + (ch * 9) * 32 + lane;
+            float4 dj[9];
+            ld9(dM, j, F, h, dj);
+            float4 g2 = zero4(), g3 = zero4();
+#pragma unroll
+            for (int c = 1; c < 4; ++c) g2 = fma4(dj[c], yb[c * 32], g2);
+#pragma unroll
+            for (int c = 4; c < 9; ++c) g3 = fma4(dj[c], yb[c * 32], g3);
+            const float* fpe = fp + p * 3 * (long long)F + h;
+            t += dot4(ldg4(fpe), mul4(dj[0], yb[0])) + dot4(ldg4(fpe + F), g2) + dot4(ldg4(fpe + 2 * F), g3);
+          }
+          t = warp_sum(t);
+          if (lane == 0) g_dist[k] = (j == b) ? 0.f : t;
+        }
+      }
+    }
+  }
+}
+
 // embedding: w_e[k,:] = C(r_e) (U_i + V_j) dp_p[k,:]  accumulated into I/A/S of atom i  (tensornet.py:554-585)
 __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict__ rhat, const float* __restrict__ dist,
                                                         const float* __restrict__ dp, const int* __restrict__ pid,
@@ -487,6 +593,24 @@ int tmd_mp_pair_bwd(const float* YI, const float* YA, const float* YS, const flo
   mp_pair_bwd_kernel<<<tmd_blocks_for((long long)n * 32, 256), 256, smem, (cudaStream_t)stream>>>(
       CIrr{YI, YA, YS}, CIrr{dMI, dMA, dMS}, f, fp, pid, nbr_j, indptr, n, F, MIrr{dYI, dYA, dYS}, d_pair_r);
   return tmd_check_launch("mp_pair_bwd");
+}
+
+// Single-pass backward of tmd_mp_fwd with pair-indexed weights: dY and, if fp != NULL, g_dist[k] = <f'_p, dM_j * Y_b> per
+// directed slot k = (b, j) (the two slots of a pair together carry dE/dr_p; self-loop slots get 0).
+int tmd_mp_edge_bwd(const float* YI, const float* YA, const float* YS, const float* dMI, const float* dMA,
+                    const float* dMS, const float* f, const float* fp, const int* pid, const int* nbr_j,
+                    const int* indptr, int n, int F, float* dYI, float* dYA, float* dYS, float* g_dist, void* stream) {
+  TMD_REQUIRE(F > 0 && F % 4 == 0, "mp_edge_bwd: F must be a positive multiple of 4");
+  TMD_REQUIRE(YI && YA && YS && dMI && dMA && dMS && f && pid && nbr_j && indptr && dYI && dYA && dYS, "mp_edge_bwd: null pointer");
+  TMD_REQUIRE(!fp || g_dist, "mp_edge_bwd: fp given without g_dist");
+  if (n == 0) return TMD_OK;
+  const int chunks = (F + 127) / 128;
+  const size_t smem = (size_t)8 * 9 * chunks * 32 * sizeof(float4);
+  TMD_REQUIRE(smem <= 200 * 1024, "mp_edge_bwd: F too large for the per-warp staging buffer");
+  cudaFuncSetAttribute(mp_edge_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  mp_edge_bwd_kernel<<<tmd_blocks_for((long long)n * 32, 256), 256, smem, (cudaStream_t)stream>>>(
+      CIrr{YI, YA, YS}, CIrr{dMI, dMA, dMS}, f, fp, pid, nbr_j, indptr, n, F, MIrr{dYI, dYA, dYS}, g_dist);
+  return tmd_check_launch("mp_edge_bwd");
 }
 
 int tmd_embed_fwd(const float* rhat, const float* dist, const float* dp, const int* pid, const int* nbr_j,

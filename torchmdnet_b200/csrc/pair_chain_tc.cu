@@ -138,6 +138,92 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(r);
 }
 
+// raw SFU ops (flush-to-zero, no range fix-ups): sigmoid(z) = rcp(1 + ex2(-z log2 e)); +-inf behave (sg -> 0 / 1)
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+struct JvpOut {
+  float* out_f; float* out_fp; float* out_hi; float* out_lo;
+  size_t pair, row_v; int N, cb; bool valid;
+};
+
+// (value, tangent) lane-pair exchange + bias + SiLU (+ cutoff): v = this lane's 32 accumulator columns; on return h / dh hold the
+// activation and its tangent for this lane's 16 columns (value lane: columns 0..15 of the chunk, tangent lane: 16..31).
+template <bool ACT, bool CUT>
+__device__ __forceinline__ void jvp_math(const uint32_t* v, bool tangent, const float* bias16, float cut, float dcut, float* h, float* dh) {
+  float bb[16];
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(bias16 + i);
+    bb[i] = b4.x; bb[i + 1] = b4.y; bb[i + 2] = b4.z; bb[i + 3] = b4.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float send = __uint_as_float(tangent ? v[i] : v[16 + i]);
+    const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+    const float z = (tangent ? recv : __uint_as_float(v[i])) + bb[i];
+    const float t = tangent ? __uint_as_float(v[16 + i]) : recv;
+    float hh = z, dd = t;
+    if (ACT) {
+      const float sg = rcp_ftz(1.f + ex2_ftz(-1.4426950408889634f * z));   // ~1e-7 relative, far inside the split-term budget
+      hh = z * sg;
+      dd = sg * fmaf(z, 1.f - sg, 1.f) * t;
+    }
+    if (CUT) { dd = fmaf(dd, cut, hh * dcut); hh *= cut; }
+    h[i] = hh; dh[i] = dd;
+  }
+}
+
+// One 32-column accumulator chunk of the (value, tangent) row pair held by lanes (2m, 2m+1): the lanes swap halves so that each
+// evaluates the activation once for 16 columns and produces both h and dh for them.
+template <bool ACT, bool FINAL, bool CUT, bool F16>
+__device__ __forceinline__ void jvp_chunk(const uint32_t* v, bool tangent, const float* bias16, float cut, float dcut, const JvpOut& o) {
+  float h[16], dh[16];
+  jvp_math<ACT, FINAL && CUT>(v, tangent, bias16, cut, dcut, h, dh);
+  if (!o.valid) return;
+  if (FINAL) {
+    float* d0 = o.out_f + o.pair * o.N + o.cb;
+    float* d1 = o.out_fp + o.pair * o.N + o.cb;
+    st8(d0, h); st8(d0 + 8, h + 8);
+    st8(d1, dh); st8(d1 + 8, dh + 8);
+    return;
+  }
+  const size_t o0 = o.row_v * o.N + o.cb, o1 = o0 + o.N;
+  if (F16) {
+    // fp16 (hi, lo): 16 columns = 32 bytes = one 256-bit store per (row, array)
+    __half* oh = reinterpret_cast<__half*>(o.out_hi);
+    __half* ol = reinterpret_cast<__half*>(o.out_lo);
+    float a[8], b[8], c[8], d[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const __half2 hh = __floats2half2_rn(h[2 * u], h[2 * u + 1]);
+      const float2 hf = __half22float2(hh);
+      const __half2 hl = __floats2half2_rn(h[2 * u] - hf.x, h[2 * u + 1] - hf.y);
+      const __half2 dh2 = __floats2half2_rn(dh[2 * u], dh[2 * u + 1]);
+      const float2 df = __half22float2(dh2);
+      const __half2 dl = __floats2half2_rn(dh[2 * u] - df.x, dh[2 * u + 1] - df.y);
+      a[u] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&hh));
+      b[u] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&hl));
+      c[u] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&dh2));
+      d[u] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&dl));
+    }
+    st8(reinterpret_cast<float*>(oh + o0), a); st8(reinterpret_cast<float*>(ol + o0), b);
+    st8(reinterpret_cast<float*>(oh + o1), c); st8(reinterpret_cast<float*>(ol + o1), d);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; i += 8) {
+      float a[8], b[8], c[8], d[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        a[u] = tf32_rna(h[i + u]);  b[u] = tf32_rna(h[i + u] - a[u]);
+        c[u] = tf32_rna(dh[i + u]); d[u] = tf32_rna(dh[i + u] - c[u]);
+      }
+      st8(o.out_hi + o0 + i, a); st8(o.out_lo + o0 + i, b);
+      st8(o.out_hi + o1 + i, c); st8(o.out_lo + o1 + i, d);
+    }
+  }
+}
+
 struct GemmParams {
   int K;            // padded to a multiple of 32
   int N;            // output width, multiple of BN
@@ -158,6 +244,7 @@ struct GemmParams {
   int f16;              // operands are fp16 (hi, lo) pairs (K-block = 64 elements) instead of tf32 (32 elements)
   int seg_t1, seg_t2;   // grouped GEMM: m-tiles [0,t1) use weight block 0, [t1,t2) block 1, [t2,..) block 2
   int b_seg_rows;       // rows of one weight block in the stacked B tensor map
+  int dbg;              // dev probe (TMD_TC_DBG): 1 epilogue off, 2 MMA off, 3 no global stores, 4 no A loads
 };
 
 template <int STAGES>
@@ -209,8 +296,8 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + (size_t)stage * stage_bytes;
           mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-          tma_load_2d(&map_a_hi, &full_bar[stage], st, kb * bk_el, m_tile * BM);
-          tma_load_2d(&map_a_lo, &full_bar[stage], st + A_TILE_BYTES, kb * bk_el, m_tile * BM);
+          tma_load_2d(&map_a_hi, &full_bar[stage], st, kb * bk_el, P.dbg == 4 ? 0 : m_tile * BM);
+          tma_load_2d(&map_a_lo, &full_bar[stage], st + A_TILE_BYTES, kb * bk_el, P.dbg == 4 ? 0 : m_tile * BM);
           tma_load_2d(&map_b_hi, &full_bar[stage], st + 2 * A_TILE_BYTES, kb * bk_el, b_row);
           tma_load_2d(&map_b_lo, &full_bar[stage], st + 2 * A_TILE_BYTES + b_tile_bytes, kb * bk_el, b_row);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -229,7 +316,7 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
-        if (elect_one()) {
+        if (P.dbg != 2 && elect_one()) {
           const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + A_TILE_BYTES);
           const uint64_t b_hi = make_desc_sw128(st + 2 * A_TILE_BYTES), b_lo = make_desc_sw128(st + 2 * A_TILE_BYTES + b_tile_bytes);
@@ -280,77 +367,25 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
-      for (int c0 = sub * 32; c0 < P.BN; c0 += 32 * (EPI_WARPS / 4)) {
+      for (int c0 = sub * 32; c0 < P.BN && P.dbg != 1; c0 += 32 * (EPI_WARPS / 4)) {
         uint32_t v[32];
         tmem_ld32(t_row + (uint32_t)c0, v);
         const int col0 = n_blk * P.BN + c0;
         if (jvp) {
           const int cb = col0 + (tangent ? 16 : 0);        // this lane's 16 columns
-          float h[16], dh[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float send = __uint_as_float(tangent ? v[i] : v[16 + i]);
-            const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-            const float z = (tangent ? recv : __uint_as_float(v[i])) + bias_s[cb + i];
-            const float t = tangent ? __uint_as_float(v[16 + i]) : recv;
-            float hh = z, dd = t;
-            if (P.act) {
-              // sigmoid on the SFU (ex2 + rcp): ~1e-7 relative, far inside the 3xTF32 error budget
-              const float sg = __fdividef(1.f, 1.f + __expf(-z));
-              hh = z * sg;
-              dd = sg * fmaf(z, 1.f - sg, 1.f) * t;
-            }
-            if (P.final_layer && P.mul_cutoff) { dd = fmaf(dd, cut, hh * dcut); hh *= cut; }
-            h[i] = hh; dh[i] = dd;
-          }
-          if (valid) {
-            if (P.final_layer) {
-              float* d0 = P.out_f + (size_t)pair * P.N + cb;
-              float* d1 = P.out_fp + (size_t)pair * P.N + cb;
-              st8(d0, h); st8(d0 + 8, h + 8);
-              st8(d1, dh); st8(d1 + 8, dh + 8);
-            } else {
-              const size_t o0 = (size_t)row_v * P.N + cb, o1 = o0 + P.N;
-              if (P.f16) {
-                // fp16 (hi, lo): 16 columns = 32 bytes = one 256-bit store per (row, array)
-                __half* oh = reinterpret_cast<__half*>(P.out_hi);
-                __half* ol = reinterpret_cast<__half*>(P.out_lo);
-                float a[8], b[8], c[8], d[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                  const __half2 hh = __floats2half2_rn(h[2 * u], h[2 * u + 1]);
-                  const float2 hf = __half22float2(hh);
-                  const __half2 hl = __floats2half2_rn(h[2 * u] - hf.x, h[2 * u + 1] - hf.y);
-                  const __half2 dh2 = __floats2half2_rn(dh[2 * u], dh[2 * u + 1]);
-                  const float2 df = __half22float2(dh2);
-                  const __half2 dl = __floats2half2_rn(dh[2 * u] - df.x, dh[2 * u + 1] - df.y);
-                  a[u] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&hh));
-                  b[u] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&hl));
-                  c[u] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&dh2));
-                  d[u] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&dl));
-                }
-                st8(reinterpret_cast<float*>(oh + o0), a); st8(reinterpret_cast<float*>(ol + o0), b);
-                st8(reinterpret_cast<float*>(oh + o1), c); st8(reinterpret_cast<float*>(ol + o1), d);
-              } else
-#pragma unroll
-              for (int i = 0; i < 16; i += 8) {
-                float a[8], b[8], c[8], d[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                  a[u] = tf32_rna(h[i + u]);  b[u] = tf32_rna(h[i + u] - a[u]);
-                  c[u] = tf32_rna(dh[i + u]); d[u] = tf32_rna(dh[i + u] - c[u]);
-                }
-                st8(P.out_hi + o0 + i, a); st8(P.out_lo + o0 + i, b);
-                st8(P.out_hi + o1 + i, c); st8(P.out_lo + o1 + i, d);
-              }
-            }
-          }
+          const JvpOut o{P.out_f, P.out_fp, P.out_hi, P.out_lo, (size_t)pair, (size_t)row_v, P.N, cb, valid && P.dbg != 3};
+          const float* bs = bias_s + cb;
+          if (P.final_layer) {
+            if (P.mul_cutoff) { if (P.act) jvp_chunk<true, true, true, false>(v, tangent, bs, cut, dcut, o); else jvp_chunk<false, true, true, false>(v, tangent, bs, cut, dcut, o); }
+            else              { if (P.act) jvp_chunk<true, true, false, false>(v, tangent, bs, cut, dcut, o); else jvp_chunk<false, true, false, false>(v, tangent, bs, cut, dcut, o); }
+          } else if (P.f16)   { if (P.act) jvp_chunk<true, false, false, true>(v, tangent, bs, cut, dcut, o); else jvp_chunk<false, false, false, true>(v, tangent, bs, cut, dcut, o); }
+          else                { if (P.act) jvp_chunk<true, false, false, false>(v, tangent, bs, cut, dcut, o); else jvp_chunk<false, false, false, false>(v, tangent, bs, cut, dcut, o); }
         } else {
           float o[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float z = __uint_as_float(v[i]) + bias_s[col0 + i];
-            float res = P.act ? z * __fdividef(1.f, 1.f + __expf(-z)) : z;
+            float res = P.act ? z * rcp_ftz(1.f + ex2_ftz(-1.4426950408889634f * z)) : z;
             if (P.final_layer && P.mul_cutoff) res *= cut;
             o[i] = res;
           }
@@ -396,6 +431,274 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused tail of the radial chain: layers 2 and 3 in ONE kernel, the 2F-wide hidden activation h2 never leaves the SM.
+//   h1 [rows, F] (fp16 hi/lo, written by the layer-1 launch of gemm3x)  --W2-->  h2 = SiLU(.)  --W3-->  f, f' (fp32, x cutoff)
+// Per 128-row tile (64 pairs x (value, tangent)):
+//   SMEM  A3 : the layer-3 A operand, 2F/64 K-blocks x (hi 16 KB + lo 16 KB) in the TMA SWIZZLE_128B K-major layout, WRITTEN BY
+//              THE EPILOGUE WARPS (st.shared + fence.proxy.async).  The h1 tile (layer-2 A operand, F/64 K-blocks) is TMA-loaded
+//              into the LAST F/64 K-blocks of the same region: it is dead once layer 2's MMAs retire, which is exactly when the
+//              second half of h2 is written there.
+//         ring: 3 slots of one weight K-block (NC rows x 128 B x (hi, lo)), streamed from L2 by TMA
+//   TMEM  [0, 2NC) layer-2 accumulator as two NC-column chunks, [2NC, 4NC) layer-3 accumulator chunks, double-buffered (NC = F)
+//   warps 0: weight TMA   1: MMA issuer   2: h1-tile TMA   3..18: epilogue (TMEM lane quarter = warp & 3, 32-column sub-chunk)
+// HBM traffic per chain call drops from 2.53 GB to ~1.4 GB (h2 is 1.13 GB of write + read).
+struct TailParams {
+  int F;                 // 64 or 128: K2 = F, N2 = 2F = K3, N3 = 3F
+  int mul_cutoff;
+  float lo, hi;
+  const float* bias2;    // [2F]
+  const float* bias3;    // [3F]
+  const float* pair_r;
+  const int* num_unique;
+  int max_pairs;
+  float* out_f;          // [P, 3F]
+  float* out_fp;
+  int dbg;               // dev probe (TMD_TC_DBG): 1 no global stores, 2 no shared-memory stores, 3 no epilogue math, 4 no MMA
+};
+
+constexpr int TAIL_EPI_WARPS = 16;
+constexpr int TAIL_THREADS = 96 + 32 * TAIL_EPI_WARPS;
+constexpr int TAIL_SLOTS = 3;
+constexpr int KBLK_BYTES = 2 * A_TILE_BYTES;   // one A K-block: hi + lo
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1)
+chain_tail_f16_kernel(const __grid_constant__ CUtensorMap map_h1_hi, const __grid_constant__ CUtensorMap map_h1_lo,
+                      const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
+                      const __grid_constant__ CUtensorMap map_w3_hi, const __grid_constant__ CUtensorMap map_w3_lo,
+                      TailParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int NC = P.F;
+  const int KB2 = P.F / 64, KB3 = 2 * P.F / 64;
+  uint8_t* a3 = smem;                                   // KB3 K-blocks
+  uint8_t* a2 = a3 + (size_t)(KB3 - KB2) * KBLK_BYTES;  // aliases the last KB2 K-blocks of a3
+  const int slot_bytes = NC * 128 * 2;
+  uint8_t* ring = a3 + (size_t)KB3 * KBLK_BYTES;
+  __shared__ __align__(8) uint64_t full_bar[TAIL_SLOTS], empty_bar[TAIL_SLOTS];
+  __shared__ __align__(8) uint64_t a2_full, a3_free, acc2_full[2], acc2_empty[2], a3_ready[2], acc3_full[2], acc3_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_pairs = min(*P.num_unique, P.max_pairs);
+  const int rows_valid = n_pairs * 2;
+  const int m_tiles = (rows_valid + BM - 1) / BM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TAIL_SLOTS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&a2_full, 1); mbar_init(&a3_free, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc2_full[a], 1); mbar_init(&acc2_empty[a], TAIL_EPI_WARPS); mbar_init(&a3_ready[a], TAIL_EPI_WARPS);
+      mbar_init(&acc3_full[a], 1); mbar_init(&acc3_empty[a], TAIL_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ weight stream: 2*KB2 + 3*KB3 slots per tile
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+        for (int g = 0; g < 5; ++g) {                    // g 0,1: layer-2 chunks; 2..4: layer-3 chunks
+          const bool l2 = g < 2;
+          const int kbs = l2 ? KB2 : KB3;
+          const int row0 = (l2 ? g : g - 2) * NC;
+          for (int kb = 0; kb < kbs; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = ring + (size_t)stage * slot_bytes;
+            mbar_expect_tx(&full_bar[stage], (uint32_t)slot_bytes);
+            tma_load_2d(l2 ? &map_w2_hi : &map_w3_hi, &full_bar[stage], st, kb * 64, row0);
+            tma_load_2d(l2 ? &map_w2_lo : &map_w3_lo, &full_bar[stage], st + slot_bytes / 2, kb * 64, row0);
+            if (++stage == TAIL_SLOTS) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ h1 tile -> the tail of the A3 region
+    if (elect_one()) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+        if (it > 0) mbar_wait(&a3_free, (uint32_t)((it - 1) & 1));   // layer-3 MMAs of the previous tile have retired
+        mbar_expect_tx(&a2_full, (uint32_t)(KB2 * KBLK_BYTES));
+        for (int kb = 0; kb < KB2; ++kb) {
+          tma_load_2d(&map_h1_hi, &a2_full, a2 + (size_t)kb * KBLK_BYTES, kb * 64, tile * BM);
+          tma_load_2d(&map_h1_lo, &a2_full, a2 + (size_t)kb * KBLK_BYTES + A_TILE_BYTES, kb * 64, tile * BM);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = make_idesc_f16(BM, NC);
+    int stage = 0; uint32_t phase = 0;
+    int it = 0, g3 = 0;
+    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+      const uint32_t tp = (uint32_t)(it & 1);
+      mbar_wait(&a2_full, tp);
+      for (int c = 0; c < 2; ++c) {                       // layer 2: D2[:, c*NC : (c+1)*NC]
+        mbar_wait(&acc2_empty[c], tp ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(c * NC);
+        for (int kb = 0; kb < KB2; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          if (P.dbg != 4 && elect_one()) {
+            const uint32_t sa = smem_u32(a2 + (size_t)kb * KBLK_BYTES);
+            const uint32_t sb = smem_u32(ring + (size_t)stage * slot_bytes);
+            const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + A_TILE_BYTES);
+            const uint64_t b_hi = make_desc_sw128(sb), b_lo = make_desc_sw128(sb + slot_bytes / 2);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adv = (uint64_t)((k * 32) >> 4);
+              umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+              umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+              umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+            }
+          }
+          __syncwarp();
+          if (elect_one()) umma_commit(&empty_bar[stage]);
+          __syncwarp();
+          if (++stage == TAIL_SLOTS) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) umma_commit(&acc2_full[c]);
+        __syncwarp();
+      }
+      for (int c = 0; c < 3; ++c, ++g3) {                 // layer 3: D3[:, c*NC : (c+1)*NC], A = h2 in shared memory
+        const int b = g3 & 1;
+        mbar_wait(&acc3_empty[b], (uint32_t)(((g3 >> 1) & 1) ^ 1));
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(2 * NC + b * NC);
+        for (int kb = 0; kb < KB3; ++kb) {
+          if (c == 0 && kb == 0) mbar_wait(&a3_ready[0], tp);          // first half of h2 written (and proxy-fenced)
+          if (c == 0 && kb == KB3 / 2) mbar_wait(&a3_ready[1], tp);    // second half
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          if (P.dbg != 4 && elect_one()) {
+            const uint32_t sa = smem_u32(a3 + (size_t)kb * KBLK_BYTES);
+            const uint32_t sb = smem_u32(ring + (size_t)stage * slot_bytes);
+            const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + A_TILE_BYTES);
+            const uint64_t b_hi = make_desc_sw128(sb), b_lo = make_desc_sw128(sb + slot_bytes / 2);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adv = (uint64_t)((k * 32) >> 4);
+              umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+              umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+              umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+            }
+          }
+          __syncwarp();
+          if (elect_one()) umma_commit(&empty_bar[stage]);
+          __syncwarp();
+          if (++stage == TAIL_SLOTS) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) umma_commit(&acc3_full[b]);
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&a3_free);              // every MMA reading this tile's A3 has retired
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps 3..18
+    const int q = warp & 3;
+    const int sub = (warp - 3) >> 2;                      // 32-column sub-chunk of an NC-column chunk (NC = 64: sub 2,3 idle)
+    const bool has_cols = sub * 32 < NC;
+    const int row_in_tile = q * 32 + lane;
+    const bool tangent = lane & 1;
+    const int r_v = row_in_tile & ~1;                     // value row of this lane's pair inside the tile
+    int it = 0, g3 = 0;
+    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+      const uint32_t tp = (uint32_t)(it & 1);
+      const int row_v = tile * BM + r_v;
+      const bool valid = row_v < rows_valid;
+      const int pair = row_v >> 1;
+      float cut = 1.f, dcut = 0.f;
+      if (P.mul_cutoff) {
+        const float r = valid ? __ldg(P.pair_r + pair) : 0.f;
+        tn::cosine_cutoff(r, P.lo, P.hi, &cut, &dcut);
+      }
+      for (int c = 0; c < 2; ++c) {                       // h2 chunk c -> A3 K-blocks
+        mbar_wait(&acc2_full[c], tp);
+        tcgen05_fence_after();
+        if (has_cols) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * NC + sub * 32), v);
+          const int kcol = c * NC + sub * 32 + (tangent ? 16 : 0);     // this lane's 16 columns of h2 = K index of layer 3
+          float h[16], dh[16];
+          if (P.dbg != 3) jvp_math<true, false>(v, tangent, P.bias2 + kcol, 1.f, 0.f, h, dh);
+          else { for (int i = 0; i < 16; ++i) { h[i] = __uint_as_float(v[i]); dh[i] = __uint_as_float(v[16 + i]); } }
+          uint8_t* kb_base = a3 + (size_t)(kcol >> 6) * KBLK_BYTES;
+          const int j0 = (kcol & 63) >> 3;                               // 16-byte chunk index inside the 128-byte row
+#pragma unroll
+          for (int rr = 0; rr < 2 && P.dbg != 2; ++rr) {                // rr 0: value row (h), 1: tangent row (dh)
+            const int r = r_v + rr;
+            const float* src = rr ? dh : h;
+            uint8_t* rowp = kb_base + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128;
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              uint32_t hi4[4], lo4[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float x0 = src[jj * 8 + 2 * u], x1 = src[jj * 8 + 2 * u + 1];
+                const __half2 hh = __floats2half2_rn(x0, x1);
+                const float2 hf = __half22float2(hh);
+                const __half2 hl = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                hi4[u] = *reinterpret_cast<const uint32_t*>(&hh);
+                lo4[u] = *reinterpret_cast<const uint32_t*>(&hl);
+              }
+              const int off = ((j0 + jj) ^ (r & 7)) * 16;
+              *reinterpret_cast<uint4*>(rowp + off) = make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
+              *reinterpret_cast<uint4*>(rowp + A_TILE_BYTES + off) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+            }
+          }
+        }
+        tcgen05_fence_before();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async proxy
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&acc2_empty[c]); mbar_arrive(&a3_ready[c]); }
+      }
+      for (int c = 0; c < 3; ++c, ++g3) {                 // f, f' chunk c -> HBM
+        const int b = g3 & 1;
+        mbar_wait(&acc3_full[b], (uint32_t)((g3 >> 1) & 1));
+        tcgen05_fence_after();
+        if (has_cols) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * NC + b * NC + sub * 32), v);
+          const int cb = c * NC + sub * 32 + (tangent ? 16 : 0);
+          float h[16], dh[16];
+          if (P.dbg == 3) { for (int i = 0; i < 16; ++i) { h[i] = __uint_as_float(v[i]); dh[i] = __uint_as_float(v[16 + i]); } }
+          else if (P.mul_cutoff) jvp_math<true, true>(v, tangent, P.bias3 + cb, cut, dcut, h, dh);
+          else jvp_math<true, false>(v, tangent, P.bias3 + cb, cut, dcut, h, dh);
+          if (valid && P.dbg != 1) {
+            const int N3 = 3 * NC;
+            float* d0 = P.out_f + (size_t)pair * N3 + cb;
+            float* d1 = P.out_fp + (size_t)pair * N3 + cb;
+            st8(d0, h); st8(d0 + 8, h + 8);
+            st8(d1, dh); st8(d1 + 8, dh + 8);
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc3_empty[b]);
+      }
     }
   }
 
@@ -544,7 +847,34 @@ int tmd_pair_chain_tc(const float* pair_r, const int* num_unique, int max_pairs,
   float* o_hi = act_b_hi; float* o_lo = act_b_lo;
   float* n_hi = act_a_hi; float* n_lo = act_a_lo;   // where the layer after this one writes
   int K = K0;
+  static int fuse_tail = -1;   // TMD_TC_FUSE=0 (dev knob) keeps the three per-layer launches
+  if (fuse_tail < 0) { const char* e = getenv("TMD_TC_FUSE"); fuse_tail = e ? atoi(e) : 1; }
+  const bool tail_ok = fuse_tail && use_f16 && n_layers == 3 && out_fp && act && (dims[1] == 64 || dims[1] == 128) &&
+                       dims[2] == 2 * dims[1] && dims[3] == 3 * dims[1];
   for (int l = 0; l < n_layers; ++l) {
+    if (l == 1 && tail_ok) {
+      // layers 2 + 3 in one kernel; in_hi / in_lo = h1 written by the layer-1 launch above
+      const int F = dims[1];
+      TMD_REQUIRE((reinterpret_cast<uintptr_t>(bias[1]) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias[2]) & 15) == 0,
+                  "pair_chain_tc: biases must be 16-byte aligned");
+      CUtensorMap mh_hi, mh_lo, m2_hi, m2_lo, m3_hi, m3_lo;
+      int rc;
+      if ((rc = make_map(&mh_hi, in_hi, rows_pad, F, BM, 1))) return rc;
+      if ((rc = make_map(&mh_lo, in_lo, rows_pad, F, BM, 1))) return rc;
+      if ((rc = make_map(&m2_hi, W_hi[1], 2 * F, F, F, 1))) return rc;
+      if ((rc = make_map(&m2_lo, W_lo[1], 2 * F, F, F, 1))) return rc;
+      if ((rc = make_map(&m3_hi, W_hi[2], 3 * F, 2 * F, F, 1))) return rc;
+      if ((rc = make_map(&m3_lo, W_lo[2], 3 * F, 2 * F, F, 1))) return rc;
+      TailParams T;
+      T.F = F; T.mul_cutoff = mul_cutoff; T.lo = (float)lo; T.hi = (float)hi; T.bias2 = bias[1]; T.bias3 = bias[2];
+      T.pair_r = pair_r; T.num_unique = num_unique; T.max_pairs = max_pairs; T.out_f = out_f; T.out_fp = out_fp;
+      { const char* e = getenv("TMD_TC_DBG"); T.dbg = e ? atoi(e) : 0; }
+      const int smem = (2 * F / 64) * KBLK_BYTES + TAIL_SLOTS * F * 128 * 2 + 1024;
+      const int tiles = rows_pad / BM;
+      cudaFuncSetAttribute(chain_tail_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      chain_tail_f16_kernel<<<tiles < 148 ? tiles : 148, TAIL_THREADS, smem, st>>>(mh_hi, mh_lo, m2_hi, m2_lo, m3_hi, m3_lo, T);
+      break;
+    }
     const int N = dims[l + 1];
     const int BN = pick_bn(N);
     TMD_REQUIRE(BN > 0, "pair_chain_tc: layer widths must be multiples of 64");
@@ -561,6 +891,7 @@ int tmd_pair_chain_tc(const float* pair_r, const int* num_unique, int max_pairs,
     P.mul_cutoff = mul_cutoff; P.lo = (float)lo; P.hi = (float)hi; P.bias = bias[l]; P.pair_r = pair_r;
     P.num_unique = num_unique; P.max_pairs = max_pairs; P.out_hi = o_hi; P.out_lo = o_lo; P.out_f = out_f; P.out_fp = out_fp;
     P.seg_t1 = P.seg_t2 = 0x7fffffff; P.b_seg_rows = 0; P.f16 = use_f16;
+    { const char* e = getenv("TMD_TC_DBG"); P.dbg = e ? atoi(e) : 0; }
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * BN * BK * 4;
     const int max_items = (rows_pad / BM) * (N / BN);
     const int grid = max_items < 148 ? max_items : 148;
@@ -606,7 +937,7 @@ int tmd_irreps_linear_tc(const float* I, const float* A, const float* S, int N, 
   GemmParams P;
   P.K = F; P.N = F; P.BN = BN; P.rows_per_pair = 1; P.act = 0; P.final_layer = 1; P.mul_cutoff = 0; P.lo = 0.f; P.hi = 1.f;
   P.bias = zero_bias; P.pair_r = nullptr; P.num_unique = nullptr; P.max_pairs = rtot; P.out_hi = nullptr; P.out_lo = nullptr;
-  P.out_f = out; P.out_fp = nullptr; P.seg_t1 = r1 / BM; P.seg_t2 = r2 / BM; P.b_seg_rows = F; P.f16 = 0;
+  P.out_f = out; P.out_fp = nullptr; P.seg_t1 = r1 / BM; P.seg_t2 = r2 / BM; P.b_seg_rows = F; P.f16 = 0; P.dbg = 0;
   const int stage_bytes = 2 * A_TILE_BYTES + 2 * BN * BK * 4;
   const int items = (rtot / BM) * (F / BN);
   const int grid = items < 148 ? items : 148;

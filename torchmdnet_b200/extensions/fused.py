@@ -238,12 +238,13 @@ def _triple(N, F, dev):
 
 
 class _InteractionMP(torch.autograd.Function):
-    """M = sum_e f(r_e) * Y_j with f = cutoff * MLP(rbf(r)) evaluated per pair (rows a6 + a7)."""
+    """M = sum_e f(r_e) * Y_j with f = cutoff * MLP(rbf(r)) evaluated per pair (rows a6 + a7).  `dist` is the per-slot
+    distance (the differentiable input); `pair_r` its per-pair gather (no autograd)."""
 
     @staticmethod
-    def forward(ctx, YI, YA, YS, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op):
+    def forward(ctx, YI, YA, YS, dist, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op):
         YI, YA, YS = YI.contiguous(), YA.contiguous(), YS.contiguous()
-        need = pair_r.requires_grad
+        need = dist.requires_grad
         f, fp = run_chain(chain, pair_r.detach(), pidx.num_unique, rbf_mod, lo, hi, need, rbf_op)
         N, F = YI.shape[0], YI.shape[-1]
         M = _triple(N, F, YI.device)
@@ -251,7 +252,7 @@ class _InteractionMP(torch.autograd.Function):
                   device=YI.device)
         ctx.save_for_backward(YI, YA, YS, f, fp if fp is not None else f, pidx.pid, g.nbr_j, g.indptr)
         ctx.has_fp = fp is not None
-        ctx.P = pair_r.shape[0]
+        ctx.E = dist.shape[0]
         return M
 
     @staticmethod
@@ -259,15 +260,15 @@ class _InteractionMP(torch.autograd.Function):
         YI, YA, YS, f, fp, pid, nbr_j, indptr = ctx.saved_tensors
         N, F = YI.shape[0], YI.shape[-1]
         dY = _triple(N, F, YI.device)
-        d_r = torch.zeros(ctx.P, device=YI.device, dtype=torch.float32) if ctx.has_fp else None
-        _lib.call("tmd_mp_pair_bwd", p(YI), p(YA), p(YS), p(dI.contiguous()), p(dA.contiguous()), p(dS.contiguous()), p(f),
-                  p(fp) if ctx.has_fp else None, p(pid), p(nbr_j), p(indptr), N, F, p(dY[0]), p(dY[1]), p(dY[2]), p(d_r),
+        g_dist = torch.zeros(ctx.E, device=YI.device, dtype=torch.float32) if ctx.has_fp else None
+        _lib.call("tmd_mp_edge_bwd", p(YI), p(YA), p(YS), p(dI.contiguous()), p(dA.contiguous()), p(dS.contiguous()), p(f),
+                  p(fp) if ctx.has_fp else None, p(pid), p(nbr_j), p(indptr), N, F, p(dY[0]), p(dY[1]), p(dY[2]), p(g_dist),
                   device=YI.device)
-        return dY[0], dY[1], dY[2], d_r, None, None, None, None, None, None, None
+        return dY[0], dY[1], dY[2], g_dist, None, None, None, None, None, None, None, None
 
 
-def interaction_message_passing(Y, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op=None):
-    return _InteractionMP.apply(Y[0], Y[1], Y[2], pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op)
+def interaction_message_passing(Y, dist, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op=None):
+    return _InteractionMP.apply(Y[0], Y[1], Y[2], dist, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op)
 
 
 class _EmbeddingMP(torch.autograd.Function):

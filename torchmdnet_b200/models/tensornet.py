@@ -146,7 +146,7 @@ class Interaction(nn.Module):
         if fast is not None:
             # fused path: f (and df/dr) once per unordered pair, message passing reads it through the pair index
             dist, pair_r, pidx, rbf_mod, rbf_op = fast
-            M = fused.interaction_message_passing(Y, pair_r, self.radial_chain(), rbf_mod, self.cutoff.cutoff_lower,
+            M = fused.interaction_message_passing(Y, dist, pair_r, self.radial_chain(), rbf_mod, self.cutoff.cutoff_lower,
                                                   self.cutoff.cutoff_upper, g, pidx, rbf_op)
         else:
             f = self.edge_weights(rbf, cut)
@@ -237,11 +237,11 @@ class TensorNet(nn.Module):
         # unit vectors; self loops (dist == 0) keep a zero vector (tensornet.py:363-366)
         rhat = vec / dist.masked_fill(dist == 0, 1).unsqueeze(1)
         if use_fused:
-            pair_r = fused.pair_distances(dist, pidx, P)
+            pair_r = pidx.pair_r[:P]   # per-pair distances (no autograd: every fused op differentiates w.r.t. the per-slot dist)
             # rbf(r) and d rbf/dr once per frame: the layer-0 tensor-core operand of every radial chain
             chains = [self.tensor_embedding.radial_chain()] + [l.radial_chain() for l in self.layers]
-            rbf_op = fused.shared_rbf_operand(chains, pair_r.detach(), pidx.num_unique, self.distance_expansion,
-                                              self.cutoff_lower, self.cutoff_upper, pair_r.requires_grad)
+            rbf_op = fused.shared_rbf_operand(chains, pair_r, pidx.num_unique, self.distance_expansion,
+                                              self.cutoff_lower, self.cutoff_upper, dist.requires_grad)
             fast = (dist, pair_r, pidx, self.distance_expansion, rbf_op)
             X = self.tensor_embedding(z, g, None, None, None, rhat, None, fast=fast)
             for layer in self.layers:

@@ -183,10 +183,10 @@ class TorchMD_ET(nn.Module):
         # the list is symmetric, so pairing (src, dst) = (a, b) covers exactly the reference's edge set
         # {(edge_index[0], edge_index[1])}; vec = pos_a - pos_b is the reference's d_ij for that edge
         if use_fused:
-            pair_r = fused.pair_distances(dist, pidx, P)
-            rbf_op = fused.shared_rbf_operand([l.radial_chain() for l in self.attention_layers], pair_r.detach(),
+            pair_r = pidx.pair_r[:P]
+            rbf_op = fused.shared_rbf_operand([l.radial_chain() for l in self.attention_layers], pair_r,
                                               pidx.num_unique, self.distance_expansion, self.cutoff_lower, self.cutoff_upper,
-                                              pair_r.requires_grad)
+                                              dist.requires_grad)
             fast = (dist, d_ij, pair_r, g, pidx, self.distance_expansion, rbf_op)
         for attn in self.attention_layers:
             dx, dv = attn.forward_fused(x, v, fast) if use_fused else attn(x, v, a, b, cut, edge_attr, d_ij)
