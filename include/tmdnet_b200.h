@@ -172,11 +172,11 @@ int tmd_pair_chain_tc(const float* pair_r, const int* num_unique, int max_pairs,
                       float* act_b_lo, float* out_f, float* out_fp, int use_f16, void* stream);
 /* ---- a9: node linears -----------------------------------------------------------------------------------------------
  * Replaces the three bias-free nn.Linear(F,F) that TensorNet applies to I / A / S (models/tensornet.py:752-754, :808-810,
- * :607-615; cuBLAS SGEMMs in the reference) by one grouped 3xTF32 tcgen05 GEMM.  W_hi/W_lo: TF32 split of the stacked
- * weights [3F,F]; row-segmented buffers of R_tot = r128(N)+r128(3N)+r128(5N) rows (r128 = round up to 128): ws_hi/ws_lo
- * scratch operands, out = fp32 result whose I/A/S blocks start at rows 0, r128(N), r128(N)+r128(3N).  F % 64 == 0, <= 256. */
+ * :607-615; cuBLAS SGEMMs in the reference) by one grouped 3xTF32 tcgen05 GEMM that reads the fp32 irreps directly (the
+ * (hi, lo) split of the A operand happens in shared memory) and writes oI [N,1,F], oA [N,3,F], oS [N,5,F].
+ * W_hi/W_lo: TF32 split of the stacked weights [3F,F].  F % 64 == 0, <= 256. */
 int tmd_irreps_linear_tc(const float* I, const float* A, const float* S, int N, int F, const float* W_hi, const float* W_lo,
-                         const float* zero_bias, float* ws_hi, float* ws_lo, float* out, void* stream);
+                         float* oI, float* oA, float* oS, void* stream);
 /* layer-0 operand of tmd_pair_chain_tc: rows (value[, d/dr]) of ExpNormalSmearing(r_p), TF32 split, K padded to a multiple
  * of 32.  Computed once per frame and shared by the embedding chain and every interaction layer (rbf_hi / rbf_lo). */
 int tmd_pair_rbf_split(const float* pair_r, const int* num_unique, int max_pairs, int R, int rows_per_pair,

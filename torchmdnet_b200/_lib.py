@@ -57,7 +57,7 @@ SIGNATURES = {
     "tmd_pair_index": ([P, P, P, P, P, I, I, P, P, P, P, P, P, P, P], 3),
     "tmd_pair_chain": ([P, P, I, P, P, P, P, P, P, P, I, I, I, P, P, D, D, D, P, P, P], 1),
     "tmd_pair_chain_tc": ([P, P, I, P, P, P, P, I, I, I, P, P, D, D, D, P, P, P, P, P, P, P, P, I, P], 3),
-    "tmd_irreps_linear_tc": ([P, P, P, I, I, P, P, P, P, P, P, P], 2),
+    "tmd_irreps_linear_tc": ([P, P, P, I, I, P, P, P, P, P, P], 1),
     "tmd_pair_rbf_split": ([P, P, I, I, I, P, P, D, D, D, P, P, I, P], 1),
     "tmd_mp_pair_bwd": ([P] * 11 + [I, I] + [P] * 4 + [P], 1),
     "tmd_et_msg_fwd": ([P] * 10 + [D, D, I, I, I, I, P, P, P], 1),
@@ -101,12 +101,13 @@ def require_cuda(*tensors):
             raise RuntimeError("torchmdnet_b200 kernels need CUDA tensors (sm_100a); there is no CPU fallback")
 
 
-def call(name, *args, device=None):
-    """Launch entry point `name` on the current stream of `device`; args before the stream."""
+def call(name, *args, device=None, launches=None):
+    """Launch entry point `name` on the current stream of `device`; args before the stream.  `launches` overrides the
+    per-call kernel count of SIGNATURES for entry points whose launch count depends on the arguments."""
     global _launches
     lib = library()
     stream = torch.cuda.current_stream(device).cuda_stream
     rc = getattr(lib, name)(*args, stream)
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {lib.tmd_last_error().decode()}")
-    _launches += SIGNATURES[name][1]
+    _launches += SIGNATURES[name][1] if launches is None else launches

@@ -741,19 +741,159 @@ __global__ void pair_rbf_split_kernel(const float* __restrict__ pair_r, const in
   }
 }
 
-// (I [N,1,F], A [N,3,F], S [N,5,F]) -> TF32 (hi, lo) in one row-segmented buffer [R_tot, F]; segment starts 0, r1, r2
-__global__ void irreps_split_kernel(const float* __restrict__ I, const float* __restrict__ A, const float* __restrict__ S,
-                                    int N, int F, int r1, int r2, float* __restrict__ hi, float* __restrict__ lo) {
-  const long long total = 9LL * N * F;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const long long row = idx / F;
-    const int c = (int)(idx - row * F);
-    float x; long long orow;
-    if (row < N) { x = I[row * F + c]; orow = row; }
-    else if (row < 4LL * N) { x = A[(row - N) * F + c]; orow = r1 + (row - N); }
-    else { x = S[(row - 4LL * N) * F + c]; orow = r2 + (row - 4LL * N); }
-    const float h = tf32_rna(x);
-    hi[orow * F + c] = h; lo[orow * F + c] = tf32_rna(x - h);
+// ---------------------------------------------------------------------------------------------------------------------
+// a9: the three bias-free F x F node linears of TensorNet as ONE grouped 3xTF32 GEMM that reads the fp32 irreps DIRECTLY.
+// The A operand is TMA-loaded as raw fp32 K-blocks; converter warps split it in shared memory, in place (hi = rna_tf32(x)
+// overwrites x, lo = rna_tf32(x - hi) goes to the twin tile at the same swizzled offsets -- the split is element-wise, so the
+// SWIZZLE_128B layout is untouched), publish it to the async proxy (fence.proxy.async) and hand the stage to the MMA warp.
+// No split pass over HBM, no padded operand / result buffers: the epilogue stores straight into the three output tensors.
+//   warps 0: TMA   1: MMA issuer   2..9: converters   10..17: epilogue (TMEM lane quarter = warp & 3)
+struct IrrParams {
+  int F;            // K = N = BN = F (64, 128, 192 or 256)
+  int n_atoms;
+  int t1, t2, tiles;  // m-tiles [0,t1) are I rows, [t1,t2) A rows, [t2,tiles) S rows
+  float* out[3];
+};
+constexpr int IRR_CONV_WARPS = 8;
+constexpr int IRR_EPI_WARPS = 8;
+constexpr int IRR_THREADS = 64 + 32 * (IRR_CONV_WARPS + IRR_EPI_WARPS);
+
+template <int STAGES>
+__global__ void __launch_bounds__(IRR_THREADS, 1)
+irreps_linear_kernel(const __grid_constant__ CUtensorMap map_i, const __grid_constant__ CUtensorMap map_a,
+                     const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_b_hi,
+                     const __grid_constant__ CUtensorMap map_b_lo, IrrParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int BN = P.F;
+  const int b_tile_bytes = BN * BK * 4;
+  const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
+  const int k_blocks = P.F / BK;
+  __shared__ __align__(8) uint64_t full_bar[STAGES], conv_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&conv_bar[s], IRR_CONV_WARPS); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], IRR_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+        const int seg = (tile >= P.t1) + (tile >= P.t2);
+        const int ltile = tile - (seg == 0 ? 0 : (seg == 1 ? P.t1 : P.t2));
+        const CUtensorMap* ma = seg == 0 ? &map_i : (seg == 1 ? &map_a : &map_s);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + (size_t)stage * stage_bytes;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)(A_TILE_BYTES + 2 * b_tile_bytes));
+          tma_load_2d(ma, &full_bar[stage], st, kb * BK, ltile * BM);
+          tma_load_2d(&map_b_hi, &full_bar[stage], st + 2 * A_TILE_BYTES, kb * BK, seg * P.F);
+          tma_load_2d(&map_b_lo, &full_bar[stage], st + 2 * A_TILE_BYTES + b_tile_bytes, kb * BK, seg * P.F);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_tf32(BM, BN);
+    int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&conv_bar[stage], phase);                 // operands split and proxy-fenced by the converters
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + A_TILE_BYTES);
+          const uint64_t b_hi = make_desc_sw128(st + 2 * A_TILE_BYTES), b_lo = make_desc_sw128(st + 2 * A_TILE_BYTES + b_tile_bytes);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+          }
+        }
+        __syncwarp();
+        if (elect_one()) umma_commit(&empty_bar[stage]);
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(&tmem_full_bar[acc]);
+      __syncwarp();
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp < 2 + IRR_CONV_WARPS) {
+    // ------------------------------------------------------------------ converters: fp32 K-block -> (hi, lo) TF32, in place
+    const int cidx = (warp - 2) * 32 + lane;
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        uint8_t* st = smem + (size_t)stage * stage_bytes;
+#pragma unroll
+        for (int u = 0; u < A_TILE_BYTES / 16 / (32 * IRR_CONV_WARPS); ++u) {
+          const int off = (cidx + u * 32 * IRR_CONV_WARPS) * 16;
+          const float4 x = *reinterpret_cast<const float4*>(st + off);
+          float4 h, l;
+          h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
+          l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
+          *reinterpret_cast<float4*>(st + off) = h;
+          *reinterpret_cast<float4*>(st + A_TILE_BYTES + off) = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: TMEM -> fp32 rows of the output tensors
+    const int q = warp & 3;
+    const int sub = (warp - 2 - IRR_CONV_WARPS) >> 2;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+      const int seg = (tile >= P.t1) + (tile >= P.t2);
+      const int ltile = tile - (seg == 0 ? 0 : (seg == 1 ? P.t1 : P.t2));
+      const long long rows_seg = (long long)P.n_atoms * (seg == 0 ? 1 : (seg == 1 ? 3 : 5));
+      const long long row = (long long)ltile * BM + q * 32 + lane;
+      float* orow = P.out[seg] + row * P.F;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
+      for (int c0 = sub * 32; c0 < BN; c0 += 32 * (IRR_EPI_WARPS / 4)) {
+        uint32_t v[32];
+        tmem_ld32(t_row + (uint32_t)c0, v);
+        if (row < rows_seg) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) st8(orow + c0 + i, reinterpret_cast<const float*>(v) + i);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
 }
 
@@ -914,41 +1054,36 @@ int tmd_pair_chain_tc(const float* pair_r, const int* num_unique, int max_pairs,
   return tmd_check_launch("pair_chain_tc");
 }
 
-// a9: the three bias-free F x F node linears of TensorNet (I, A, S rows each with its own weight) as ONE grouped 3xTF32
-// GEMM on tcgen05.  W_hi / W_lo: TF32 split of the stacked weights [3F, F] (rows 0..F-1 act on I, F..2F-1 on A, 2F..3F-1 on S).
-// Row-segmented buffers of R_tot = r128(N) + r128(3N) + r128(5N) rows: ws_hi, ws_lo (operands) and out (fp32 result);
-// the I / A / S blocks of `out` start at rows 0, r128(N), r128(N) + r128(3N).  zero_bias: F zeros.
+// a9: the three bias-free F x F node linears of TensorNet (I [N,1,F], A [N,3,F], S [N,5,F], each with its own weight) as ONE
+// grouped 3xTF32 GEMM on tcgen05, reading the fp32 irreps directly (split in shared memory) and writing oI / oA / oS.
+// W_hi / W_lo: TF32 split of the stacked weights [3F, F] (rows 0..F-1 act on I, F..2F-1 on A, 2F..3F-1 on S).
 int tmd_irreps_linear_tc(const float* I, const float* A, const float* S, int N, int F, const float* W_hi, const float* W_lo,
-                         const float* zero_bias, float* ws_hi, float* ws_lo, float* out, void* stream) {
-  TMD_REQUIRE(I && A && S && W_hi && W_lo && zero_bias && ws_hi && ws_lo && out, "irreps_linear_tc: null pointer");
+                         float* oI, float* oA, float* oS, void* stream) {
+  TMD_REQUIRE(I && A && S && W_hi && W_lo && oI && oA && oS, "irreps_linear_tc: null pointer");
   TMD_REQUIRE(F % 64 == 0 && F <= 256, "irreps_linear_tc: F must be a multiple of 64, <= 256");
   if (N == 0) return TMD_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  auto r128 = [](long long x) { return (int)(((x + BM - 1) / BM) * BM); };
-  const int r1 = r128(N), r2 = r1 + r128(3LL * N), rtot = r2 + r128(5LL * N);
-  irreps_split_kernel<<<tmd_blocks_for(9LL * N * F, 256), 256, 0, st>>>(I, A, S, N, F, r1, r2, ws_hi, ws_lo);
-  const int BN = pick_bn(F);
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  auto tiles_of = [](long long rows) { return (int)((rows + BM - 1) / BM); };
+  IrrParams P;
+  P.F = F; P.n_atoms = N; P.t1 = tiles_of(N); P.t2 = P.t1 + tiles_of(3LL * N); P.tiles = P.t2 + tiles_of(5LL * N);
+  P.out[0] = oI; P.out[1] = oA; P.out[2] = oS;
+  CUtensorMap mi, ma, ms, mb_hi, mb_lo;
   int rc;
-  if ((rc = make_map(&ma_hi, ws_hi, rtot, F, BM))) return rc;
-  if ((rc = make_map(&ma_lo, ws_lo, rtot, F, BM))) return rc;
-  if ((rc = make_map(&mb_hi, W_hi, 3 * F, F, BN))) return rc;
-  if ((rc = make_map(&mb_lo, W_lo, 3 * F, F, BN))) return rc;
-  GemmParams P;
-  P.K = F; P.N = F; P.BN = BN; P.rows_per_pair = 1; P.act = 0; P.final_layer = 1; P.mul_cutoff = 0; P.lo = 0.f; P.hi = 1.f;
-  P.bias = zero_bias; P.pair_r = nullptr; P.num_unique = nullptr; P.max_pairs = rtot; P.out_hi = nullptr; P.out_lo = nullptr;
-  P.out_f = out; P.out_fp = nullptr; P.seg_t1 = r1 / BM; P.seg_t2 = r2 / BM; P.b_seg_rows = F; P.f16 = 0; P.dbg = 0;
-  const int stage_bytes = 2 * A_TILE_BYTES + 2 * BN * BK * 4;
-  const int items = (rtot / BM) * (F / BN);
-  const int grid = items < 148 ? items : 148;
+  if ((rc = make_map(&mi, I, N, F, BM))) return rc;
+  if ((rc = make_map(&ma, A, 3 * N, F, BM))) return rc;
+  if ((rc = make_map(&ms, S, 5 * N, F, BM))) return rc;
+  if ((rc = make_map(&mb_hi, W_hi, 3 * F, F, F))) return rc;
+  if ((rc = make_map(&mb_lo, W_lo, 3 * F, F, F))) return rc;
+  const int stage_bytes = 2 * A_TILE_BYTES + 2 * F * BK * 4;
+  const int grid = P.tiles < 148 ? P.tiles : 148;
   if (stage_bytes * 3 + 1024 <= 200 * 1024) {
     const int smem = stage_bytes * 3 + 1024;
-    cudaFuncSetAttribute(gemm3x_tf32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    gemm3x_tf32_kernel<3><<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
+    cudaFuncSetAttribute(irreps_linear_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    irreps_linear_kernel<3><<<grid, IRR_THREADS, smem, st>>>(mi, ma, ms, mb_hi, mb_lo, P);
   } else {
     const int smem = stage_bytes * 2 + 1024;
-    cudaFuncSetAttribute(gemm3x_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    gemm3x_tf32_kernel<2><<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
+    cudaFuncSetAttribute(irreps_linear_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    irreps_linear_kernel<2><<<grid, IRR_THREADS, smem, st>>>(mi, ma, ms, mb_hi, mb_lo, P);
   }
   return tmd_check_launch("irreps_linear_tc");
 }

@@ -6,6 +6,7 @@ message passing is a single gather kernel that emits dE/dr per pair.  Training (
 using the autograd-composed ops of tensornet_ops.py.
 """
 import ctypes
+import os
 from typing import NamedTuple, Optional, Sequence
 
 import torch
@@ -201,6 +202,15 @@ def shared_rbf_operand(chains, pair_r: Tensor, num_unique: Tensor, rbf_mod, lo: 
     return precompute_rbf(pair_r, num_unique, rbf_mod, lo, hi, want_tangent, f16=modes.pop())
 
 
+def _chain_launches(dims, n_layers, f16, tangent, act, have_rbf):
+    """kernels one tmd_pair_chain_tc call launches: rbf operand (unless shared) + one per layer, layers 2+3 fused when the
+    tail kernel applies (pair_chain_tc.cu: tail_ok)."""
+    n = n_layers + (0 if have_rbf else 1)
+    fused_tail = (os.environ.get("TMD_TC_FUSE", "1") != "0" and f16 and n_layers == 3 and tangent and act and
+                  dims[1] in (64, 128) and dims[2] == 2 * dims[1] and dims[3] == 3 * dims[1])
+    return n - 1 if fused_tail else n
+
+
 def run_chain(chain: RadialChain, pair_r: Tensor, num_unique: Tensor, rbf_mod, lo: float, hi: float, want_tangent: bool,
               rbf_op: Optional[RbfOperand] = None):
     """-> (f [P,N_last], f' or None).  `rbf_mod` is the ExpNormalSmearing module (means/betas/alpha)."""
@@ -221,7 +231,8 @@ def run_chain(chain: RadialChain, pair_r: Tensor, num_unique: Tensor, rbf_mod, l
                   ctypes.cast(p_lo, ctypes.c_void_p), ctypes.cast(p_b, ctypes.c_void_p), ctypes.cast(dims, ctypes.c_void_p),
                   len(wt), int(chain.act), int(chain.mul_cutoff), p(rbf_mod.means.detach()), p(rbf_mod.betas.detach()),
                   float(rbf_mod.alpha), float(lo), float(hi), p(rbf_op.hi) if rbf_op else None, p(rbf_op.lo) if rbf_op else None,
-                  p(ws[0]), p(ws[1]), p(ws[2]), p(ws[3]), p(f), p(fp), int(f16), device=pair_r.device)
+                  p(ws[0]), p(ws[1]), p(ws[2]), p(ws[3]), p(f), p(fp), int(f16), device=pair_r.device,
+                  launches=_chain_launches(list(dims), len(wt), f16, want_tangent, chain.act, rbf_op is not None))
         return f, fp
     if not chain.supported_ffma():
         raise RuntimeError("radial chain widths are supported by neither the tcgen05 nor the fp32 chain kernel")
@@ -372,32 +383,28 @@ class IrrepsLinearWeights:
             W = torch.cat([l.weight.detach() for l in self.linears], 0)              # [3F, F]: out = x W_k^T  ->  B[n, k] = W_k
             Wt = torch.cat([l.weight.detach().t() for l in self.linears], 0)        # backward: dx = dy W_k   ->  B[n, k] = W_k^T
             self._fwd, self._bwd = _tf32_split(W), _tf32_split(Wt.contiguous())
-            self._zero = torch.zeros(W.shape[1], device=W.device, dtype=torch.float32)
             self._key = key
-        return self._fwd, self._bwd, self._zero
+        return self._fwd, self._bwd
 
 
-def _irreps_gemm(I, A, S, w_hi, w_lo, zero):
+def _irreps_gemm(I, A, S, w_hi, w_lo):
     I, A, S = I.contiguous(), A.contiguous(), S.contiguous()
     N, F = I.shape[0], I.shape[-1]
-    r128 = lambda x: -(-x // 128) * 128
-    r1 = r128(N); r2 = r1 + r128(3 * N); rtot = r2 + r128(5 * N)
-    ws = torch.empty(2, rtot, F, device=I.device, dtype=torch.float32)
-    out = torch.empty(rtot, F, device=I.device, dtype=torch.float32)
-    _lib.call("tmd_irreps_linear_tc", p(I), p(A), p(S), N, F, p(w_hi), p(w_lo), p(zero), p(ws[0]), p(ws[1]), p(out), device=I.device)
-    return out[:N].view(N, 1, F), out[r1:r1 + 3 * N].view(N, 3, F), out[r2:r2 + 5 * N].view(N, 5, F)
+    oI, oA, oS = _triple(N, F, I.device)
+    _lib.call("tmd_irreps_linear_tc", p(I), p(A), p(S), N, F, p(w_hi), p(w_lo), p(oI), p(oA), p(oS), device=I.device)
+    return oI, oA, oS
 
 
 class _IrrepsLinear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, I, A, S, weights):
-        fwd, bwd, zero = weights.tensors()
-        ctx.bwd, ctx.zero = bwd, zero
-        return _irreps_gemm(I, A, S, fwd[0], fwd[1], zero)
+        fwd, bwd = weights.tensors()
+        ctx.bwd = bwd
+        return _irreps_gemm(I, A, S, fwd[0], fwd[1])
 
     @staticmethod
     def backward(ctx, dI, dA, dS):
-        gI, gA, gS = _irreps_gemm(dI, dA, dS, ctx.bwd[0], ctx.bwd[1], ctx.zero)
+        gI, gA, gS = _irreps_gemm(dI, dA, dS, ctx.bwd[0], ctx.bwd[1])
         return gI, gA, gS, None
 
 
