@@ -294,7 +294,11 @@ def main():
         N = z.numel(); F = hp["embedding_dimension"]; R = hp["num_rbf"]
         pair_r = pidx.pair_r[:Pn].contiguous()
         chain = rep.layers[0].radial_chain()
-        run = lambda: fused.run_chain(chain, pair_r, pidx.num_unique, rep.distance_expansion, 0.0, hp["cutoff_upper"], True)
+        f16_mode = bool(chain.supported_tc() and chain.f16_safe(rep.distance_expansion, 0.0, hp["cutoff_upper"]))
+        # the rbf operand is built once per frame and shared by the chains of all layers (as in the model's forward)
+        rbf_op = fused.precompute_rbf(pair_r, pidx.num_unique, rep.distance_expansion, 0.0, hp["cutoff_upper"], True, f16=f16_mode) \
+            if chain.supported_tc() else None
+        run = lambda: fused.run_chain(chain, pair_r, pidx.num_unique, rep.distance_expansion, 0.0, hp["cutoff_upper"], True, rbf_op)
         for _ in range(3):
             run()
         torch.cuda.synchronize()
@@ -309,14 +313,17 @@ def main():
         # = 270 336 flop per evaluated row at F=128, R=32); the 3xTF32 split executes 3x this on the tensor pipe
         flops = 2 * Pn * 2 * (R * F + F * 2 * F + 2 * F * 3 * F)
         ach_tf = flops / (c_ms * 1e-3) / 1e12
-        f16_mode = bool(chain.supported_tc() and chain.f16_safe(rep.distance_expansion, 0.0, hp["cutoff_upper"]))
         split_div = 3.0 if f16_mode else 6.0   # 3 split MMAs per product; tf32 additionally runs at half the 16-bit rate
-        roofline = {"kernel": "gemm3x_tf32_kernel x3: tcgen05 radial chain of one interaction layer (3 split-term GEMMs), value + d/dr on unique pairs",
+        fused_tail = f16_mode and os.environ.get("TMD_TC_FUSE", "1") != "0" and F in (64, 128)
+        kname = ("gemm3x_tf32_kernel (layer 1) + chain_tail_f16_kernel (layers 2+3 fused, h2 in shared memory)" if fused_tail
+                 else "gemm3x_tf32_kernel x3")
+        roofline = {"kernel": kname + ": tcgen05 radial chain of one interaction layer (3 split-term MMAs per product), value + d/dr on unique pairs",
                     "bound": "tensor", "achieved": ach_tf, "peak": tc_peak, "peak_source": how + " dense bf16 burst", "unit": "TFLOP/s",
                     "frac": ach_tf / tc_peak, "frac_of_split_ceiling": ach_tf / (tc_peak / split_div),
                     "operands": "fp16 (hi, lo) split terms" if f16_mode else "tf32 (hi, lo) split terms",
                     "note": f"fp32-parity path: every product needs 3 split MMAs (lo.hi + hi.lo + hi.hi), so the tensor ceiling of this kernel is peak/{split_div:.0f}",
-                    "traffic": (2.53e9 if f16_mode else 4.240e9), "traffic_source": "ncu --set full r01 (dram read+write summed over the 3 GEMM launches of one chain call, profiles/r01_gemm3x_ncu.md)",
+                    "traffic": (1.45e9 if fused_tail else (2.53e9 if f16_mode else 4.240e9)),
+                    "traffic_source": "ncu --set full r01, dram read+write summed over the launches of one chain call on the C4 pair count (profiles/r01_chain_tail_ncu.md, profiles/r01_gemm3x_ncu.md)",
                     "algorithmic_flops": flops, "kernel_ms": c_ms, "pairs": Pn}
         # ---- secondary: interaction message passing forward (a7), HBM/L2-gather bound ----
         I_, A_, S_ = (torch.randn(N, k, F, device=dev) for k in (1, 3, 5))
