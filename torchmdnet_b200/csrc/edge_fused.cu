@@ -464,6 +464,7 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict_
   }
 }
 // backward wrt geometry only (U, V, weights are inference constants): g_dist[e], g_rhat[e,3]
+template <bool ONE_CHUNK>
 __global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict__ rhat, const float* __restrict__ dist,
                                                         const float* __restrict__ dp, const float* __restrict__ dpp,
                                                         const int* __restrict__ pid, const int* __restrict__ nbr_j,
@@ -473,6 +474,9 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict_
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < n; b += gridDim.x * wpb) {
     const int k0 = indptr[b], k1 = indptr[b + 1];
+    // ONE_CHUNK (F <= 128): the row's own dOut and U are loaded once, not once per edge
+    float4 d[9], ub = zero4();
+    if (ONE_CHUNK && lane * 4 < F) { ld9(dout, b, F, lane * 4, d); ub = ldg4(U + (long long)b * F + lane * 4); }
     for (int k = k0; k < k1; ++k) {
       const long long j = nbr_j[k], p = pid[k];
       const float r[3] = {__ldg(rhat + 3 * k), __ldg(rhat + 3 * k + 1), __ldg(rhat + 3 * k + 2)};
@@ -483,9 +487,8 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict_
       float gr[3] = {0.f, 0.f, 0.f};
       float gd = 0.f;
       for (int h = lane * 4; h < F; h += 128) {
-        float4 d[9];
-        ld9(dout, b, F, h, d);
-        const float4 z = add4(ldg4(U + (long long)b * F + h), ldg4(V + j * F + h));
+        if (!ONE_CHUNK) { ld9(dout, b, F, h, d); ub = ldg4(U + (long long)b * F + h); }
+        const float4 z = add4(ub, ldg4(V + j * F + h));
         const float* de = dp + p * 3 * (long long)F + h;
         const float* dde = dpp + p * 3 * (long long)F + h;
         const float4 q1 = ldg4(de), q2 = ldg4(de + F), q3 = ldg4(de + 2 * F);
@@ -629,8 +632,12 @@ int tmd_embed_bwd(const float* rhat, const float* dist, const float* dp, const f
   TMD_REQUIRE(F > 0 && F % 4 == 0, "embed_bwd: F must be a positive multiple of 4");
   TMD_REQUIRE(rhat && dist && dp && dpp && pid && nbr_j && indptr && U && V && dI && dA && dS && g_dist && g_rhat, "embed_bwd: null pointer");
   if (n == 0) return TMD_OK;
-  embed_bwd_kernel<<<tmd_blocks_for((long long)n * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-      rhat, dist, dp, dpp, pid, nbr_j, indptr, U, V, (float)lo, (float)hi, n, F, CIrr{dI, dA, dS}, g_dist, g_rhat);
+  if (F <= 128)
+    embed_bwd_kernel<true><<<tmd_blocks_for((long long)n * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        rhat, dist, dp, dpp, pid, nbr_j, indptr, U, V, (float)lo, (float)hi, n, F, CIrr{dI, dA, dS}, g_dist, g_rhat);
+  else
+    embed_bwd_kernel<false><<<tmd_blocks_for((long long)n * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        rhat, dist, dp, dpp, pid, nbr_j, indptr, U, V, (float)lo, (float)hi, n, F, CIrr{dI, dA, dS}, g_dist, g_rhat);
   return tmd_check_launch("embed_bwd");
 }
 

@@ -243,15 +243,19 @@ __global__ void __launch_bounds__(256) neighbor_rows_kernel(
 // single-CTA exclusive scan: out[0]=0, out[k+1]=sum_{t<=k} in[t]; total -> *total_out (optional)
 __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int* __restrict__ in, int n, int* __restrict__ out,
                                                                int* __restrict__ total_out) {
+  constexpr int ITEMS = 8;   // consecutive elements per thread and pass: 8192 per pass instead of 1024
   __shared__ int warp_tot[32];
   __shared__ int carry_s;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (threadIdx.x == 0) { carry_s = 0; out[0] = 0; }
   __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int i = base + threadIdx.x;
-    int v = (i < n) ? in[i] : 0;
-    int x = v;
+  for (int base = 0; base < n; base += 1024 * ITEMS) {
+    const int i0 = base + threadIdx.x * ITEMS;
+    int v[ITEMS];
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) { v[k] = (i0 + k < n) ? in[i0 + k] : 0; sum += v[k]; }
+    int x = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
     if (lane == 31) warp_tot[w] = x;
@@ -263,8 +267,10 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int* __restr
       warp_tot[lane] = t;
     }
     __syncthreads();
-    const int incl = x + (w > 0 ? warp_tot[w - 1] : 0) + carry_s;
-    if (i < n) out[i + 1] = incl;
+    const int incl = x + (w > 0 ? warp_tot[w - 1] : 0) + carry_s;   // inclusive prefix up to this thread's last element
+    int run = incl - sum;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) { run += v[k]; if (i0 + k < n) out[i0 + k + 1] = run; }
     __syncthreads();
     if (threadIdx.x == 1023) carry_s = incl;
     __syncthreads();
@@ -289,15 +295,24 @@ __global__ void reverse_edge_kernel(const int* __restrict__ indptr, const int* _
 // a2: dpos_i = sum_{e in row i} (g_e - g_rev(e)),  g_e = dvec_e + ddist_e * vec_e / dist_e (0 where dist == 0)
 // (reference: extensions/neighbor_utils.py:11-46, there as two index_add_ with atomics)
 template <typename T>
-__global__ void neighbor_grad_csr_kernel(const int* __restrict__ indptr, const int* __restrict__ rev,
-                                         const int* __restrict__ num_pairs, int max_pairs, int n,
-                                         const T* __restrict__ vec, const T* __restrict__ dist,
-                                         const T* __restrict__ gvec, const T* __restrict__ gdist, T* __restrict__ gpos) {
+__device__ __forceinline__ T warp_sum_t(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// one warp per atom: lanes stride over the row's slots (fixed summation tree -> deterministic), no atomics
+template <typename T>
+__global__ void __launch_bounds__(256) neighbor_grad_csr_kernel(const int* __restrict__ indptr, const int* __restrict__ rev,
+                                                                const int* __restrict__ num_pairs, int max_pairs, int n,
+                                                                const T* __restrict__ vec, const T* __restrict__ dist,
+                                                                const T* __restrict__ gvec, const T* __restrict__ gdist,
+                                                                T* __restrict__ gpos) {
   const int E = min(*num_pairs, max_pairs);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
     T ax = 0, ay = 0, az = 0;
     const int e1 = min(indptr[i + 1], E);
-    for (int e = indptr[i]; e < e1; ++e) {
+    for (int e = indptr[i] + lane; e < e1; e += 32) {
 #pragma unroll
       for (int side = 0; side < 2; ++side) {
         const int k = side == 0 ? e : rev[e];
@@ -310,7 +325,8 @@ __global__ void neighbor_grad_csr_kernel(const int* __restrict__ indptr, const i
         if (side == 0) { ax += gx; ay += gy; az += gz; } else { ax -= gx; ay -= gy; az -= gz; }
       }
     }
-    gpos[3 * i] = ax; gpos[3 * i + 1] = ay; gpos[3 * i + 2] = az;
+    ax = warp_sum_t(ax); ay = warp_sum_t(ay); az = warp_sum_t(az);
+    if (lane == 0) { gpos[3 * (size_t)i] = ax; gpos[3 * (size_t)i + 1] = ay; gpos[3 * (size_t)i + 2] = az; }
   }
 }
 
@@ -441,7 +457,7 @@ int tmd_neighbor_grad_csr_f32(const int* indptr, const int* rev, const int* num_
                               float* gpos, void* stream) {
   TMD_REQUIRE(indptr && rev && num_pairs && vec && dist && gpos, "neighbor_grad_csr: null pointer");
   if (n == 0) return TMD_OK;
-  neighbor_grad_csr_kernel<float><<<tmd_blocks_for(n, 128), 128, 0, (cudaStream_t)stream>>>(
+  neighbor_grad_csr_kernel<float><<<tmd_blocks_for((long long)n * 32, 256), 256, 0, (cudaStream_t)stream>>>(
       indptr, rev, num_pairs, max_pairs, n, vec, dist, gvec, gdist, gpos);
   return tmd_check_launch("neighbor_grad_csr");
 }
@@ -450,7 +466,7 @@ int tmd_neighbor_grad_csr_f64(const int* indptr, const int* rev, const int* num_
                               double* gpos, void* stream) {
   TMD_REQUIRE(indptr && rev && num_pairs && vec && dist && gpos, "neighbor_grad_csr: null pointer");
   if (n == 0) return TMD_OK;
-  neighbor_grad_csr_kernel<double><<<tmd_blocks_for(n, 128), 128, 0, (cudaStream_t)stream>>>(
+  neighbor_grad_csr_kernel<double><<<tmd_blocks_for((long long)n * 32, 256), 256, 0, (cudaStream_t)stream>>>(
       indptr, rev, num_pairs, max_pairs, n, vec, dist, gvec, gdist, gpos);
   return tmd_check_launch("neighbor_grad_csr");
 }
