@@ -276,12 +276,41 @@ def main():
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     ms_e2e = t2.item()
 
+    # ---- the same frame with the radial tables off: every pair of every frame goes through the tcgen05 chain ----
+    exact_arm = None
+    from torchmdnet_b200.extensions import fused as _fused
+    table_on = bool(_fused.USE_RADIAL_TABLE)
+    if table_on and is_tn and args.workload != "c5":
+        _fused.USE_RADIAL_TABLE = False
+        try:
+            ff2 = None
+            if ff is not None:
+                from torchmdnet_b200.calculators import CUDAGraphForceField
+                ff2 = CUDAGraphForceField(model, zd, bd, box=boxd, num_systems=n_sys).capture(pos_d)
+            frame2 = (lambda p: ff2(p)) if ff2 is not None else (lambda p: model(zd, p, bd, box=boxd, num_systems=n_sys))
+            for _ in range(3):
+                frame2(pos_d.clone())
+            barrier()
+            ev0.record()
+            for _ in range(args.steps):
+                frame2(pos_d.clone())
+            ev1.record()
+            barrier()
+            t3 = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+            if dist_on:
+                dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+            exact_arm = {"value": world * args.steps / (t3.item() * 1e-3), "unit": UNIT, "ms_per_step": t3.item() / args.steps,
+                         "note": "radial tables off (TMD_RADIAL_TABLE=0): the radial MLP of every pair is evaluated on the tcgen05 chain each frame"}
+            del ff2
+        finally:
+            _fused.USE_RADIAL_TABLE = True
+
     if rank != 0:
         if dist_on:
             dist.destroy_process_group()
         return
 
-    roofline = roofline2 = None
+    roofline = roofline2 = roofline3 = None
     N = z.numel()
     if is_tn:
         # ---- roofline of the dominant hand-written kernel: the tcgen05 radial chain of one interaction layer (a6) ----
@@ -298,7 +327,7 @@ def main():
         # the rbf operand is built once per frame and shared by the chains of all layers (as in the model's forward)
         rbf_op = fused.precompute_rbf(pair_r, pidx.num_unique, rep.distance_expansion, 0.0, hp["cutoff_upper"], True, f16=f16_mode) \
             if chain.supported_tc() else None
-        run = lambda: fused.run_chain(chain, pair_r, pidx.num_unique, rep.distance_expansion, 0.0, hp["cutoff_upper"], True, rbf_op)
+        run = lambda: fused.run_chain(chain, pair_r, pidx.num_unique, rep.distance_expansion, 0.0, hp["cutoff_upper"], True, rbf_op, exact=True)
         for _ in range(3):
             run()
         torch.cuda.synchronize()
@@ -317,7 +346,7 @@ def main():
         fused_tail = f16_mode and os.environ.get("TMD_TC_FUSE", "1") != "0" and F in (64, 128)
         kname = ("gemm3x_tf32_kernel (layer 1) + chain_tail_f16_kernel (layers 2+3 fused, h2 in shared memory)" if fused_tail
                  else "gemm3x_tf32_kernel x3")
-        roofline = {"kernel": kname + ": tcgen05 radial chain of one interaction layer (3 split-term MMAs per product), value + d/dr on unique pairs",
+        roofline3 = {"kernel": kname + ": tcgen05 radial chain of one interaction layer (3 split-term MMAs per product), value + d/dr on unique pairs",
                     "bound": "tensor", "achieved": ach_tf, "peak": tc_peak, "peak_source": how + " dense bf16 burst", "unit": "TFLOP/s",
                     "frac": ach_tf / tc_peak, "frac_of_split_ceiling": ach_tf / (tc_peak / split_div),
                     "operands": "fp16 (hi, lo) split terms" if f16_mode else "tf32 (hi, lo) split terms",
@@ -325,6 +354,34 @@ def main():
                     "traffic": (1.45e9 if fused_tail else (2.53e9 if f16_mode else 4.240e9)),
                     "traffic_source": "ncu --set full r01, dram read+write summed over the launches of one chain call on the C4 pair count (profiles/r01_chain_tail_ncu.md, profiles/r01_gemm3x_ncu.md)",
                     "algorithmic_flops": flops, "kernel_ms": c_ms, "pairs": Pn}
+        roofline3["role"] = ("exact evaluation of the radial MLP: every frame when the tables are off or rejected by their gate; "
+                             "with tables on it runs once per model, at table build")
+        # ---- dominant kernel of the frame: interaction message-passing backward (a7 + dE/dr), HBM/L2-gather bound ----
+        from torchmdnet_b200 import _lib as L
+        from torchmdnet_b200._lib import ptr as _p
+        Y = [torch.randn(N, k, F, device=dev) for k in (1, 3, 5)]
+        dM = [torch.randn(N, k, F, device=dev) for k in (1, 3, 5)]
+        dY = [torch.empty(N, k, F, device=dev) for k in (1, 3, 5)]
+        f_ = torch.randn(Pn, 3, F, device=dev); fp_ = torch.randn(Pn, 3, F, device=dev)
+        gd = torch.zeros(E, device=dev)
+        eb = lambda: L.call("tmd_mp_edge_bwd", _p(Y[0]), _p(Y[1]), _p(Y[2]), _p(dM[0]), _p(dM[1]), _p(dM[2]), _p(f_), _p(fp_), _p(pidx.pid),
+                            _p(g.nbr_j), _p(g.indptr), N, F, _p(dY[0]), _p(dY[1]), _p(dY[2]), _p(gd), device=dev)
+        for _ in range(3):
+            eb()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(reps):
+            eb()
+        ev1.record(); torch.cuda.synchronize()
+        b_ms = ev0.elapsed_time(ev1) / reps
+        # algorithmic bytes: f and f' once per unique pair, Y_b / dM / dY once per node, CSR (nbr_j, pid) + g_dist per slot
+        eb_bytes = 4 * (2 * 3 * Pn * F + 3 * 9 * N * F) + 4 * (3 * E + N + 1)
+        eb_ach = eb_bytes / (b_ms * 1e-3) / 1e9
+        roofline = {"kernel": "mp_edge_bwd_kernel (interaction message passing backward fused with dE/dr, one layer): dY_b = sum f_p dM_j, g_dist = <f'_p, dM_j * Y_b>",
+                    "bound": "hbm", "achieved": eb_ach, "peak": hbm_peak, "peak_source": how, "unit": "GB/s", "frac": eb_ach / hbm_peak,
+                    "traffic": 1.53e9, "traffic_source": "ncu --set full r01 (dram read 1.48 GB + write 0.05 GB per launch, profiles/r01_mp_ncu.md): f and f' are fetched once per direction when the two uses of a pair are further apart than L2",
+                    "algorithmic_bytes": eb_bytes, "kernel_ms": b_ms, "edges": E, "pairs": Pn,
+                    "share_of_frame": "largest single kernel of the frame (3 launches), profiles/r01_launches_final.md"}
         # ---- secondary: interaction message passing forward (a7), HBM/L2-gather bound ----
         I_, A_, S_ = (torch.randn(N, k, F, device=dev) for k in (1, 3, 5))
         w = torch.randn(E, 3, F, device=dev)
@@ -359,11 +416,13 @@ def main():
            "data": "synthetic",
            "config": {"workload": desc, "atoms_per_gpu": N, "edges_per_gpu": int(model.representation_model.distance.graph(pos_d, bd, boxd).num_pairs.item()), "boxes": world, "parallelism": f"dp{world} (one box per GPU, one scalar all-reduce)",
                       "l2": "per-frame working set ~4 GB >> 126 MB L2; no explicit flush",
-                      "cuda_graph": ff is not None},
+                      "cuda_graph": ff is not None,
+                      "radial_table": table_on and is_tn},
            "clocks": clocks.summary(),
            "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": ms_e2e / args.steps},
-           "gpu_launches": launches, "roofline": roofline, "roofline_secondary": roofline2, "cpu_baseline": cpu}
+           "gpu_launches": launches, "roofline": roofline, "roofline_secondary": roofline2, "roofline_exact_chain": roofline3,
+           "exact_chain": exact_arm, "cpu_baseline": cpu}
     print(json.dumps(out), flush=True)
     if dist_on:
         dist.destroy_process_group()

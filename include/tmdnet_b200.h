@@ -170,6 +170,14 @@ int tmd_pair_chain_tc(const float* pair_r, const int* num_unique, int max_pairs,
                       int mul_cutoff, const float* means, const float* betas, double alpha, double lo, double hi,
                       const float* rbf_hi, const float* rbf_lo, float* act_a_hi, float* act_a_lo, float* act_b_hi,
                       float* act_b_lo, float* out_f, float* out_fp, int use_f16, void* stream);
+/* ---- 8(f).1: tabulated radial function ---------------------------------------------------------------------------------
+ * SURVEY 8(f) item 1 ("tabulating each layer's radial function r -> MLP(RBF(r)) C(r) ... gated by a parity check"): for frozen
+ * weights the chain of tmd_pair_chain* is a fixed R -> R^N function of one scalar (models/tensornet.py:738-743).  table is
+ * [n_int][4][N] fp32 = (f_i, f_{i+1}-f_i, h f'_i, h f'_{i+1}) on the intervals [i h, (i+1) h), h = 2^-k (nodes exact in fp32),
+ * built on the host in fp64 and accepted only if it reproduces the exact path (extensions/fused.py: RadialChain.table).
+ * Writes out_f [P,N] and, if out_fp != NULL, d/dr -- same contract as tmd_pair_chain_tc. */
+int tmd_radial_table(const float* pair_r, const int* num_unique, int max_pairs, const float* table, int n_int, double h, int N,
+                     float* out_f, float* out_fp, void* stream);
 /* ---- a9: node linears -----------------------------------------------------------------------------------------------
  * Replaces the three bias-free nn.Linear(F,F) that TensorNet applies to I / A / S (models/tensornet.py:752-754, :808-810,
  * :607-615; cuBLAS SGEMMs in the reference) by one grouped 3xTF32 tcgen05 GEMM that reads the fp32 irreps directly (the

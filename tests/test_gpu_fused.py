@@ -36,13 +36,15 @@ def test_pair_index():
     assert torch.equal(pidx.pair_r[:P], g.dist[:E][ce])
 
 
-@pytest.mark.parametrize("tc", ["f16", "tf32", False])
+@pytest.mark.parametrize("tc", ["table", "f16", "tf32", False])
 @pytest.mark.parametrize("cfg", ["interaction", "embedding", "single_act"])
 def test_pair_chain_value_and_tangent(cfg, tc, monkeypatch):
-    """tc='f16'/'tf32': tcgen05 GEMM chain with fp16 / tf32 split terms (tmd_pair_chain_tc); False: fp32 CUDA-core chain."""
+    """tc='f16'/'tf32': tcgen05 GEMM chain with fp16 / tf32 split terms (tmd_pair_chain_tc); False: fp32 CUDA-core chain;
+    'table': the validated per-model table of the frozen chain (tmd_radial_table) -- all against torch autograd."""
     from torchmdnet_b200.extensions import fused
     monkeypatch.setattr(fused, "USE_TENSOR_CORES", bool(tc))
-    monkeypatch.setattr(fused, "USE_F16_SPLIT", tc == "f16")
+    monkeypatch.setattr(fused, "USE_F16_SPLIT", tc in ("f16", "table"))
+    monkeypatch.setattr(fused, "USE_RADIAL_TABLE", tc == "table")
     from torchmdnet_b200.models.utils import ExpNormalSmearing, CosineCutoff
     torch.manual_seed(0)
     R, F = 32, 128
@@ -64,6 +66,11 @@ def test_pair_chain_value_and_tangent(cfg, tc, monkeypatch):
     r.data[:5] = torch.tensor([0.0, 4.9999, 5.0, 5.2, 1e-3], device=dev)
     nu = torch.tensor([P], device=dev, dtype=torch.int32)
     f, fp = fused.run_chain(chain, r.detach(), nu, rbf, 0.0, 5.0, True)
+    if tc == "table":
+        rep = chain.table_report   # the gate accepted a table: error vs fp64 below 2e-6, vs the exact GPU chain below 1e-5
+        print(cfg, rep)
+        assert chain.table(rbf, 0.0, 5.0) is not None and rep["err_f_vs_fp64"] < 2e-6 and rep["err_fp_vs_fp64"] < 2e-6
+        assert rep["err_f_vs_exact"] < 1e-5 and rep["err_fp_vs_exact"] < 1e-5
     x = rbf(r)
     if cfg == "interaction":
         for l in lins:

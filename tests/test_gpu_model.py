@@ -55,15 +55,18 @@ CASES = [os.path.basename(f)[:-3] for f in sorted(glob.glob(os.path.join(GOLDEN,
          if "neighbor" not in f and "caffeine_tensornet_q2" not in f]
 
 
-@pytest.mark.parametrize("path", ["fused", "composed"])
+@pytest.mark.parametrize("path", ["fused", "fused_exact", "composed"])
 @pytest.mark.parametrize("name", CASES)
-def test_golden_energy_forces(name, path):
-    """path=fused: pair pipeline (tmd_pair_chain + fused message-passing backward); path=composed: the autograd-composed
-    granular kernels (what training uses).  ET has a single path."""
+def test_golden_energy_forces(name, path, monkeypatch):
+    """path=fused: pair pipeline with the radial functions read from their validated tables (default inference path);
+    path=fused_exact: same with the exact tcgen05 chain for every pair (tables off); path=composed: the autograd-composed
+    granular kernels (what training uses)."""
+    from torchmdnet_b200.extensions import fused as fused_mod
+    monkeypatch.setattr(fused_mod, "USE_RADIAL_TABLE", path == "fused")
     fx = torch.load(os.path.join(GOLDEN, name + ".pt"), weights_only=False)
     m = build(fx)
-    m.representation_model.fused_edge_path = None if path == "fused" else False
-    if path == "fused":
+    m.representation_model.fused_edge_path = False if path == "composed" else None
+    if path != "composed":
         if fx["hparams"]["model"] == "tensornet" or fx["hparams"]["embedding_dimension"] <= 128:
             assert m.representation_model._fused_path_ok()
         else:

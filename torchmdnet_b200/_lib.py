@@ -58,6 +58,7 @@ SIGNATURES = {
     "tmd_pair_chain": ([P, P, I, P, P, P, P, P, P, P, I, I, I, P, P, D, D, D, P, P, P], 1),
     "tmd_pair_chain_tc": ([P, P, I, P, P, P, P, I, I, I, P, P, D, D, D, P, P, P, P, P, P, P, P, I, P], 3),
     "tmd_irreps_linear_tc": ([P, P, P, I, I, P, P, P, P, P, P], 1),
+    "tmd_radial_table": ([P, P, I, P, I, D, I, P, P], 1),
     "tmd_pair_rbf_split": ([P, P, I, I, I, P, P, D, D, D, P, P, I, P], 1),
     "tmd_mp_pair_bwd": ([P] * 11 + [I, I] + [P] * 4 + [P], 1),
     "tmd_et_msg_fwd": ([P] * 10 + [D, D, I, I, I, I, P, P, P], 1),

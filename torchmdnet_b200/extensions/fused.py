@@ -6,7 +6,9 @@ message passing is a single gather kernel that emits dE/dr per pair.  Training (
 using the autograd-composed ops of tensornet_ops.py.
 """
 import ctypes
+import math
 import os
+import warnings
 from typing import NamedTuple, Optional, Sequence
 
 import torch
@@ -21,6 +23,11 @@ p = _lib.ptr
 USE_TENSOR_CORES = True
 # fp16 (hi, lo) split terms instead of tf32 ones when a host-side bound proves every hidden activation / tangent fits fp16
 USE_F16_SPLIT = True
+# read the radial functions of a frozen model from a validated per-model table instead of re-evaluating the
+# chain for every pair of every frame (TMD_RADIAL_TABLE=0 or this flag off -> always the exact tcgen05 / FFMA chain)
+USE_RADIAL_TABLE = os.environ.get("TMD_RADIAL_TABLE", "1") != "0"
+TABLE_TOL = 2e-6          # interpolation vs the fp64 evaluation, relative to max|f| resp. max|f'|
+TABLE_TOL_EXACT = 1e-5    # interpolation vs the exact GPU chain (SURVEY's gate)
 
 
 class PairIndex(NamedTuple):
@@ -127,6 +134,83 @@ class RadialChain:
             self._tc_key = self._key
         return self._tc
 
+    # ---- tabulated radial function ------------------------------------------------------------------
+    def _eval_fp64(self, rbf_mod, lo: float, hi: float, r: Tensor):
+        """f(r), f'(r) of this chain in fp64 (torch, forward-mode): table nodes and the reference of the gate."""
+        means, betas = rbf_mod.means.detach().double(), rbf_mod.betas.detach().double()
+        alpha = float(rbf_mod.alpha)
+
+        def cos_cut(d, a, b):
+            if a > 0:
+                return 0.5 * (torch.cos(math.pi * (2 * (d - a) / (b - a) + 1.0)) + 1.0) * (d < b) * (d > a)
+            return 0.5 * (torch.cos(d * math.pi / b) + 1.0) * (d < b)
+
+        def fn(rr):
+            d = rr.unsqueeze(-1)
+            x = cos_cut(d, 0.0, hi) * torch.exp(-betas * (torch.exp(alpha * (lo - d)) - means) ** 2)
+            for layer in self.layers:
+                W = torch.cat([m.weight.detach() for m in layer], 0).double()
+                b = torch.cat([m.bias.detach() if m.bias is not None else m.weight.new_zeros(m.out_features) for m in layer], 0).double()
+                x = torch.nn.functional.linear(x, W, b)
+                if self.act:
+                    x = torch.nn.functional.silu(x)
+            if self.mul_cutoff:
+                x = x * cos_cut(d, lo, hi)
+            return x
+
+        return torch.func.jvp(fn, (r,), (torch.ones_like(r),))
+
+    def table(self, rbf_mod, lo: float, hi: float):
+        """-> (table [n_int,4,N] fp32, n_int, h) or None.  Built once per weight version: nodes at i*2^-k evaluated in fp64,
+        accepted only if the CUDA interpolation reproduces the fp64 function (TABLE_TOL) and the exact GPU chain
+        (TABLE_TOL_EXACT) at 3 interior points of every interval; refined (k -> k+1) until it does, else None."""
+        from ..models.utils import ExpNormalSmearing
+        if not isinstance(rbf_mod, ExpNormalSmearing):
+            return None
+        self.tensors()
+        key = (self._key, float(lo), float(hi), rbf_mod.means.data_ptr(), rbf_mod.means._version, rbf_mod.betas._version)
+        if getattr(self, "_tab_key", None) == key:
+            return self._tab
+        if torch.cuda.is_current_stream_capturing():
+            return None                       # cannot validate (host sync) inside a capture; the warm-up pass builds it
+        dev = self._wt[0].device
+        N = self._wt[-1].shape[1]
+        result = None
+        with torch.no_grad():
+            for k in (9, 10, 11, 12):
+                h = 2.0 ** -k
+                n_int = int(math.ceil(hi / h))
+                nodes = torch.arange(n_int + 1, device=dev, dtype=torch.float64) * h
+                f, fp = self._eval_fp64(rbf_mod, lo, hi, nodes)
+                m = fp * h
+                tab = torch.stack([f[:-1], f[1:] - f[:-1], m[:-1], m[1:]], 1).float().contiguous()
+                # gate: three interior points per interval, through the CUDA kernel
+                rt = ((torch.arange(n_int, device=dev, dtype=torch.float64).unsqueeze(1) +
+                       torch.tensor([0.25, 0.5, 0.75], device=dev, dtype=torch.float64)) * h).reshape(-1)
+                rt = rt[rt < hi]
+                f64, fp64 = self._eval_fp64(rbf_mod, lo, hi, rt)
+                r32 = rt.float()
+                nu = torch.tensor([r32.numel()], device=dev, dtype=torch.int32)
+                fi = torch.empty(r32.numel(), N, device=dev, dtype=torch.float32)
+                fpi = torch.empty_like(fi)
+                _lib.call("tmd_radial_table", p(r32), p(nu), r32.numel(), p(tab), n_int, h, N, p(fi), p(fpi), device=dev)
+                sf, sfp = f64.abs().max().clamp_min(1e-30), fp64.abs().max().clamp_min(1e-30)
+                e_f = ((fi.double() - f64).abs().max() / sf).item()
+                e_fp = ((fpi.double() - fp64).abs().max() / sfp).item()
+                if e_f < TABLE_TOL and e_fp < TABLE_TOL:
+                    fe, fpe = run_chain(self, r32, nu, rbf_mod, lo, hi, True, exact=True)
+                    x_f = ((fi - fe).abs().max() / sf).item()
+                    x_fp = ((fpi - fpe).abs().max() / sfp).item()
+                    if x_f < TABLE_TOL_EXACT and x_fp < TABLE_TOL_EXACT:
+                        result = (tab, n_int, h)
+                        self.table_report = {"k": k, "intervals": n_int, "bytes": tab.numel() * 4, "err_f_vs_fp64": e_f,
+                                             "err_fp_vs_fp64": e_fp, "err_f_vs_exact": x_f, "err_fp_vs_exact": x_fp}
+                    else:
+                        warnings.warn(f"radial table disagrees with the exact chain ({x_f:.1e}, {x_fp:.1e}); using the exact path")
+                    break
+        self._tab_key, self._tab = key, result
+        return result
+
     def f16_safe(self, rbf_mod, lo: float, hi: float) -> bool:
         """Conservative bound on |hidden activations| and |d/dr| of the chain (infinity-norm of each weight, |SiLU'| <= 1.1):
         fp16 operands are used only if everything stays below 3e4 and hidden widths are multiples of 64."""
@@ -193,8 +277,11 @@ def precompute_rbf(pair_r: Tensor, num_unique: Tensor, rbf_mod, lo: float, hi: f
 
 
 def shared_rbf_operand(chains, pair_r: Tensor, num_unique: Tensor, rbf_mod, lo: float, hi: float, want_tangent: bool):
-    """One layer-0 operand for all radial chains of a frame when they agree on the operand type (fp16 / tf32)."""
+    """One layer-0 operand for all radial chains of a frame when they agree on the operand type (fp16 / tf32); none when every
+    chain is read from its table."""
     if not USE_TENSOR_CORES or not all(c.supported_tc() for c in chains):
+        return None
+    if USE_RADIAL_TABLE and all(c.table(rbf_mod, lo, hi) is not None for c in chains):
         return None
     modes = {c.f16_safe(rbf_mod, lo, hi) for c in chains}
     if len(modes) != 1:
@@ -212,13 +299,20 @@ def _chain_launches(dims, n_layers, f16, tangent, act, have_rbf):
 
 
 def run_chain(chain: RadialChain, pair_r: Tensor, num_unique: Tensor, rbf_mod, lo: float, hi: float, want_tangent: bool,
-              rbf_op: Optional[RbfOperand] = None):
-    """-> (f [P,N_last], f' or None).  `rbf_mod` is the ExpNormalSmearing module (means/betas/alpha)."""
+              rbf_op: Optional[RbfOperand] = None, exact: bool = False):
+    """-> (f [P,N_last], f' or None).  `rbf_mod` is the ExpNormalSmearing module (means/betas/alpha).  Unless `exact`, a frozen
+    chain is read from its validated table; the exact tcgen05 / FFMA chain is the fallback and the gate."""
     wt, b, dims = chain.tensors()
     P = pair_r.shape[0]
     n_last = wt[-1].shape[1]
     f = torch.empty(P, n_last, device=pair_r.device, dtype=torch.float32)
     fp = torch.empty_like(f) if want_tangent else None
+    if USE_RADIAL_TABLE and not exact and P > 0 and n_last % 4 == 0:
+        tab = chain.table(rbf_mod, lo, hi)
+        if tab is not None:
+            _lib.call("tmd_radial_table", p(pair_r), p(num_unique), P, p(tab[0]), tab[1], tab[2], n_last, p(f), p(fp),
+                      device=pair_r.device)
+            return f, fp
     if USE_TENSOR_CORES and chain.supported_tc() and P > 0:
         f16 = chain.f16_safe(rbf_mod, lo, hi)
         his, los, p_hi, p_lo, p_b = chain.tc_tensors(f16)
