@@ -185,3 +185,36 @@ def test_rotation_invariance_and_force_equivariance(kind):
         y2, f2 = m(z.to(dev), (pos.to(dev) @ R.T).contiguous(), batch.to(dev))
         assert (y1 - y2).abs().max() < 2e-5 * (1 + y1.abs().max())
         assert (f1 @ R.T - f2).abs().max() < 5e-5 * (1 + f1.abs().max())
+
+
+@pytest.mark.parametrize("boxed", [False, True])
+def test_external_adapter(boxed):
+    """reference tests/test_calculator.py:15-82: the TorchMD adapter `External` with and without CUDA-graph
+    capture agrees over repeated calls with changing positions; replicas are independent systems; output transform presets."""
+    import copy
+    from torchmdnet_b200.calculators import External
+    hp = systems.tensornet_hparams(num_layers=2, F=128, R=32, max_nb=128, static_shapes=True)
+    m = seeded_model(hp, 5).eval().to(dev)
+    z, pos, _, _ = systems.molecule_batch(n_mol=1, seed=2)
+    n = z.numel()
+    emb = torch.stack([z, z])                                   # two replicas of the same molecule
+    g = torch.Generator().manual_seed(3)
+    pos2 = torch.cat([pos, pos + 0.05 * torch.randn(n, 3, generator=g)]).float()
+    box = (torch.eye(3) * 4 * hp["cutoff_upper"]) if boxed else None
+    calc = External(m, emb, device="cuda:0", use_cuda_graph=False)
+    calc_g = External(copy.deepcopy(m), emb, device="cuda:0", use_cuda_graph=True, cuda_graph_warmup_steps=3)
+    for it in range(4):
+        p = pos2 + 0.02 * it * torch.randn(2 * n, 3, generator=g)
+        e0, f0 = calc.calculate(p, box)
+        e1, f1 = calc_g.calculate(p, box)
+        assert e0.shape == (2, 1) and f0.shape == (2, n, 3) and f1.shape == (2, n, 3)
+        torch.testing.assert_close(e0, e1, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(f0, f1, rtol=3e-4, atol=1e-5)
+    # replica 0 alone gives the same energy and forces (no cross-replica edges)
+    y, f = m(z.to(dev), p[:n].to(dev), torch.zeros(n, dtype=torch.long, device=dev), box=None if box is None else box.to(dev))
+    torch.testing.assert_close(e0[0], y[0], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(f0[0], f, rtol=3e-4, atol=1e-5)
+    ek, fk = External(m, emb, device="cuda:0", output_transform="eV/A -> kcal/mol/A").calculate(p, box)
+    torch.testing.assert_close(ek, e0 * 23.0609)
+    with pytest.raises(ValueError):
+        External(m, emb, device="cpu")

@@ -6,10 +6,18 @@ docs/source/usage.rst:132).  `CUDAGraphForceField` is that capability for the B2
 model must be built with `static_shapes=True` (capacity-sized neighbour buffers + device-side counters:
 nothing in the frame depends on a host-visible shape, so ~250 launches replay with zero CPU work).
 """
+import warnings
 from typing import Optional, Tuple
 
 import torch
 from torch import Tensor
+
+# preset output transforms of the reference adapter (torchmdnet/calculators.py:9-23; the misspelt name is the reference's)
+tranforms = {
+    "eV/A -> kcal/mol/A": lambda energy, forces: (energy * 23.0609, forces * 23.0609),
+    "Hartree/Bohr -> kcal/mol/A": lambda energy, forces: (energy * 627.509, forces * 627.509 / 0.529177),
+    "Hartree/A -> kcal/mol/A": lambda energy, forces: (energy * 627.509, forces * 627.509),
+}
 
 
 class CUDAGraphForceField:
@@ -69,3 +77,76 @@ class CUDAGraphForceField:
             self.pos.copy_(pos, non_blocking=True)
         self.graph.replay()
         return self.energy, self.forces
+
+
+class External:
+    """TorchMD adapter with the reference's interface (torchmdnet/calculators.py:26-177):
+    `External(netfile, embeddings, device, output_transform, use_cuda_graph, cuda_graph_warmup_steps, dtype, **kwargs)` and
+    `calculate(pos, box) -> (energy [n_replicas,1], forces [n_replicas,n_atoms,3])`.
+
+    `embeddings` is [n_replicas, n_atoms] atomic numbers; replicas are independent systems (batch ids 0..n_replicas-1).
+    With `use_cuda_graph=True` the whole frame is captured once (static shapes) and replayed: positions and box are copied into
+    the graph's static buffers every call.  This package has no CPU path: `device` must be a CUDA device."""
+
+    def __init__(self, netfile, embeddings, device="cuda", output_transform=None, use_cuda_graph=False,
+                 cuda_graph_warmup_steps=12, dtype=torch.float32, **kwargs):
+        from .models.model import load_model
+        if not str(device).startswith("cuda"):
+            raise ValueError("torchmdnet_b200 runs on CUDA devices only (sm_100a); there is no CPU path")
+        if isinstance(netfile, str):
+            extra_args = dict(kwargs)
+            if use_cuda_graph:
+                warnings.warn("CUDA graphs are enabled, setting static_shapes=True")
+                extra_args["static_shapes"] = True
+            self.model = load_model(netfile, device=device, derivative=True, **extra_args)
+        elif isinstance(netfile, torch.nn.Module):
+            if kwargs:
+                warnings.warn("Warning: extra arguments are being ignored when passing a torch.nn.Module")
+            self.model = netfile
+        else:
+            raise ValueError(f"Expected a path to a checkpoint file or a torch.nn.Module, got {type(netfile)}")
+        self.device = device
+        self.n_atoms = embeddings.size(1)
+        self.n_replicas = embeddings.size(0)
+        self.embeddings = embeddings.reshape(-1).to(device)
+        self.batch = torch.arange(embeddings.size(0), device=device).repeat_interleave(embeddings.size(1))
+        self.model.eval()
+        if not output_transform:
+            self.output_transformer = lambda energy, forces: (energy, forces)
+        elif output_transform in tranforms:
+            self.output_transformer = tranforms[output_transform]
+        elif callable(output_transform):
+            self.output_transformer = output_transform
+        else:
+            raise ValueError(f"Unknown output_transform {output_transform!r}: a key of `tranforms` or a callable")
+        self.use_cuda_graph = use_cuda_graph
+        self.cuda_graph_warmup_steps = cuda_graph_warmup_steps
+        self._ff = None
+        if isinstance(dtype, str):
+            try:
+                dtype = getattr(torch, dtype)
+            except AttributeError:
+                raise ValueError(f"Unknown torch dtype {dtype}")
+        if dtype != torch.float32:
+            raise ValueError("the B200 TensorNet / ET kernels compute in float32")
+        self.dtype = dtype
+
+    def calculate(self, pos, box=None):
+        pos = pos.to(self.device).to(self.dtype).reshape(-1, 3)
+        if box is not None:
+            box = box.to(self.device).to(self.dtype)
+        if self.use_cuda_graph:
+            if self._ff is None:
+                for p_ in self.model.parameters():   # inference adapter: weights are constants of the captured frame
+                    p_.requires_grad_(False)
+                self._ff = CUDAGraphForceField(self.model, self.embeddings, self.batch, box=box, num_systems=self.n_replicas,
+                                               warmup=self.cuda_graph_warmup_steps)
+            elif box is not None:
+                with torch.no_grad():
+                    self._ff.box.copy_(box)
+            energy, forces = self._ff(pos.detach())
+        else:
+            energy, forces = self.model(self.embeddings, pos, self.batch, box=box, num_systems=self.n_replicas)
+        assert forces is not None, "The model is not returning forces"
+        assert energy is not None, "The model is not returning energy"
+        return self.output_transformer(energy.clone().detach(), forces.clone().reshape(-1, self.n_atoms, 3).detach())
