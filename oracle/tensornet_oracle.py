@@ -221,26 +221,8 @@ def _lin(sd, key, x, bias=True):
 # --------------------------------------------------------------------------------------
 # a5-a10  TensorNet representation
 # --------------------------------------------------------------------------------------
-def tensornet_representation(sd: StateDict, hp: dict, z, ei, vec, dist, q_atom, prefix="representation_model."):
-    """models/tensornet.py:308-402 (TensorNet.forward), :543-619 (TensorEmbedding.forward),
-    :729-814 (Interaction.forward), with the pure-PyTorch message passing :405-445, :622-679."""
-    F_ = int(hp["embedding_dimension"])
-    lo, hi = float(hp["cutoff_lower"]), float(hp["cutoff_upper"])
-    act = _act(hp["activation"])
-    group = hp.get("equivariance_invariance_group", "O(3)")
-    n = z.shape[0]
-    i, j = ei[0], ei[1]
-    p = prefix
-    if hp["rbf_type"] == "expnorm":
-        rbf = expnorm_rbf(dist, sd[p + "distance_expansion.means"], sd[p + "distance_expansion.betas"], lo, hi)
-    else:
-        rbf = gauss_rbf(dist, sd[p + "distance_expansion.offset"], sd[p + "distance_expansion.coeff"])
-    self_mask = i == j
-    rhat = vec / dist.masked_fill(self_mask, 1).unsqueeze(1)  # tensornet.py:363-366
-    C = cosine_cutoff(dist, lo, hi)
-
-    # ---- embedding (tensornet.py:526-619)
-    te = p + "tensor_embedding."
+def _tensor_embedding(sd: StateDict, te: str, F_: int, act, z, i, j, rhat, rbf, C, n: int) -> Tensor:
+    """models/tensornet.py:526-619 (TensorEmbedding.forward) -> X [N,3,3,F]; shared by TensorNet and TensorNet2."""
     Z = sd[te + "emb.weight"][z]
     Zij = _lin(sd, te + "emb2", torch.cat([Z[i], Z[j]], dim=-1))
     w = (C[:, None] * Zij)[:, None, :] * torch.stack(
@@ -260,7 +242,29 @@ def tensornet_representation(sd: StateDict, hp: dict, z, ei, vec, dist, q_atom, 
     I = Fn.linear(I, sd[te + "linears_tensor.0.weight"]) * nrm[:, 0]
     A = Fn.linear(A, sd[te + "linears_tensor.1.weight"]) * nrm[:, 1, None, None, :]
     S = Fn.linear(S, sd[te + "linears_tensor.2.weight"]) * nrm[:, 2, None, None, :]
-    X = compose(I, A, S)
+    return compose(I, A, S)
+
+
+def tensornet_representation(sd: StateDict, hp: dict, z, ei, vec, dist, q_atom, prefix="representation_model."):
+    """models/tensornet.py:308-402 (TensorNet.forward), :543-619 (TensorEmbedding.forward),
+    :729-814 (Interaction.forward), with the pure-PyTorch message passing :405-445, :622-679."""
+    F_ = int(hp["embedding_dimension"])
+    lo, hi = float(hp["cutoff_lower"]), float(hp["cutoff_upper"])
+    act = _act(hp["activation"])
+    group = hp.get("equivariance_invariance_group", "O(3)")
+    n = z.shape[0]
+    i, j = ei[0], ei[1]
+    p = prefix
+    if hp["rbf_type"] == "expnorm":
+        rbf = expnorm_rbf(dist, sd[p + "distance_expansion.means"], sd[p + "distance_expansion.betas"], lo, hi)
+    else:
+        rbf = gauss_rbf(dist, sd[p + "distance_expansion.offset"], sd[p + "distance_expansion.coeff"])
+    self_mask = i == j
+    rhat = vec / dist.masked_fill(self_mask, 1).unsqueeze(1)  # tensornet.py:363-366
+    C = cosine_cutoff(dist, lo, hi)
+
+    X = _tensor_embedding(sd, p + "tensor_embedding.", F_, act, z, i, j, rhat, rbf, C, n)
+    dt = X.dtype
 
     # ---- interaction layers (tensornet.py:729-814)
     qf = (1 + 0.1 * q_atom.to(dt))[:, None, None, None]
@@ -297,6 +301,130 @@ def tensornet_representation(sd: StateDict, hp: dict, z, ei, vec, dist, q_atom, 
     x = torch.cat([3 * I ** 2, tnorm(A), tnorm(S)], dim=-1)
     x = Fn.layer_norm(x, (3 * F_,), sd[p + "out_norm.weight"], sd[p + "out_norm.bias"])
     return act(_lin(sd, p + "linear", x))
+
+
+# --------------------------------------------------------------------------------------
+# TensorNet2 (neutral charge equilibration) + ScalarPlusWeightedCoulomb
+# (oracle first: the GPU path for this row is not built yet; these functions and their goldens pin the arithmetic)
+# --------------------------------------------------------------------------------------
+def _mol_sum(x: Tensor, batch: Tensor, m: int) -> Tensor:
+    """tensornet2.py:65-100 (ChargePredict.mol_sum): per-molecule sum."""
+    return torch.zeros(m, x.shape[-1], dtype=x.dtype).index_add(0, batch, x)
+
+
+def charge_predict(sd: StateDict, key: str, X: Tensor, batch: Tensor, Q_atom: Tensor, q_dim: int, act, m: int) -> Tensor:
+    """tensornet2.py:142-157 (ChargePredict.forward, pure-PyTorch branch) and :102-140 (qeq):
+    features (I, |A|^2, |S|^2) -> LayerNorm -> MLP(3F -> F -> F -> 2 q_dim) -> (charges, f);
+    new_charges = charges + f^2 / (sum_mol f^2 + 1e-6) * (Q - sum_mol charges)."""
+    I, A, S = decompose(X)
+    x = torch.cat([I, tnorm(A), tnorm(S)], dim=-1)
+    F3 = x.shape[-1]
+    x = Fn.layer_norm(x, (F3,), sd[key + "q_norm.weight"], sd[key + "q_norm.bias"])
+    x = act(_lin(sd, key + "q_mlp.layers.0", x))
+    x = act(_lin(sd, key + "q_mlp.layers.2", x))
+    x = _lin(sd, key + "q_mlp.layers.4", x)
+    charges, f = x[:, :q_dim], x[:, q_dim:]
+    f_u = f ** 2
+    F_u = _mol_sum(f_u, batch, m) + 1.0e-6
+    Q_u = _mol_sum(charges, batch, m)
+    dQ = Q_atom.to(x.dtype).unsqueeze(-1) - Q_u[batch]
+    return charges + f_u / F_u[batch] * dQ
+
+
+def tensornet2_representation(sd: StateDict, hp: dict, z, ei, vec, dist, batch, q_mol, prefix="representation_model."):
+    """models/tensornet2.py:343-462 (TensorNet2.forward, pure-PyTorch branch) and :519-626 (Interaction.forward): the TensorNet
+    embedding (tensornet.py:543-619), then per layer an edge MLP on cat(rbf, q_i, q_j) (NOT a function of r alone and not
+    symmetric in (i, j)), the TensorNet tensor update without the (1 + 0.1 q) factor, and a charge re-equilibration."""
+    F_ = int(hp["embedding_dimension"])
+    q_dim = int(hp["q_dim"])
+    lo, hi = float(hp["cutoff_lower"]), float(hp["cutoff_upper"])
+    act = _act(hp["activation"])
+    group = hp.get("equivariance_invariance_group", "O(3)")
+    n = z.shape[0]
+    m = int(batch.max()) + 1
+    i, j = ei[0], ei[1]
+    p = prefix
+    rbf = expnorm_rbf(dist, sd[p + "distance_expansion.means"], sd[p + "distance_expansion.betas"], lo, hi) \
+        if hp["rbf_type"] == "expnorm" else gauss_rbf(dist, sd[p + "distance_expansion.offset"], sd[p + "distance_expansion.coeff"])
+    rhat = vec / dist.masked_fill(i == j, 1).unsqueeze(1)
+    C = cosine_cutoff(dist, lo, hi)
+    Q_atom = torch.zeros(n, dtype=dist.dtype) if q_mol is None else q_mol[batch].to(dist.dtype)
+    X = _tensor_embedding(sd, p + "tensor_embedding.", F_, act, z, i, j, rhat, rbf, C, n)
+    charges = [charge_predict(sd, p + "charge_predict_0.", X, batch, Q_atom, q_dim, act, m)]
+    for l in range(int(hp["num_layers"])):
+        lp = p + f"layers.{l}."
+        f = torch.cat([rbf, charges[-1][i], charges[-1][j]], dim=-1)
+        for k in range(3):
+            f = act(_lin(sd, lp + f"linears_scalar.{k}", f))
+        f = (f * C[:, None]).reshape(-1, 3, F_)
+        X = X / (tnorm(X) + 1)[:, None, None, :]
+        I, A, S = decompose(X)
+        I = Fn.linear(I, sd[lp + "linears_tensor.0.weight"])
+        A = Fn.linear(A, sd[lp + "linears_tensor.1.weight"])
+        S = Fn.linear(S, sd[lp + "linears_tensor.2.weight"])
+        Y = compose(I, A, S)
+        Im = torch.zeros_like(I).index_add(0, i, f[:, 0] * I[j])
+        Am = torch.zeros_like(A).index_add(0, i, f[:, 1, None, None, :] * A[j])
+        Sm = torch.zeros_like(S).index_add(0, i, f[:, 2, None, None, :] * S[j])
+        M = compose(Im, Am, Sm)
+        Cn = (mm3(M, Y) + mm3(Y, M)) if group == "O(3)" else 2 * mm3(Y, M)
+        I, A, S = decompose(Cn)
+        np1 = tnorm(Cn) + 1
+        I = Fn.linear(I / np1, sd[lp + "linears_tensor.3.weight"])
+        A = Fn.linear(A / np1[:, None, None, :], sd[lp + "linears_tensor.4.weight"])
+        S = Fn.linear(S / np1[:, None, None, :], sd[lp + "linears_tensor.5.weight"])
+        dX = compose(I, A, S)
+        X = X + dX + mm3(dX, dX)
+        charges.append(charge_predict(sd, p + f"charge_predicts.{l}.", X, batch, Q_atom, q_dim, act, m))
+    I, A, S = decompose(X)
+    x = torch.cat([3 * I ** 2, tnorm(A), tnorm(S)], dim=-1)
+    x = Fn.layer_norm(x, (3 * F_,), sd[p + "out_norm.weight"], sd[p + "out_norm.bias"])
+    x = act(_lin(sd, p + "linear", x))
+    return x, torch.cat(charges, dim=-1)
+
+
+def exp_cutoff(d: Tensor, rc: float) -> Tensor:
+    """output_modules.py:321-330 (_exp_cutoff): short-range damping taken from aimnet."""
+    return torch.exp(-1.0 / (1.0 - (d / rc).clamp(0, 1.0 - 1e-6).pow(2))) / 0.36787944117144233
+
+
+def weighted_coulomb_per_atom(hp: dict, charges: Tensor, pos: Tensor, batch: Tensor, box: Optional[Tensor]) -> Tensor:
+    """output_modules.py:344-609 (ScalarPlusWeightedCoulomb.pre_reduce): damped Coulomb energy of the predicted charge channels,
+    weighted mean over channels, split equally between the two atoms of a pair.  coulomb_cutoff None: all pairs of a molecule;
+    else pairs within the cutoff (half list, minimum image) with the reaction-field form."""
+    q_dim, L = int(hp["q_dim"]), int(hp["num_layers"])
+    w = torch.tensor([float(hp["q_weights"][l]) for l in range(L + 1)], dtype=charges.dtype).repeat_interleave(q_dim)
+    factor = 0.5 * 27.211386024367243 * 0.5291772105638411
+    n = pos.shape[0]
+    rc = hp.get("coulomb_cutoff", None)
+    ii, jj = torch.triu_indices(n, n, 1).unbind(0)
+    keep = batch[ii] == batch[jj]
+    ii, jj = ii[keep], jj[keep]
+    d = pos[ii] - pos[jj]
+    if rc is None:
+        assert box is None, "PBC is not supported with coulomb_cutoff = None"
+        r = torch.linalg.norm(d, dim=-1)
+        shape = 1.0 / r
+    else:
+        if box is not None:
+            b = box if box.dim() == 3 else box[None].expand(int(batch.max()) + 1, 3, 3)
+            bb = b[batch[ii]].to(d.dtype)
+            # triclinic minimum image in the reference's order z, y, x (SURVEY appendix A.1)
+            s3 = round_half_away(d[:, 2] / bb[:, 2, 2]); d = d - s3[:, None] * bb[:, 2]
+            s2 = round_half_away(d[:, 1] / bb[:, 1, 1]); d = d - s2[:, None] * bb[:, 1]
+            s1 = round_half_away(d[:, 0] / bb[:, 0, 0]); d = d - s1[:, None] * bb[:, 0]
+        r = torch.linalg.norm(d, dim=-1)
+        inside = r < float(rc)
+        ii, jj, r = ii[inside], jj[inside], r[inside]
+        eps = float(hp.get("coulomb_epsilon_solvent", 78.3))
+        k_rf = (1.0 / rc ** 3) * (eps - 1.0) / (2.0 * eps + 1.0)
+        c_rf = (1.0 / rc) * (3.0 * eps) / (2.0 * eps + 1.0)
+        shape = 1.0 / r + k_rf * r ** 2 - c_rf
+    fc = 1.0 - exp_cutoff(r, 4.6)
+    e_ij = factor * (fc * shape).unsqueeze(-1) * charges[ii] * charges[jj]
+    e_ij = (e_ij * w[None, :]).sum(-1) / w.sum()
+    e_i = torch.zeros(n, dtype=charges.dtype).index_add(0, ii, e_ij).index_add(0, jj, e_ij)
+    return e_i
 
 
 # --------------------------------------------------------------------------------------
@@ -392,6 +520,11 @@ def energy_and_forces(sd: StateDict, hp: dict, z: Tensor, pos: Tensor, batch: Op
         q_atom = torch.zeros(z.shape[0], dtype=pos.dtype) if q is None else q[batch]
         x = tensornet_representation(sd, hp, z, ei, vec, dist, q_atom)
         e = _lin(sd, "output_model.output_network.layers.2", act(_lin(sd, "output_model.output_network.layers.0", x)))
+    elif model == "tensornet2":
+        x, charges = tensornet2_representation(sd, hp, z, ei, vec, dist, batch, q)
+        e = _lin(sd, "output_model.output_network.layers.2", act(_lin(sd, "output_model.output_network.layers.0", x)))
+        if "Coul" in hp["output_model"]:
+            e = e + weighted_coulomb_per_atom(hp, charges, pos, batch, box).unsqueeze(-1)
     elif model == "equivariant-transformer":
         x, v = et_representation(sd, hp, z, ei, vec, dist)
         F_ = int(hp["embedding_dimension"])

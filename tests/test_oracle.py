@@ -104,3 +104,30 @@ def test_oracle_neighbors_match_numpy_reference():
 def test_round_half_away():
     x = torch.tensor([0.5, -0.5, 1.5, 2.5, -2.5, 0.49999997, 2.4, -2.6])
     assert torch.equal(orc.round_half_away(x), torch.tensor([1.0, -1.0, 2.0, 3.0, -3.0, 0.0, 2.0, -3.0]))
+
+
+@pytest.mark.parametrize("name", ["tn2_mol4_alltoall", "tn2_box120_rf"])
+def test_oracle_tensornet2_pinned(name):
+    """SURVEY 8(f) item 3, oracle first: TensorNet2 + ScalarPlusWeightedCoulomb (reference models/tensornet2.py,
+    output_modules.py:344-609) restated in the oracle and pinned to outputs of the unmodified reference
+    (oracle/make_golden_tn2.py: total molecular charges, all-pairs and reaction-field Coulomb, O(3) and SO(3)).
+    The GPU path of this row is not built yet; these fixtures live in tests/golden/next/ and feed only this test."""
+    fx = torch.load(os.path.join(GOLDEN, "next", name + ".pt"), weights_only=False)
+    hp, sd = fx["hparams"], fx["state_dict"]
+    g = lambda t, dt: None if t is None else t.to(dt)
+    y64, f64 = orc.energy_and_forces(orc.cast_state_dict(sd, torch.float64), hp, fx["z"], fx["pos"].double(), fx["batch"],
+                                     g(fx["box"], torch.float64), g(fx["q"], torch.float64))
+    assert (y64 - fx["ref_E64"]).abs().max() < 1e-11 * max(1.0, fx["ref_E64"].abs().max().item())
+    assert (f64 - fx["ref_F64"]).abs().max() < 1e-10 * fx["ref_F64"].abs().max().item()
+    y32, f32 = orc.energy_and_forces(sd, hp, fx["z"], fx["pos"], fx["batch"], fx["box"], fx["q"])
+    assert (y32 - fx["ref_E32"]).abs().max() < 2e-5 * max(1.0, fx["ref_E32"].abs().max().item())
+    assert (f32 - fx["ref_F32"]).abs().max() < 2e-5 * fx["ref_F32"].abs().max().item()
+    # the total charge is conserved by every charge head (qeq): sum of each channel per molecule == Q
+    import tensornet_oracle as o
+    ei, vec, dist = o.neighbor_list_from_pos(fx["pos"].double(), fx["batch"], g(fx["box"], torch.float64), hp, loop=True)
+    _, ch = o.tensornet2_representation(orc.cast_state_dict(sd, torch.float64), hp, fx["z"], ei, vec, dist, fx["batch"],
+                                        g(fx["q"], torch.float64))
+    m = int(fx["batch"].max()) + 1
+    tot = torch.zeros(m, ch.shape[1], dtype=ch.dtype).index_add(0, fx["batch"], ch)
+    Q = torch.zeros(m, dtype=ch.dtype) if fx["q"] is None else fx["q"].double()
+    assert (tot - Q[:, None]).abs().max() < 1e-3      # exact up to the epsilon = 1e-6 regulariser: dQ * eps / (sum f^2 + eps)
