@@ -42,7 +42,8 @@ def _worker(rank, world, port, q):
     tot, y, f, rng = parallel.sharded_energy_forces(ToyModel(), z, pos, batch, box=box)
     yall = parallel.gather_system_energies(y, parallel.partition_systems(sizes, world))
     lz, lpos, lbatch, lbox, _, rng2, sl = parallel.shard_batch(z, pos, batch, box, None, rank, world)
-    q.put((rank, tot.item(), yall, f, rng, (sl.start, sl.stop), int(lbatch.min()) if lbatch.numel() else 0, lbox.shape[0]))
+    # plain lists, not tensors: a tensor in an mp.Queue travels as a shared-memory handle that dies with this process
+    q.put((rank, tot.item(), yall.tolist(), f.tolist(), rng, (sl.start, sl.stop), int(lbatch.min()) if lbatch.numel() else 0, lbox.shape[0]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -66,6 +67,7 @@ def test_sharded_energy_two_ranks():
     z = torch.randint(1, 9, (pos.shape[0],), generator=g)
     yref, fref = ToyModel()(z, pos, batch, num_systems=5)
     for rank, tot, yall, f, rng, (a0, a1), bmin, nbox in res:
+        yall, f = torch.tensor(yall), torch.tensor(f).reshape(-1, 3)
         assert abs(tot - yref.sum().item()) < 1e-4          # one scalar all-reduce -> same total on every rank
         assert torch.allclose(yall, yref, atol=1e-5)         # optional all-gather of per-system energies
         assert torch.allclose(f, fref[a0:a1], atol=1e-6)     # forces stay local to the owning rank
