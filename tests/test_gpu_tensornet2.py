@@ -1,0 +1,35 @@
+"""-m gpu, OPT-IN (TMD_EXPERIMENTAL_TESTS=1): TensorNet2 + ScalarPlusWeightedCoulomb assembled from the TensorNet kernels
+(models/tensornet2.py) against the reference outputs in tests/golden/next/ (oracle/make_golden_tn2.py).
+
+Not part of the default GPU run yet: the model was written after the round's GPU budget was spent, so this file has never been
+executed on a B200.  The oracle side of the row is pinned (tests/test_oracle.py::test_oracle_tensornet2_pinned) and the host side
+is covered on the CPU (tests/test_tensornet2_host.py); running this file is the first step of the next round."""
+import os
+
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("TMD_EXPERIMENTAL_TESTS") != "1",
+                                 reason="TensorNet2 GPU forward not validated on hardware yet (set TMD_EXPERIMENTAL_TESTS=1)")]
+TOL = 1e-4
+
+
+@pytest.mark.parametrize("static_shapes", [False, True])
+@pytest.mark.parametrize("name", ["tn2_mol4_alltoall", "tn2_box120_rf"])
+def test_tensornet2_golden_energy_forces(name, static_shapes):
+    from torchmdnet_b200.models.model import create_model
+    dev = torch.device("cuda:0")
+    fx = torch.load(os.path.join(GOLDEN, "next", name + ".pt"), weights_only=False)
+    hp = dict(fx["hparams"]); hp["static_shapes"] = static_shapes
+    m = create_model(hp)
+    m.load_state_dict(fx["state_dict"])
+    m = m.eval().to(dev)
+    g = lambda t: None if t is None else t.to(dev)
+    y, f = m(fx["z"].to(dev), fx["pos"].to(dev).clone(), fx["batch"].to(dev), box=g(fx["box"]), q=g(fx["q"]))
+    eE = ((y.double().cpu() - fx["ref_E64"]).abs().max() / max(1.0, fx["ref_E64"].abs().max().item())).item()
+    eF = ((f.double().cpu() - fx["ref_F64"]).abs().max() / fx["ref_F64"].abs().max()).item()
+    print(f"{name} static={static_shapes}: relE={eE:.2e} relF={eF:.2e}")
+    assert eE < TOL and eF < TOL

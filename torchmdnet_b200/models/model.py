@@ -47,7 +47,13 @@ def create_model(args, prior_model=None, mean=None, std=None):
                                     distance_influence=args["distance_influence"],
                                     neighbor_embedding=args["neighbor_embedding"], vector_cutoff=args["vector_cutoff"],
                                     **shared)
-    elif kind in ("graph-network", "transformer", "tensornet2"):
+    elif kind == "tensornet2":
+        from .tensornet2 import TensorNet2   # host structure + composed forward (see the module docstring)
+        is_equivariant = False
+        representation = TensorNet2(equivariance_invariance_group=args["equivariance_invariance_group"],
+                                    static_shapes=args["static_shapes"], q_dim=args.get("q_dim", 0),
+                                    output_charges="Coul" in args["output_model"], **shared)
+    elif kind in ("graph-network", "transformer"):
         raise ValueError(f'architecture "{kind}" is outside the B200 hot-path scope (tensornet, equivariant-transformer)')
     else:
         raise ValueError(f'Unknown architecture: {kind}')
@@ -63,7 +69,10 @@ def create_model(args, prior_model=None, mean=None, std=None):
     output_model = getattr(output_modules, head_name)(
         args["embedding_dimension"], activation=args["activation"], reduce_op=args["reduce_op"], dtype=dtype,
         static_shapes=args.get("static_shapes", False), num_hidden_layers=args.get("output_mlp_num_layers", 0),
-        num_layers=0)
+        num_layers=args["num_layers"] if args["output_model"] == "ScalarPlusWeightedCoulomb" else 0,   # reference issue 343
+        q_dim=args.get("q_dim", 0), q_weights=args.get("q_weights", []), coulomb_cutoff=args.get("coulomb_cutoff", None),
+        coulomb_max_num_neighbors=args.get("coulomb_max_num_neighbors", None),
+        coulomb_neighbor_strategy=args.get("coulomb_neighbor_strategy", "brute"))
     return TorchMD_Net(representation, output_model, prior_model=prior_model, mean=mean, std=std,
                        derivative=args["derivative"], dtype=dtype)
 
@@ -121,13 +130,14 @@ def load_model(filepath, args=None, device="cpu", return_std=False, **kwargs):
     sd.setdefault("representation_model.distance.box", torch.zeros(3, 3))
 
     old_layout = "check_errors" in ckpt.get("hyper_parameters", {})
-    if kwargs.get("compatibility_load", old_layout) and args["model"] == "tensornet":
+    if kwargs.get("compatibility_load", old_layout) and args["model"] in ("tensornet", "tensornet2"):
         if old_layout and "compatibility_load" not in kwargs:
             warnings.warn("Old-format checkpoint detected ('check_errors' found in hyper_parameters). "
                           "Automatically applying compatibility_load to remap linear-layer weights. "
                           "Pass compatibility_load=False to suppress this.")
         keys = ["representation_model.tensor_embedding.linears_scalar.1"]
-        keys += [f"representation_model.layers.{l}.linears_scalar.2" for l in range(args["num_layers"])]
+        if args["model"] == "tensornet":   # TensorNet2 interaction layers keep their layout (reference model.py:299)
+            keys += [f"representation_model.layers.{l}.linears_scalar.2" for l in range(args["num_layers"])]
         for k in keys:
             sd[k + ".weight"], sd[k + ".bias"] = _remix_rows(sd[k + ".weight"], sd[k + ".bias"])
     model.load_state_dict(sd)
