@@ -142,6 +142,8 @@ class External:
                 self._ff = CUDAGraphForceField(self.model, self.embeddings, self.batch, box=box, num_systems=self.n_replicas,
                                                warmup=self.cuda_graph_warmup_steps)
             elif box is not None:
+                if self._ff.box is None:
+                    raise ValueError("the frame was captured without a box; pass the box on the first call when use_cuda_graph=True")
                 with torch.no_grad():
                     self._ff.box.copy_(box)
             energy, forces = self._ff(pos.detach())
