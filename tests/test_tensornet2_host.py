@@ -70,3 +70,18 @@ def test_all_pairs_coulomb_matches_oracle():
     assert (gg - gw).abs().max() < 1e-11 * max(1.0, gw.abs().max().item())
     with pytest.raises(ValueError):
         head.coulomb_per_atom(charges, fx["z"], pos, fx["batch"], torch.eye(3, dtype=torch.float64) * 30)
+
+
+def test_load_model_roundtrip_and_legacy_name(tmp_path):
+    """reference model.py:208-374: a Lightning-style checkpoint ('model.' key prefix, hyper_parameters) loads back bit-identically;
+    the development name of the architecture ('tensornet-nqe', model.py:244-247) maps to tensornet2."""
+    from torchmdnet_b200.models.model import load_model
+    fx = torch.load(os.path.join(NEXT, "tn2_box120_rf.pt"), weights_only=False)
+    hp = dict(fx["hparams"], model="tensornet-nqe")
+    path = str(tmp_path / "tn2.ckpt")
+    torch.save({"hyper_parameters": hp, "state_dict": {"model." + k: v for k, v in fx["state_dict"].items()}}, path)
+    m = load_model(path, derivative=True)
+    assert type(m.representation_model).__name__ == "TensorNet2" and type(m.output_model).__name__ == "ScalarPlusWeightedCoulomb"
+    sd = m.state_dict()
+    assert all(torch.equal(sd[k], v) for k, v in fx["state_dict"].items())
+    assert m.output_model.mode == "cutoff" and m.representation_model.output_charges
