@@ -85,6 +85,11 @@ def import_reference():
         raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
     if "torchmdnet" in sys.modules and getattr(sys.modules["torchmdnet"], "_is_reference", False):
         return sys.modules["torchmdnet"]
+    # the repo ships a `torchmdnet` alias package that resolves to the B200 build: never let it stand in for the reference
+    for name in [m for m in sys.modules if m == "torchmdnet" or m.startswith("torchmdnet.")]:
+        del sys.modules[name]
+    repo_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:] = [q for q in sys.path if os.path.abspath(q or ".") != repo_root] + [repo_root]
     # stub 1: lightning_utilities
     lu = types.ModuleType("lightning_utilities")
     lu_core = types.ModuleType("lightning_utilities.core")

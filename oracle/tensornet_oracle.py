@@ -120,13 +120,17 @@ def neighbor_list(
     return torch.stack([ei[order], ej[order]]), vec[order], dist[order]
 
 
-def neighbor_list_from_pos(pos, batch, box, hp, loop=True):
+def neighbor_list_from_pos(pos, batch, box, hp, loop=True, graph=None):
     """Differentiable wrt pos: indices from `neighbor_list`, vec/dist recomputed with
     autograd-tracked ops (the reference's backward is extensions/neighbor_utils.py:11-46,
     which is exactly d vec/d pos = +-1 and d dist/d vec = vec/dist, masked at dist==0)."""
     with torch.no_grad():
-        ei, vec0, dist0 = neighbor_list(pos.detach(), batch, box, float(hp["cutoff_lower"]),
-                                        float(hp["cutoff_upper"]), loop=loop)
+        if graph is not None:   # prebuilt (ei, vec0, dist0) on pos.device: lets a caller keep the host-side O(N^2) search out of a timed region
+            ei, vec0, dist0 = graph
+        else:
+            ei, vec0, dist0 = neighbor_list(pos.detach().cpu(), batch.cpu(), None if box is None else box.cpu(),
+                                            float(hp["cutoff_lower"]), float(hp["cutoff_upper"]), loop=loop)
+            ei, vec0, dist0 = ei.to(pos.device), vec0.to(pos.device), dist0.to(pos.device)
     i, j = ei[0], ei[1]
     shift = vec0 - (pos.detach()[i] - pos.detach()[j])  # integer box-vector combination
     vec = pos[i] - pos[j] + shift
@@ -175,7 +179,7 @@ def expnorm_initial_params(lo: float, hi: float, num_rbf: int, dtype=torch.float
 # a8  3x3 irreducible-tensor algebra, [N,3,3,F] layout (models/tensornet.py:18-146)
 # --------------------------------------------------------------------------------------
 def _eye(x):
-    return torch.eye(3, dtype=x.dtype)[None, :, :, None]
+    return torch.eye(3, dtype=x.dtype, device=x.device)[None, :, :, None]
 
 
 def skew(v: Tensor) -> Tensor:
@@ -221,18 +225,45 @@ def _lin(sd, key, x, bias=True):
 # --------------------------------------------------------------------------------------
 # a5-a10  TensorNet representation
 # --------------------------------------------------------------------------------------
-def _tensor_embedding(sd: StateDict, te: str, F_: int, act, z, i, j, rhat, rbf, C, n: int) -> Tensor:
+def _edge_sum(fn, E: int, edge_chunks: int, *edge_tensors):
+    """sum over edge chunks of fn(*[t[chunk] for t in edge_tensors]) (a tuple of per-atom tensors).  edge_chunks <= 1: one
+    call on all edges (the plain restatement).  edge_chunks > 1: the same arithmetic chunk by chunk under activation
+    checkpointing, so that a 10k-atom box fits in host memory in fp64 (per-edge intermediates [E,3,3,F] are the footprint);
+    only the order of the per-atom partial sums changes."""
+    if edge_chunks <= 1 or E == 0:
+        return fn(*edge_tensors)
+    from torch.utils.checkpoint import checkpoint
+    step = -(-E // edge_chunks)
+    total = None
+    for s in range(0, E, step):
+        part = checkpoint(fn, *[t[s:s + step] for t in edge_tensors], use_reentrant=False)
+        total = part if total is None else tuple(a + b for a, b in zip(total, part))
+    return total
+
+
+def _tensor_embedding(sd: StateDict, te: str, F_: int, act, z, i, j, rhat, rbf, C, n: int, edge_chunks: int = 0) -> Tensor:
     """models/tensornet.py:526-619 (TensorEmbedding.forward) -> X [N,3,3,F]; shared by TensorNet and TensorNet2."""
     Z = sd[te + "emb.weight"][z]
-    Zij = _lin(sd, te + "emb2", torch.cat([Z[i], Z[j]], dim=-1))
-    w = (C[:, None] * Zij)[:, None, :] * torch.stack(
-        [_lin(sd, te + "distance_proj1", rbf), _lin(sd, te + "distance_proj2", rbf), _lin(sd, te + "distance_proj3", rbf)],
-        dim=1)  # [E,3,F]
-    dt = w.dtype
-    I = torch.zeros(n, F_, dtype=dt).index_add(0, i, w[:, 0])
-    Av = torch.zeros(n, 3, F_, dtype=dt).index_add(0, i, w[:, 1, None, :] * rhat[:, :, None])
-    outer = rhat[:, :, None] * rhat[:, None, :]
-    Sf = torch.zeros(n, 3, 3, F_, dtype=dt).index_add(0, i, w[:, 2, None, None, :] * outer[..., None])
+
+    def edges(i, j, rhat, rbf, C):
+        Zij = _lin(sd, te + "emb2", torch.cat([Z[i], Z[j]], dim=-1))
+        w = (C[:, None] * Zij)[:, None, :] * torch.stack(
+            [_lin(sd, te + "distance_proj1", rbf), _lin(sd, te + "distance_proj2", rbf), _lin(sd, te + "distance_proj3", rbf)],
+            dim=1)  # [E,3,F]
+        dt = w.dtype
+        dev = w.device
+        I = torch.zeros(n, F_, dtype=dt, device=dev).index_add(0, i, w[:, 0])
+        Av = torch.zeros(n, 3, F_, dtype=dt, device=dev).index_add(0, i, w[:, 1, None, :] * rhat[:, :, None])
+        outer = rhat[:, :, None] * rhat[:, None, :]
+        Sf = torch.zeros(n, 3, 3, F_, dtype=dt, device=dev).index_add(0, i, w[:, 2, None, None, :] * outer[..., None])
+        return I, Av, Sf
+
+    I, Av, Sf = _edge_sum(edges, i.shape[0], edge_chunks, i, j, rhat, rbf, C)
+    return _tensor_embedding_nodes(sd, te, F_, act, I, Av, Sf)
+
+
+def _tensor_embedding_nodes(sd: StateDict, te: str, F_: int, act, I, Av, Sf) -> Tensor:
+    """per-atom half of TensorEmbedding.forward (tensornet.py:587-617)."""
     A = skew(Av)
     S = 0.5 * (Sf + Sf.transpose(1, 2)) - Sf.diagonal(dim1=1, dim2=2).mean(-1)[:, None, None, :] * _eye(Sf)
     X = compose(I, A, S)
@@ -245,7 +276,8 @@ def _tensor_embedding(sd: StateDict, te: str, F_: int, act, z, i, j, rhat, rbf, 
     return compose(I, A, S)
 
 
-def tensornet_representation(sd: StateDict, hp: dict, z, ei, vec, dist, q_atom, prefix="representation_model."):
+def tensornet_representation(sd: StateDict, hp: dict, z, ei, vec, dist, q_atom, prefix="representation_model.",
+                             edge_chunks: int = 0):
     """models/tensornet.py:308-402 (TensorNet.forward), :543-619 (TensorEmbedding.forward),
     :729-814 (Interaction.forward), with the pure-PyTorch message passing :405-445, :622-679."""
     F_ = int(hp["embedding_dimension"])
@@ -263,26 +295,31 @@ def tensornet_representation(sd: StateDict, hp: dict, z, ei, vec, dist, q_atom, 
     rhat = vec / dist.masked_fill(self_mask, 1).unsqueeze(1)  # tensornet.py:363-366
     C = cosine_cutoff(dist, lo, hi)
 
-    X = _tensor_embedding(sd, p + "tensor_embedding.", F_, act, z, i, j, rhat, rbf, C, n)
+    X = _tensor_embedding(sd, p + "tensor_embedding.", F_, act, z, i, j, rhat, rbf, C, n, edge_chunks)
     dt = X.dtype
 
     # ---- interaction layers (tensornet.py:729-814)
     qf = (1 + 0.1 * q_atom.to(dt))[:, None, None, None]
     for l in range(int(hp["num_layers"])):
         lp = p + f"layers.{l}."
-        f = rbf
-        for k in range(3):
-            f = act(_lin(sd, lp + f"linears_scalar.{k}", f))
-        f = (f * C[:, None]).reshape(-1, 3, F_)
         X = X / (tnorm(X) + 1)[:, None, None, :]
         I, A, S = decompose(X)
         I = Fn.linear(I, sd[lp + "linears_tensor.0.weight"])
         A = Fn.linear(A, sd[lp + "linears_tensor.1.weight"])
         S = Fn.linear(S, sd[lp + "linears_tensor.2.weight"])
         Y = compose(I, A, S)
-        Im = torch.zeros_like(I).index_add(0, i, f[:, 0] * I[j])
-        Am = torch.zeros_like(A).index_add(0, i, f[:, 1, None, None, :] * A[j])
-        Sm = torch.zeros_like(S).index_add(0, i, f[:, 2, None, None, :] * S[j])
+
+        def edges(i, j, rbf, C, I=I, A=A, S=S, lp=lp):
+            f = rbf
+            for k in range(3):
+                f = act(_lin(sd, lp + f"linears_scalar.{k}", f))
+            f = (f * C[:, None]).reshape(-1, 3, F_)
+            Im = torch.zeros_like(I).index_add(0, i, f[:, 0] * I[j])
+            Am = torch.zeros_like(A).index_add(0, i, f[:, 1, None, None, :] * A[j])
+            Sm = torch.zeros_like(S).index_add(0, i, f[:, 2, None, None, :] * S[j])
+            return Im, Am, Sm
+
+        Im, Am, Sm = _edge_sum(edges, i.shape[0], edge_chunks, i, j, rbf, C)
         M = compose(Im, Am, Sm)
         if group == "O(3)":
             Cn = qf * (mm3(M, Y) + mm3(Y, M))
@@ -309,7 +346,7 @@ def tensornet_representation(sd: StateDict, hp: dict, z, ei, vec, dist, q_atom, 
 # --------------------------------------------------------------------------------------
 def _mol_sum(x: Tensor, batch: Tensor, m: int) -> Tensor:
     """tensornet2.py:65-100 (ChargePredict.mol_sum): per-molecule sum."""
-    return torch.zeros(m, x.shape[-1], dtype=x.dtype).index_add(0, batch, x)
+    return torch.zeros(m, x.shape[-1], dtype=x.dtype, device=x.device).index_add(0, batch, x)
 
 
 def charge_predict(sd: StateDict, key: str, X: Tensor, batch: Tensor, Q_atom: Tensor, q_dim: int, act, m: int) -> Tensor:
@@ -348,7 +385,7 @@ def tensornet2_representation(sd: StateDict, hp: dict, z, ei, vec, dist, batch, 
         if hp["rbf_type"] == "expnorm" else gauss_rbf(dist, sd[p + "distance_expansion.offset"], sd[p + "distance_expansion.coeff"])
     rhat = vec / dist.masked_fill(i == j, 1).unsqueeze(1)
     C = cosine_cutoff(dist, lo, hi)
-    Q_atom = torch.zeros(n, dtype=dist.dtype) if q_mol is None else q_mol[batch].to(dist.dtype)
+    Q_atom = torch.zeros(n, dtype=dist.dtype, device=dist.device) if q_mol is None else q_mol[batch].to(dist.dtype)
     X = _tensor_embedding(sd, p + "tensor_embedding.", F_, act, z, i, j, rhat, rbf, C, n)
     charges = [charge_predict(sd, p + "charge_predict_0.", X, batch, Q_atom, q_dim, act, m)]
     for l in range(int(hp["num_layers"])):
@@ -393,7 +430,7 @@ def weighted_coulomb_per_atom(hp: dict, charges: Tensor, pos: Tensor, batch: Ten
     weighted mean over channels, split equally between the two atoms of a pair.  coulomb_cutoff None: all pairs of a molecule;
     else pairs within the cutoff (half list, minimum image) with the reaction-field form."""
     q_dim, L = int(hp["q_dim"]), int(hp["num_layers"])
-    w = torch.tensor([float(hp["q_weights"][l]) for l in range(L + 1)], dtype=charges.dtype).repeat_interleave(q_dim)
+    w = torch.tensor([float(hp["q_weights"][l]) for l in range(L + 1)], dtype=charges.dtype, device=charges.device).repeat_interleave(q_dim)
     factor = 0.5 * 27.211386024367243 * 0.5291772105638411
     n = pos.shape[0]
     rc = hp.get("coulomb_cutoff", None)
@@ -423,7 +460,7 @@ def weighted_coulomb_per_atom(hp: dict, charges: Tensor, pos: Tensor, batch: Ten
     fc = 1.0 - exp_cutoff(r, 4.6)
     e_ij = factor * (fc * shape).unsqueeze(-1) * charges[ii] * charges[jj]
     e_ij = (e_ij * w[None, :]).sum(-1) / w.sum()
-    e_i = torch.zeros(n, dtype=charges.dtype).index_add(0, ii, e_ij).index_add(0, jj, e_ij)
+    e_i = torch.zeros(n, dtype=charges.dtype, device=charges.device).index_add(0, ii, e_ij).index_add(0, jj, e_ij)
     return e_i
 
 
@@ -451,9 +488,9 @@ def et_representation(sd: StateDict, hp: dict, z, ei, vec, dist, prefix="represe
         ne = p + "neighbor_embedding."
         W = _lin(sd, ne + "distance_proj", rbf) * C[:, None]
         msg = (W * sd[ne + "embedding.weight"][z][dst])[notself]
-        xn = torch.zeros(n, F_, dtype=x.dtype).index_add(0, src[notself], msg)
+        xn = torch.zeros(n, F_, dtype=x.dtype, device=x.device).index_add(0, src[notself], msg)
         x = _lin(sd, ne + "combine", torch.cat([x, xn], dim=1))
-    v3 = torch.zeros(n, 3, F_, dtype=x.dtype)
+    v3 = torch.zeros(n, 3, F_, dtype=x.dtype, device=x.device)
     di = hp.get("distance_influence", "both")
     vcut = bool(hp.get("vector_cutoff", False))
     for l in range(int(hp["num_layers"])):
@@ -480,8 +517,8 @@ def et_representation(sd: StateDict, hp: dict, z, ei, vec, dist, prefix="represe
         s, m1, m2 = torch.split(v_j, hd, dim=2)
         xs = s * attn.unsqueeze(2)
         vm = vec_j * m1.unsqueeze(1) + m2.unsqueeze(1) * dhat[:, :, None, None]
-        xagg = torch.zeros(n, H, hd, dtype=x.dtype).index_add(0, dst, xs).reshape(-1, F_)
-        vagg = torch.zeros(n, 3, H, hd, dtype=x.dtype).index_add(0, dst, vm).reshape(-1, 3, F_)
+        xagg = torch.zeros(n, H, hd, dtype=x.dtype, device=x.device).index_add(0, dst, xs).reshape(-1, F_)
+        vagg = torch.zeros(n, 3, H, hd, dtype=x.dtype, device=x.device).index_add(0, dst, vm).reshape(-1, 3, F_)
         o1, o2, o3 = torch.split(_lin(sd, lp + "o_proj", xagg), F_, dim=1)
         x = x + vec_dot * o2 + o3
         v3 = v3 + vec3 * o1.unsqueeze(1) + vagg
@@ -507,18 +544,19 @@ def gated_equivariant_block(sd, key, x, v, out_channels, act, scalar_activation)
 # a11-a12  heads, reduction, forces
 # --------------------------------------------------------------------------------------
 def energy_and_forces(sd: StateDict, hp: dict, z: Tensor, pos: Tensor, batch: Optional[Tensor] = None,
-                      box: Optional[Tensor] = None, q: Optional[Tensor] = None, derivative: bool = True):
+                      box: Optional[Tensor] = None, q: Optional[Tensor] = None, derivative: bool = True,
+                      edge_chunks: int = 0, graph=None):
     """models/model.py:530-631 (TorchMD_Net.forward): representation -> output head
     (output_modules.py:79-163) -> *std -> (Atomref prior, priors/atomref.py) -> scatter-sum
     per molecule (output_modules.py:43-73, utils.py:671-701) -> +mean -> F = -dE/dpos."""
     batch = torch.zeros_like(z) if batch is None else batch
     pos = pos.detach().clone().requires_grad_(derivative)
-    ei, vec, dist = neighbor_list_from_pos(pos, batch, box, hp, loop=True)
+    ei, vec, dist = neighbor_list_from_pos(pos, batch, box, hp, loop=True, graph=graph)
     act = _act(hp["activation"])
     model = hp["model"]
     if model == "tensornet":
-        q_atom = torch.zeros(z.shape[0], dtype=pos.dtype) if q is None else q[batch]
-        x = tensornet_representation(sd, hp, z, ei, vec, dist, q_atom)
+        q_atom = torch.zeros(z.shape[0], dtype=pos.dtype, device=pos.device) if q is None else q[batch]
+        x = tensornet_representation(sd, hp, z, ei, vec, dist, q_atom, edge_chunks=edge_chunks)
         e = _lin(sd, "output_model.output_network.layers.2", act(_lin(sd, "output_model.output_network.layers.0", x)))
     elif model == "tensornet2":
         x, charges = tensornet2_representation(sd, hp, z, ei, vec, dist, batch, q)
@@ -537,7 +575,7 @@ def energy_and_forces(sd: StateDict, hp: dict, z: Tensor, pos: Tensor, batch: Op
     if "prior_model.0.atomref.weight" in sd:
         e = e + sd["prior_model.0.atomref.weight"][z]
     m = int(batch.max()) + 1
-    y = torch.zeros(m, 1, dtype=e.dtype).index_add(0, batch, e)
+    y = torch.zeros(m, 1, dtype=e.dtype, device=e.device).index_add(0, batch, e)
     if hp.get("reduce_op", "add") == "mean":
         y = y / torch.bincount(batch, minlength=m).to(y.dtype)[:, None]
     y = y + sd["mean"]

@@ -28,6 +28,13 @@ def seeded_model(hp, seed):
     return create_model(dict(hp))
 
 
+def freeze(m):
+    """inference: weights are constants (what TMDNETCalculator / External do) -> the fused pair pipeline is selected"""
+    for p_ in m.parameters():
+        p_.requires_grad_(False)
+    return m
+
+
 def build(fx):
     if "state_dict" in fx:
         from torchmdnet_b200.models.model import create_model
@@ -67,6 +74,7 @@ def test_golden_energy_forces(name, path, monkeypatch):
     m = build(fx)
     m.representation_model.fused_edge_path = False if path == "composed" else None
     if path != "composed":
+        freeze(m)
         if fx["hparams"]["model"] == "tensornet" or fx["hparams"]["embedding_dimension"] <= 128:
             assert m.representation_model._fused_path_ok()
         else:
@@ -106,7 +114,7 @@ def test_expected_pkl():
     """reference tests/test_model.py:277-329, atol/rtol 1e-5, weights rebuilt from seed 1234."""
     for name in ("expected_tensornet", "expected_equivariant_transformer"):
         fx = torch.load(os.path.join(GOLDEN, name + ".pt"), weights_only=False)
-        y, f = run(build(fx), fx)
+        y, f = run(freeze(build(fx)), fx)
         torch.testing.assert_close(y.cpu(), fx["pkl_pred"], atol=1e-5, rtol=1e-5)
         torch.testing.assert_close(f.cpu(), fx["pkl_deriv"], atol=1e-5, rtol=1e-5)
 
@@ -117,7 +125,7 @@ def test_static_shapes_equal_dynamic():
     outs = []
     for static in (False, True):
         hp = dict(fx["hparams"]); hp["static_shapes"] = static
-        m = seeded_model(hp, fx["weight_seed"]).eval().to(dev)
+        m = freeze(seeded_model(hp, fx["weight_seed"]).eval().to(dev))
         outs.append(run(m, fx, num_systems=1))
     assert rel(outs[1][0], outs[0][0].double().cpu()) < 1e-6 and relF(outs[1][1], outs[0][1].double().cpu()) < 1e-5
 
@@ -129,7 +137,7 @@ def test_against_oracle_fresh_system():
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
     z, pos, batch, box = systems.water_box(n_side=4, L=12.4, seed=3)
     y64, f64 = orc.energy_and_forces(orc.cast_state_dict(sd, torch.float64), hp, z, pos.double(), batch, box.double())
-    m = m.to(dev)
+    m = freeze(m.to(dev))
     y, f = m(z.to(dev), pos.to(dev), batch.to(dev), box=box.to(dev))
     assert rel(y, y64) < TOL and relF(f, f64) < TOL
 
@@ -137,7 +145,7 @@ def test_against_oracle_fresh_system():
 def test_multi_molecule_batch_and_permutation():
     """independent molecules: per-molecule energies are unchanged when evaluated alone (no cross-batch edges)."""
     hp = systems.tensornet_hparams(num_layers=1, F=64, R=16, max_nb=64)
-    m = seeded_model(hp, 3).eval().to(dev)
+    m = freeze(seeded_model(hp, 3).eval().to(dev))
     z, pos, batch, _ = systems.molecule_batch(n_mol=5, seed=1)
     y, f = m(z.to(dev), pos.to(dev), batch.to(dev))
     for k in range(5):
@@ -175,7 +183,7 @@ def test_rotation_invariance_and_force_equivariance(kind):
     """reference tests/test_equivariance.py:10-53: E(R x) = E(x), F(R x) = R F(x) (random rotation, incl. an improper one for O(3))."""
     hp = systems.tensornet_hparams(num_layers=2, F=64, R=32, max_nb=64) if kind == "tensornet" else \
         systems.et_hparams(num_layers=2, F=64, R=32, H=4, cutoff=5.0, max_nb=64)
-    m = seeded_model(hp, 11).eval().to(dev)
+    m = freeze(seeded_model(hp, 11).eval().to(dev))
     z, pos, batch, _ = systems.molecule_batch(n_mol=3, seed=9)
     g = torch.Generator().manual_seed(0)
     Q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g, dtype=torch.float64))
@@ -194,7 +202,7 @@ def test_external_adapter(boxed):
     import copy
     from torchmdnet_b200.calculators import External
     hp = systems.tensornet_hparams(num_layers=2, F=128, R=32, max_nb=128, static_shapes=True)
-    m = seeded_model(hp, 5).eval().to(dev)
+    m = freeze(seeded_model(hp, 5).eval().to(dev))
     z, pos, _, _ = systems.molecule_batch(n_mol=1, seed=2)
     n = z.numel()
     emb = torch.stack([z, z])                                   # two replicas of the same molecule
@@ -218,3 +226,79 @@ def test_external_adapter(boxed):
     torch.testing.assert_close(ek, e0 * 23.0609)
     with pytest.raises(ValueError):
         External(m, emb, device="cpu")
+
+
+class _Cell:
+    def __init__(self, a):
+        self.array = np.asarray(a, dtype=float)
+
+
+class _Atoms:
+    """the slice of ase.Atoms that TMDNETCalculator.calculate reads (calculators.py:253-283 of the reference)"""
+
+    def __init__(self, numbers, positions, charge=0, cell=None):
+        self.numbers, self.positions = np.asarray(numbers), np.asarray(positions, dtype=float)
+        self.info = {"charge": charge}
+        self.pbc = np.array([cell is not None] * 3)
+        self.cell = _Cell(np.zeros((3, 3)) if cell is None else cell)
+
+    def copy(self):
+        a = _Atoms(self.numbers.copy(), self.positions.copy(), self.info["charge"], self.cell.array.copy() if self.pbc.any() else None)
+        return a
+
+
+@pytest.mark.parametrize("with_ase_stub", [False, True])
+@pytest.mark.parametrize("compile_", [False, True])
+def test_ase_calculator_caffeine_known_answer(with_ase_stub, compile_, monkeypatch):
+    """reference tests/test_calculator.py:85-162 (test_ase_calculator): caffeine + example_tensornet.ckpt through
+    TMDNETCalculator.calculate -> E = -113.6652, forces atol 1e-4; with and without a (stub) `ase.calculators.calculator`,
+    eager and compile=True (whole-frame CUDA graph), and a charge change detected through atoms.info."""
+    import importlib
+    import sys
+    import types
+    if with_ase_stub:
+        ase = types.ModuleType("ase"); calcs = types.ModuleType("ase.calculators"); calc = types.ModuleType("ase.calculators.calculator")
+
+        class Calculator:   # 20-line stand-in for ase.calculators.calculator.Calculator
+            implemented_properties = []
+
+            def __init__(self, **kw):
+                self.atoms, self.results = None, {}
+
+            def calculate(self, atoms=None, properties=None, system_changes=None):
+                if atoms is not None:
+                    self.atoms = atoms.copy()
+
+            def check_state(self, atoms, tol=1e-15):
+                return []
+
+            def get_forces(self, atoms):
+                self.calculate(atoms, ["forces"], calc.all_changes)
+                return self.results["forces"]
+
+        calc.Calculator, calc.all_changes = Calculator, ["positions", "numbers", "cell", "pbc"]
+        ase.calculators, calcs.calculator = calcs, calc
+        for k, v in (("ase", ase), ("ase.calculators", calcs), ("ase.calculators.calculator", calc)):
+            monkeypatch.setitem(sys.modules, k, v)
+    import torchmdnet_b200.calculators as C
+    C = importlib.reload(C)
+    try:
+        assert (C.ase_calc is not None) == with_ase_stub
+        fx = torch.load(os.path.join(GOLDEN, "caffeine_tensornet.pt"), weights_only=False)
+        calc_ = C.TMDNETCalculator(os.path.join(GOLDEN, "example_tensornet_slim.ckpt"), device="cuda:0", compile=compile_)
+        atoms = _Atoms(fx["z"].numpy(), fx["pos"].numpy(), charge=0)
+        calc_.calculate(atoms, ["energy", "forces"], C.all_changes)
+        assert abs(calc_.results["energy"] - fx["kat_E"]) < 1e-4
+        F = torch.from_numpy(calc_.results["forces"])
+        assert (F[0] - fx["kat_F0"]).abs().max() < 1e-4 and (F[23] - fx["kat_F23"]).abs().max() < 1e-4
+        assert (F - fx["ref_F32"]).abs().max() < 1e-4
+        # a second call with the same numbers reuses the capture; the charge is read from atoms.info every call
+        fq = torch.load(os.path.join(GOLDEN, "caffeine_tensornet_q2.pt"), weights_only=False)
+        atoms.info["charge"] = 2
+        F2 = torch.from_numpy(calc_.get_forces(atoms))
+        assert relF(F2, fq["ref_F64"]) < TOL and rel(torch.tensor([[calc_.results["energy"]]]), fq["ref_E64"]) < TOL
+        with pytest.raises(ValueError):
+            C.TMDNETCalculator(os.path.join(GOLDEN, "example_tensornet_slim.ckpt"), device="cpu")
+    finally:
+        monkeypatch.undo()
+        importlib.reload(C)

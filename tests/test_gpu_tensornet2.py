@@ -1,9 +1,7 @@
-"""-m gpu, OPT-IN (TMD_EXPERIMENTAL_TESTS=1): TensorNet2 + ScalarPlusWeightedCoulomb assembled from the TensorNet kernels
-(models/tensornet2.py) against the reference outputs in tests/golden/next/ (oracle/make_golden_tn2.py).
-
-Not part of the default GPU run yet: the model was written after the round's GPU budget was spent, so this file has never been
-executed on a B200.  The oracle side of the row is pinned (tests/test_oracle.py::test_oracle_tensornet2_pinned) and the host side
-is covered on the CPU (tests/test_tensornet2_host.py); running this file is the first step of the next round."""
+"""-m gpu: TensorNet2 + ScalarPlusWeightedCoulomb assembled from the TensorNet kernels (models/tensornet2.py)
+against the reference outputs in tests/golden/next/ (oracle/make_golden_tn2.py: the unmodified reference in fp64 and fp32).
+The oracle side of the row is pinned (tests/test_oracle.py::test_oracle_tensornet2_pinned) and the host side is covered on the
+CPU (tests/test_tensornet2_host.py)."""
 import os
 
 import pytest
@@ -11,9 +9,7 @@ import torch
 
 from conftest import GOLDEN
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("TMD_EXPERIMENTAL_TESTS") != "1",
-                                 reason="TensorNet2 GPU forward not validated on hardware yet (set TMD_EXPERIMENTAL_TESTS=1)")]
+pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 

@@ -13,6 +13,7 @@ from typing import NamedTuple, Optional, Sequence
 
 import torch
 from torch import Tensor
+from torch.autograd.function import once_differentiable
 
 from .. import _lib
 from .neighbors import NeighborGraph
@@ -65,6 +66,7 @@ class _PairDist(torch.autograd.Function):
         return dist.index_select(0, pair_edge[:P].long())
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g_pair):
         (pid,) = ctx.saved_tensors
         return 0.5 * g_pair.index_select(0, pid[:ctx.E].long().clamp_(max=g_pair.shape[0] - 1)), None, None, None
@@ -342,6 +344,39 @@ def _triple(N, F, dev):
     return (torch.empty(N, 1, F, device=dev), torch.empty(N, 3, F, device=dev), torch.empty(N, 5, F, device=dev))
 
 
+class MessagePassingPlan:
+    """The interaction message passing of one frame in the form the model calls it (pair-indexed radial weights f[P_u,3F] read
+    through `pid`): `forward(Y, f) -> M`, `backward(Y, dM, f, fp) -> (dY, g_dist)`.  bench.py times these two entry points for
+    the `roofline` / `roofline_secondary` keys, so the benchmark and the model share one launch path."""
+
+    fwd_kernel_name = "mp_fwd_kernel"
+    bwd_kernel_name = "mp_edge_bwd_kernel"
+    fwd_traffic_bytes = 0.627e9
+    bwd_traffic_bytes = 1.53e9
+    traffic_source = "ncu --set full, dram read + write per launch on the C4 graph (profiles/r01_mp_ncu.md)"
+
+    def __init__(self, g: NeighborGraph, pidx: PairIndex):
+        self.g, self.pidx = g, pidx
+        self.N = g.indptr.shape[0] - 1
+
+    def forward(self, Y, f):
+        YI, YA, YS = Y
+        N, F = self.N, YI.shape[-1]
+        M = _triple(N, F, YI.device)
+        _lib.call("tmd_mp_fwd", p(YI), p(YA), p(YS), p(f), p(self.pidx.pid), p(self.g.nbr_j), p(self.g.indptr), N, F, p(M[0]), p(M[1]),
+                  p(M[2]), device=YI.device)
+        return M
+
+    def backward(self, Y, dM, f, fp):
+        YI, YA, YS = Y
+        N, F = self.N, YI.shape[-1]
+        dY = _triple(N, F, YI.device)
+        g_dist = torch.zeros(self.g.dist.shape[0], device=YI.device, dtype=torch.float32) if fp is not None else None
+        _lib.call("tmd_mp_edge_bwd", p(YI), p(YA), p(YS), p(dM[0]), p(dM[1]), p(dM[2]), p(f), p(fp), p(self.pidx.pid), p(self.g.nbr_j),
+                  p(self.g.indptr), N, F, p(dY[0]), p(dY[1]), p(dY[2]), p(g_dist), device=YI.device)
+        return dY, g_dist
+
+
 class _InteractionMP(torch.autograd.Function):
     """M = sum_e f(r_e) * Y_j with f = cutoff * MLP(rbf(r)) evaluated per pair (rows a6 + a7).  `dist` is the per-slot
     distance (the differentiable input); `pair_r` its per-pair gather (no autograd)."""
@@ -351,24 +386,18 @@ class _InteractionMP(torch.autograd.Function):
         YI, YA, YS = YI.contiguous(), YA.contiguous(), YS.contiguous()
         need = dist.requires_grad
         f, fp = run_chain(chain, pair_r.detach(), pidx.num_unique, rbf_mod, lo, hi, need, rbf_op)
-        N, F = YI.shape[0], YI.shape[-1]
-        M = _triple(N, F, YI.device)
-        _lib.call("tmd_mp_fwd", p(YI), p(YA), p(YS), p(f), p(pidx.pid), p(g.nbr_j), p(g.indptr), N, F, p(M[0]), p(M[1]), p(M[2]),
-                  device=YI.device)
-        ctx.save_for_backward(YI, YA, YS, f, fp if fp is not None else f, pidx.pid, g.nbr_j, g.indptr)
-        ctx.has_fp = fp is not None
-        ctx.E = dist.shape[0]
+        plan = MessagePassingPlan(g, pidx)
+        M = plan.forward((YI, YA, YS), f)
+        ctx.save_for_backward(YI, YA, YS, f, fp if fp is not None else f)
+        ctx.has_fp, ctx.plan = fp is not None, plan
         return M
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dI, dA, dS):
-        YI, YA, YS, f, fp, pid, nbr_j, indptr = ctx.saved_tensors
-        N, F = YI.shape[0], YI.shape[-1]
-        dY = _triple(N, F, YI.device)
-        g_dist = torch.zeros(ctx.E, device=YI.device, dtype=torch.float32) if ctx.has_fp else None
-        _lib.call("tmd_mp_edge_bwd", p(YI), p(YA), p(YS), p(dI.contiguous()), p(dA.contiguous()), p(dS.contiguous()), p(f),
-                  p(fp) if ctx.has_fp else None, p(pid), p(nbr_j), p(indptr), N, F, p(dY[0]), p(dY[1]), p(dY[2]), p(g_dist),
-                  device=YI.device)
+        YI, YA, YS, f, fp = ctx.saved_tensors
+        dM = (dI.contiguous(), dA.contiguous(), dS.contiguous())   # bound to a local: the copies outlive the launch
+        dY, g_dist = ctx.plan.backward((YI, YA, YS), dM, f, fp if ctx.has_fp else None)
         return dY[0], dY[1], dY[2], g_dist, None, None, None, None, None, None, None, None
 
 
@@ -393,14 +422,16 @@ class _EmbeddingMP(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dI, dA, dS):
         dist, rhat, dp, dpp, pid, nbr_j, indptr, U, V = ctx.saved_tensors
         if not ctx.has_tangent:
             return (None,) * 12
         N, F = U.shape[0], U.shape[-1]
         g_dist, g_rhat = torch.zeros_like(dist), torch.zeros_like(rhat)
+        dI, dA, dS = dI.contiguous(), dA.contiguous(), dS.contiguous()
         _lib.call("tmd_embed_bwd", p(rhat), p(dist), p(dp), p(dpp), p(pid), p(nbr_j), p(indptr), p(U), p(V), ctx.lo, ctx.hi,
-                  N, F, p(dI.contiguous()), p(dA.contiguous()), p(dS.contiguous()), p(g_dist), p(g_rhat), device=U.device)
+                  N, F, p(dI), p(dA), p(dS), p(g_dist), p(g_rhat), device=U.device)
         return g_dist, g_rhat, None, None, None, None, None, None, None, None, None, None
 
 
@@ -427,6 +458,7 @@ class _ETMessage(torch.autograd.Function):
         return xagg, vagg
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gx, gv):
         q, kk, v, vec, dkv, dkvp, pid, nbr_j, indptr, dist, rhat = ctx.saved_tensors
         lo, hi, vcut, hd, has_t = ctx.cfg
@@ -436,7 +468,8 @@ class _ETMessage(torch.autograd.Function):
         gq, gk = torch.empty_like(q), torch.empty_like(kk)
         gvo, gvec = torch.empty_like(v), torch.empty_like(vec)
         g_dist, g_rhat = torch.zeros_like(dist), torch.zeros_like(rhat)
-        _lib.call("tmd_et_msg_bwd", p(q), p(kk), p(v), p(vec), p(dkv), p(dkvp), p(gx.contiguous()), p(gv.contiguous()), p(pid),
+        gx, gv = gx.contiguous(), gv.contiguous()
+        _lib.call("tmd_et_msg_bwd", p(q), p(kk), p(v), p(vec), p(dkv), p(dkvp), p(gx), p(gv), p(pid),
                   p(nbr_j), p(indptr), p(dist), p(rhat), lo, hi, vcut, N, F, hd, p(gq), p(gk), p(gvo), p(gvec), p(g_dist),
                   p(g_rhat), device=q.device)
         return (gq, gk, gvo, gvec, g_dist, g_rhat) + (None,) * 10
@@ -497,6 +530,7 @@ class _IrrepsLinear(torch.autograd.Function):
         return _irreps_gemm(I, A, S, fwd[0], fwd[1])
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dI, dA, dS):
         gI, gA, gS = _irreps_gemm(dI, dA, dS, ctx.bwd[0], ctx.bwd[1])
         return gI, gA, gS, None

@@ -67,8 +67,9 @@ def _neighbor_bwd(ctx, grads):
     g_vec, g_dist = grads[1], grads[2]
     gpos = torch.zeros(ctx.n, 3, device=vec.device, dtype=vec.dtype)
     if ctx.n and vec.shape[0]:
-        _lib.call("tmd_neighbor_grad_coo_" + _suffix(vec.dtype), p(neighbors), vec.shape[0], p(vec), p(dist),
-                  p(None if g_vec is None else g_vec.contiguous()), p(None if g_dist is None else g_dist.contiguous()), p(gpos),
+        gv = None if g_vec is None else g_vec.contiguous()     # bound to locals: the copies must outlive the launch
+        gd = None if g_dist is None else g_dist.contiguous()
+        _lib.call("tmd_neighbor_grad_coo_" + _suffix(vec.dtype), p(neighbors), vec.shape[0], p(vec), p(dist), p(gv), p(gd), p(gpos),
                   device=vec.device)
     return (gpos,) + (None,) * (ctx.nargs - 1)
 

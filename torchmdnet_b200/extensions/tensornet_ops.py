@@ -16,6 +16,7 @@ from typing import List, Tuple
 
 import torch
 from torch import Tensor
+from torch.autograd.function import once_differentiable
 
 from .. import _lib
 
@@ -74,6 +75,7 @@ class _Compose(torch.autograd.Function):
         return X
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dX):
         dX = _c(dX)
         N, F = dX.shape[0], dX.shape[-1]
@@ -92,6 +94,7 @@ class _Decompose(torch.autograd.Function):
         return I, A, S
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dI, dA, dS):
         dI, dA, dS = _c(dI), _c(dA), _c(dS)
         N, F = dI.shape[0], dI.shape[-1]
@@ -111,6 +114,7 @@ def _make_matmul(kind):
             return Z
 
         @staticmethod
+        @once_differentiable
         def backward(ctx, dZ):
             X, Y = ctx.saved_tensors
             dZ = _c(dZ)
@@ -135,6 +139,7 @@ class _Norm3(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dout):
         (X,) = ctx.saved_tensors
         dout = _c(dout)
@@ -156,6 +161,7 @@ class _RadialMP(torch.autograd.Function):
         return I, A, S
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dI, dA, dS):
         rhat, w, row_data, row_indptr = ctx.saved_tensors
         dI, dA, dS = _c(dI), _c(dA), _c(dS)
@@ -179,6 +185,7 @@ class _MP(torch.autograd.Function):
         return oI, oA, oS
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dI, dA, dS):
         I, A, S, w, col_data, col_indices, col_indptr = ctx.saved_tensors
         dI, dA, dS = _c(dI), _c(dA), _c(dS)
@@ -244,6 +251,7 @@ class _Norm2C(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dout):
         I, A, S = ctx.saved_tensors
         N, F = I.shape[0], I.shape[-1]
@@ -263,6 +271,7 @@ class _Norm3C(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dout):
         I, A, S = ctx.saved_tensors
         N, F = I.shape[0], I.shape[-1]
@@ -283,6 +292,7 @@ class _Gate(torch.autograd.Function):
         return o
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dI, dA, dS):
         I, A, S, g = ctx.saved_tensors
         N, F = I.shape[0], I.shape[-1]
@@ -304,6 +314,7 @@ class _P1(torch.autograd.Function):
         return o
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dI, dA, dS):
         I, A, S = ctx.saved_tensors
         N, F = I.shape[0], I.shape[-1]
@@ -328,6 +339,7 @@ class _P2(torch.autograd.Function):
         return o
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dI, dA, dS):
         YI, YA, YS, MI, MA, MS, qf = ctx.saved_tensors
         N, F = YI.shape[0], YI.shape[-1]
@@ -351,6 +363,7 @@ class _P3(torch.autograd.Function):
         return o
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dI, dA, dS):
         DI, DA, DS, qf = ctx.saved_tensors
         N, F = DI.shape[0], DI.shape[-1]

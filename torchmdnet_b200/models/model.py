@@ -3,8 +3,8 @@
 
 `torchmd-train` (LNNP, module.py:86-89) and `TMDNETCalculator` (calculators.py:213-225) only touch these
 entry points, the `hyper_parameters` dict and the state-dict keys -- all preserved -- so they run on the
-B200 kernels unchanged.  Architectures in scope: "tensornet" and "equivariant-transformer"
-(SURVEY.md section 8); the deprecated graph-network / transformer models and TensorNet2 raise.
+B200 kernels unchanged.  Architectures in scope: "tensornet", "equivariant-transformer"  and
+"tensornet2" (+ ScalarPlusWeightedCoulomb); the deprecated graph-network / transformer models raise.
 """
 import os
 import re
@@ -128,6 +128,8 @@ def load_model(filepath, args=None, device="cpu", return_std=False, **kwargs):
                      (r"output_model.output_network.([02]).(weight|bias)", r"output_model.output_network.layers.\1.\2")):
         sd = {re.sub(pat, rep, k): v for k, v in sd.items()}
     sd.setdefault("representation_model.distance.box", torch.zeros(3, 3))
+    if getattr(model.output_model, "distance", None) is not None:   # Coulomb head with a cutoff (reference model.py:286-291)
+        sd.setdefault("output_model.distance.box", torch.zeros(3, 3))
 
     old_layout = "check_errors" in ckpt.get("hyper_parameters", {})
     if kwargs.get("compatibility_load", old_layout) and args["model"] in ("tensornet", "tensornet2"):

@@ -14,6 +14,7 @@ reference `torchmdnet/models/tensornet.py:149-402`; the forward is re-designed f
 
 Dense linears (nn.Linear on [E,.] / [N,.]) are plain library GEMMs (cuBLAS through torch).
 """
+import warnings
 from typing import Optional, Tuple
 
 import torch
@@ -211,7 +212,14 @@ class TensorNet(nn.Module):
         emb = self.tensor_embedding
         emb_frozen = not any(t.requires_grad for t in (emb.emb.weight, emb.emb2.weight, emb.emb2.bias))
         frozen = rbf_frozen and emb_frozen and all(c.frozen() for c in chains)
-        return frozen or not (self.training and torch.is_grad_enabled())
+        if frozen or not torch.is_grad_enabled():
+            return True
+        if not self.training and not getattr(self, "_warned_unfrozen", False):
+            self._warned_unfrozen = True
+            warnings.warn("torchmdnet_b200: parameters require grad, so the autograd-composed kernels are used (weight gradients "
+                          "stay correct); freeze them (p.requires_grad_(False), as TMDNETCalculator / External do) to get the fused "
+                          "inference path")
+        return False
 
     def forward(self, z: Tensor, pos: Tensor, batch: Tensor, box: Optional[Tensor] = None, q: Optional[Tensor] = None,
                 s: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor], Tensor, Tensor, Tensor]:

@@ -6,6 +6,7 @@ the neighbour list; the per-edge attention message a
 run on the sorted CSR graph (deterministic `index_add` over rows already grouped by target atom), with no
 boolean-mask compaction or `.all()` host syncs.
 """
+import warnings
 from typing import Optional, Tuple
 
 import torch
@@ -150,7 +151,14 @@ class TorchMD_ET(nn.Module):
             return False
         rbf_frozen = not any(t.requires_grad for t in (self.distance_expansion.means, self.distance_expansion.betas))
         frozen = rbf_frozen and all(c.frozen() for c in chains)
-        return frozen or not (self.training and torch.is_grad_enabled())
+        if frozen or not torch.is_grad_enabled():
+            return True
+        if not self.training and not getattr(self, "_warned_unfrozen", False):
+            self._warned_unfrozen = True
+            warnings.warn("torchmdnet_b200: parameters require grad, so the autograd-composed kernels are used (weight gradients "
+                          "stay correct); freeze them (p.requires_grad_(False), as TMDNETCalculator / External do) to get the fused "
+                          "inference path")
+        return False
 
     def reset_parameters(self):
         self.embedding.reset_parameters()
