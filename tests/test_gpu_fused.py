@@ -224,3 +224,98 @@ def test_irreps_linear_tensor_cores(F):
     g2 = torch.autograd.grad(sum((r * w_.double()).sum() for r, w_ in zip(ref, ws)), X)
     for a, b in zip(g1, g2):
         assert (a.double() - b.double()).abs().max() < 3e-6 * (1 + b.abs().max())
+
+
+@pytest.mark.parametrize("case", ["water_cells", "water_cells_static", "random_box_no_cells", "molecules", "F64", "tail_group"])
+def test_cooperative_message_passing_bit_exact(case, monkeypatch):
+    """csrc/mp_coop.cu (group-staged neighbour rows, async radial-row rings) == the warp-per-atom kernels, bit for bit: every row
+    accumulates its edges in the same ascending-j order with the same FMA sequence.  Cases: cell-ordered groups (periodic water
+    box, exact-size and capacity-padded buffers), identity order (small random box: segment scan, no cell grid), a non-periodic
+    molecule batch, F = 64 (half the lanes idle), and an atom count that leaves a partial last group."""
+    from torchmdnet_b200.extensions import fused
+    from torchmdnet_b200.extensions.neighbors import neighbor_graph
+    torch.manual_seed(0)
+    F = 64 if case == "F64" else 128
+    if case in ("water_cells", "water_cells_static", "F64"):
+        z, pos, batch, box = systems.water_box(n_side=6, L=46.42 * 6 / 15, seed=1)
+        cap = z.numel() * (64 if case != "water_cells_static" else 96)
+    elif case == "tail_group":
+        z, pos, batch, box = systems.random_box(1003, seed=2)
+        cap = z.numel() * 96
+    elif case == "random_box_no_cells":
+        z, pos, batch, box = systems.random_box(300, seed=3)
+        cap = z.numel() * 96
+    else:
+        z, pos, batch, box = systems.molecule_batch(n_mol=12, seed=4)
+        cap = z.numel() * 48
+    n = z.numel()
+    g = neighbor_graph(pos.to(dev), batch.to(dev), None if box is None else box.to(dev), box is not None, 0.0, 5.0, True, cap)
+    assert int(g.num_pairs) <= cap
+    uses_cells = bool(g.order_flag.item()) if g.order_flag is not None else False
+    assert uses_cells == (case in ("water_cells", "water_cells_static", "F64", "tail_group"))
+    pidx = fused.build_pair_index(g)
+    P = int(pidx.num_unique)
+    Y = [torch.randn(n, k, F, device=dev) for k in (1, 3, 5)]
+    dM = [torch.randn(n, k, F, device=dev) for k in (1, 3, 5)]
+    f, fp = torch.randn(P, 3, F, device=dev), torch.randn(P, 3, F, device=dev)
+    monkeypatch.setattr(fused, "USE_MP_COOP", False)
+    ref = fused.MessagePassingPlan(g, pidx, F)
+    assert not ref.coop
+    M0 = ref.forward(Y, f)
+    dY0, gd0 = ref.backward(Y, dM, f, fp)
+    dY0n, _ = ref.backward(Y, dM, f, None)
+    monkeypatch.setattr(fused, "USE_MP_COOP", True)
+    plan = fused.MessagePassingPlan(g, pidx, F)
+    assert plan.coop
+    M1 = plan.forward(Y, f)
+    dY1, gd1 = plan.backward(Y, dM, f, fp)
+    dY1n, gdn = plan.backward(Y, dM, f, None)
+    torch.cuda.synchronize()
+    E = int(g.num_pairs)
+    # the plan itself: groups cover every row once; union positions point at the edge's neighbour
+    rows = plan.rows.long()
+    assert torch.equal(torch.sort(rows).values, torch.arange(n, device=dev))
+    gcnt = plan.gcnt.long()
+    assert (gcnt >= 0).all(), "no group may overflow the staged path on these inputs"
+    grp_of_row = torch.empty(n, dtype=torch.long, device=dev); grp_of_row[rows] = torch.arange(n, device=dev) // 16
+    ge = grp_of_row[g.nbr_i[:E].long()]
+    up = plan.upos[:E].to(torch.int32) & 0xFFFF
+    t = (up & 0x7FFF).long()
+    assert (t < gcnt[ge]).all()
+    assert torch.equal(plan.union_j[(plan.goff.long()[ge] + t)].long(), g.nbr_j[:E].long())
+    assert torch.equal((up & 0x8000) != 0, g.nbr_i[:E] == g.nbr_j[:E])
+    print(f"{case}: n={n} E={E} groups={gcnt.numel()} mean union={gcnt.float().mean():.1f} edges/union={E / gcnt.sum().item():.2f}")
+    for a, b in zip(M0 + dY0 + dY0n, M1 + dY1 + dY1n):
+        assert torch.equal(a, b)
+    assert torch.equal(gd0[:E], gd1[:E]) and gdn is None
+
+
+def test_cooperative_message_passing_overflow_fallback():
+    """a group whose rows hold more than 2048 distinct neighbours is flagged (gcnt = -1) and gathered directly -- same bits."""
+    from torchmdnet_b200.extensions import fused
+    from torchmdnet_b200.extensions.neighbors import neighbor_graph
+    torch.manual_seed(1)
+    n, F = 3000, 64
+    g0 = torch.Generator().manual_seed(5)
+    pos = torch.rand(n, 3, generator=g0) * 6.0          # everything within the 12 A cutoff of everything: rows of 3000 neighbours
+    batch = torch.zeros(n, dtype=torch.long)
+    g = neighbor_graph(pos.to(dev), batch.to(dev), None, False, 0.0, 12.0, True, n * n)
+    pidx = fused.build_pair_index(g)
+    P = int(pidx.num_unique)
+    Y = [torch.randn(n, k, F, device=dev) for k in (1, 3, 5)]
+    dM = [torch.randn(n, k, F, device=dev) for k in (1, 3, 5)]
+    f, fp = torch.randn(P, 3, F, device=dev), torch.randn(P, 3, F, device=dev)
+    fused_coop = fused.USE_MP_COOP
+    try:
+        fused.USE_MP_COOP = False
+        ref = fused.MessagePassingPlan(g, pidx, F)
+        M0 = ref.forward(Y, f); dY0, gd0 = ref.backward(Y, dM, f, fp)
+        fused.USE_MP_COOP = True
+        plan = fused.MessagePassingPlan(g, pidx, F)
+        assert (plan.gcnt == -1).all()
+        M1 = plan.forward(Y, f); dY1, gd1 = plan.backward(Y, dM, f, fp)
+    finally:
+        fused.USE_MP_COOP = fused_coop
+    for a, b in zip(M0 + dY0, M1 + dY1):
+        assert torch.equal(a, b)
+    assert torch.equal(gd0[: int(g.num_pairs)], gd1[: int(g.num_pairs)])

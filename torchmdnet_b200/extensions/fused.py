@@ -344,36 +344,83 @@ def _triple(N, F, dev):
     return (torch.empty(N, 1, F, device=dev), torch.empty(N, 3, F, device=dev), torch.empty(N, 5, F, device=dev))
 
 
+# cooperative (group-staged) message passing kernels, csrc/mp_coop.cu; TMD_MP_COOP=0 selects the warp-per-atom kernels
+USE_MP_COOP = os.environ.get("TMD_MP_COOP", "1") != "0"
+
+
 class MessagePassingPlan:
     """The interaction message passing of one frame in the form the model calls it (pair-indexed radial weights f[P_u,3F] read
     through `pid`): `forward(Y, f) -> M`, `backward(Y, dM, f, fp) -> (dY, g_dist)`.  bench.py times these two entry points for
-    the `roofline` / `roofline_secondary` keys, so the benchmark and the model share one launch path."""
+    the `roofline` / `roofline_secondary` keys, so the benchmark and the model share one launch path.
 
-    fwd_kernel_name = "mp_fwd_kernel"
-    bwd_kernel_name = "mp_edge_bwd_kernel"
+    Cooperative path (F <= 128): one `tmd_mp_plan` launch per frame groups the rows 16 by 16 in the neighbour search's cell order
+    (spatially adjacent atoms share most neighbours) and lists each group's distinct neighbours; the forward / backward kernels
+    stage every distinct neighbour row once per group in shared memory.  Results are bit-identical to the warp-per-atom kernels."""
+
+    def __init__(self, g: NeighborGraph, pidx: PairIndex, F: Optional[int] = None):
+        self.g, self.pidx = g, pidx
+        self.N = g.indptr.shape[0] - 1
+        self.coop = bool(USE_MP_COOP and self.N > 0 and (F is None or (F % 4 == 0 and F <= 128)))
+        if self.coop:
+            dev, cap, n = g.dist.device, g.dist.shape[0], self.N
+            ng = -(-n // 16)
+            i32 = dict(device=dev, dtype=torch.int32)
+            self.rows = torch.empty(n, **i32)
+            self.union_j = torch.empty(cap, **i32)
+            self.ucount = torch.empty(cap, device=dev, dtype=torch.uint8)
+            self.upos = torch.empty(cap, device=dev, dtype=torch.int16)
+            self.goff, self.gcnt = torch.empty(ng, **i32), torch.empty(ng, **i32)
+            self.cursor = torch.empty(1, **i32)
+            has_order = g.order is not None and g.order.numel() == n
+            _lib.call("tmd_mp_plan", p(g.indptr), p(g.nbr_j), p(g.num_pairs), cap, n, p(g.order) if has_order else None,
+                      p(g.order_flag) if has_order else None, p(self.rows), p(self.cursor), p(self.union_j), p(self.ucount),
+                      p(self.upos), p(self.goff), p(self.gcnt), device=dev)
+
+    @property
+    def fwd_kernel_name(self):
+        return "mp_coop_fwd_kernel" if self.coop else "mp_fwd_kernel"
+
+    @property
+    def bwd_kernel_name(self):
+        return "mp_coop_bwd_kernel" if self.coop else "mp_edge_bwd_kernel"
+
+    # dram bytes per launch on the C4 graph from the committed ncu captures (bench.py `roofline.traffic`)
     fwd_traffic_bytes = 0.627e9
     bwd_traffic_bytes = 1.53e9
     traffic_source = "ncu --set full, dram read + write per launch on the C4 graph (profiles/r01_mp_ncu.md)"
 
-    def __init__(self, g: NeighborGraph, pidx: PairIndex):
-        self.g, self.pidx = g, pidx
-        self.N = g.indptr.shape[0] - 1
+    def _ok(self, F):
+        return self.coop and F % 4 == 0 and F <= 128
 
     def forward(self, Y, f):
         YI, YA, YS = Y
         N, F = self.N, YI.shape[-1]
         M = _triple(N, F, YI.device)
-        _lib.call("tmd_mp_fwd", p(YI), p(YA), p(YS), p(f), p(self.pidx.pid), p(self.g.nbr_j), p(self.g.indptr), N, F, p(M[0]), p(M[1]),
-                  p(M[2]), device=YI.device)
+        g, x = self.g, self.pidx
+        if self._ok(F):
+            _lib.call("tmd_mp_coop_fwd", p(YI), p(YA), p(YS), p(f), p(x.pid), p(g.nbr_j), p(g.indptr), p(g.num_pairs), g.dist.shape[0],
+                      N, F, p(self.rows), p(self.union_j), p(self.ucount), p(self.upos), p(self.goff), p(self.gcnt), p(M[0]), p(M[1]),
+                      p(M[2]), device=YI.device)
+        else:
+            _lib.call("tmd_mp_fwd", p(YI), p(YA), p(YS), p(f), p(x.pid), p(g.nbr_j), p(g.indptr), N, F, p(M[0]), p(M[1]), p(M[2]),
+                      device=YI.device)
         return M
 
     def backward(self, Y, dM, f, fp):
         YI, YA, YS = Y
         N, F = self.N, YI.shape[-1]
         dY = _triple(N, F, YI.device)
-        g_dist = torch.zeros(self.g.dist.shape[0], device=YI.device, dtype=torch.float32) if fp is not None else None
-        _lib.call("tmd_mp_edge_bwd", p(YI), p(YA), p(YS), p(dM[0]), p(dM[1]), p(dM[2]), p(f), p(fp), p(self.pidx.pid), p(self.g.nbr_j),
-                  p(self.g.indptr), N, F, p(dY[0]), p(dY[1]), p(dY[2]), p(g_dist), device=YI.device)
+        g, x = self.g, self.pidx
+        if self._ok(F):
+            # every valid slot is written by the kernel; padded slots (static shapes) are never read by the position gradient
+            g_dist = torch.empty(g.dist.shape[0], device=YI.device, dtype=torch.float32) if fp is not None else None
+            _lib.call("tmd_mp_coop_bwd", p(YI), p(YA), p(YS), p(dM[0]), p(dM[1]), p(dM[2]), p(f), p(fp), p(x.pid), p(g.nbr_j),
+                      p(g.indptr), p(g.num_pairs), g.dist.shape[0], N, F, p(self.rows), p(self.union_j), p(self.ucount), p(self.upos),
+                      p(self.goff), p(self.gcnt), p(dY[0]), p(dY[1]), p(dY[2]), p(g_dist), device=YI.device)
+        else:
+            g_dist = torch.zeros(g.dist.shape[0], device=YI.device, dtype=torch.float32) if fp is not None else None
+            _lib.call("tmd_mp_edge_bwd", p(YI), p(YA), p(YS), p(dM[0]), p(dM[1]), p(dM[2]), p(f), p(fp), p(x.pid), p(g.nbr_j),
+                      p(g.indptr), N, F, p(dY[0]), p(dY[1]), p(dY[2]), p(g_dist), device=YI.device)
         return dY, g_dist
 
 
@@ -382,11 +429,12 @@ class _InteractionMP(torch.autograd.Function):
     distance (the differentiable input); `pair_r` its per-pair gather (no autograd)."""
 
     @staticmethod
-    def forward(ctx, YI, YA, YS, dist, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op):
+    def forward(ctx, YI, YA, YS, dist, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op, plan):
         YI, YA, YS = YI.contiguous(), YA.contiguous(), YS.contiguous()
         need = dist.requires_grad
         f, fp = run_chain(chain, pair_r.detach(), pidx.num_unique, rbf_mod, lo, hi, need, rbf_op)
-        plan = MessagePassingPlan(g, pidx)
+        if plan is None:
+            plan = MessagePassingPlan(g, pidx, YI.shape[-1])
         M = plan.forward((YI, YA, YS), f)
         ctx.save_for_backward(YI, YA, YS, f, fp if fp is not None else f)
         ctx.has_fp, ctx.plan = fp is not None, plan
@@ -398,11 +446,11 @@ class _InteractionMP(torch.autograd.Function):
         YI, YA, YS, f, fp = ctx.saved_tensors
         dM = (dI.contiguous(), dA.contiguous(), dS.contiguous())   # bound to a local: the copies outlive the launch
         dY, g_dist = ctx.plan.backward((YI, YA, YS), dM, f, fp if ctx.has_fp else None)
-        return dY[0], dY[1], dY[2], g_dist, None, None, None, None, None, None, None, None
+        return dY[0], dY[1], dY[2], g_dist, None, None, None, None, None, None, None, None, None
 
 
-def interaction_message_passing(Y, dist, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op=None):
-    return _InteractionMP.apply(Y[0], Y[1], Y[2], dist, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op)
+def interaction_message_passing(Y, dist, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op=None, plan=None):
+    return _InteractionMP.apply(Y[0], Y[1], Y[2], dist, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op, plan)
 
 
 class _EmbeddingMP(torch.autograd.Function):

@@ -23,6 +23,8 @@ class NeighborGraph(NamedTuple):
     num_pairs: Tensor   # [1] int32  pairs found (may exceed P: overflow, checked by the caller)
     vec: Tensor         # [P,3]  pos_i - pos_j (minimum image)
     dist: Tensor        # [P]
+    order: Optional[Tensor] = None       # [N] int32  atoms grouped by search cell (spatially adjacent rows are consecutive) ...
+    order_flag: Optional[Tensor] = None  # [1] int32  ... valid iff non-zero (the cell grid was used); else use 0..N-1
 
 
 def _suffix(dtype):
@@ -63,7 +65,7 @@ def _build(pos, batch, box, use_periodic, lo, hi, loop, transpose, max_pairs, wa
     num_pairs = torch.zeros(1, **i32)
     if n == 0:
         indptr.zero_()
-        return indptr, nbr_i, nbr_j, rev, num_pairs, vec, dist
+        return indptr, nbr_i, nbr_j, rev, num_pairs, vec, dist, None, None
     # cell grid for one rectangular periodic box (decided on the device from the box tensor); otherwise segment scan
     max_cells = min(4 * n + 64, 1 << 20) if (use_periodic and stride == 0 and n >= 512) else 0
     ws = torch.empty(5 * n + 8 + 3 * (max_cells + 1), **i32)
@@ -71,7 +73,10 @@ def _build(pos, batch, box, use_periodic, lo, hi, loop, transpose, max_pairs, wa
               int(use_periodic), n, float(lo), float(hi), int(loop), int(transpose), int(max_pairs), max_cells, _lib.ptr(indptr),
               _lib.ptr(nbr_i), _lib.ptr(nbr_j), _lib.ptr(vec), _lib.ptr(dist), _lib.ptr(num_pairs), _lib.ptr(rev),
               _lib.ptr(ws), device=dev)
-    return indptr, nbr_i, nbr_j, rev, num_pairs, vec, dist
+    # workspace layout (csrc/neighbors.cu): seg_lo[n] seg_hi[n] deg[n] flag[1] | hdr[4] cell_of[n] cell_atoms[n] ...;
+    # hdr[3] != 0 <=> the cell grid was used and cell_atoms lists the atoms cell by cell
+    order, order_flag = ws[4 * n + 5: 5 * n + 5], ws[3 * n + 4: 3 * n + 5]
+    return indptr, nbr_i, nbr_j, rev, num_pairs, vec, dist, order, order_flag
 
 
 def _grad_pos_torch(nbr_i, nbr_j, vec, dist, g_vec, g_dist, n):
@@ -93,15 +98,18 @@ def _grad_pos_torch(nbr_i, nbr_j, vec, dist, g_vec, g_dist, n):
 class _NeighborGraphFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pos, batch, box, use_periodic, lo, hi, loop, max_pairs):
-        indptr, nbr_i, nbr_j, rev, num_pairs, vec, dist = _build(pos, batch, box, use_periodic, lo, hi, loop, True,
-                                                                  max_pairs, True)
+        indptr, nbr_i, nbr_j, rev, num_pairs, vec, dist, order, order_flag = _build(pos, batch, box, use_periodic, lo, hi, loop,
+                                                                                     True, max_pairs, True)
         ctx.save_for_backward(indptr, nbr_i, nbr_j, rev, num_pairs, vec, dist)
         ctx.n = pos.shape[0]
-        ctx.mark_non_differentiable(indptr, nbr_i, nbr_j, rev, num_pairs)
-        return indptr, nbr_i, nbr_j, rev, num_pairs, vec, dist
+        if order is None:
+            order = torch.zeros(0, device=pos.device, dtype=torch.int32)
+            order_flag = torch.zeros(1, device=pos.device, dtype=torch.int32)
+        ctx.mark_non_differentiable(indptr, nbr_i, nbr_j, rev, num_pairs, order, order_flag)
+        return indptr, nbr_i, nbr_j, rev, num_pairs, vec, dist, order, order_flag
 
     @staticmethod
-    def backward(ctx, _a, _b, _c, _d, _e, g_vec, g_dist):
+    def backward(ctx, _a, _b, _c, _d, _e, g_vec, g_dist, _o=None, _of=None):
         indptr, nbr_i, nbr_j, rev, num_pairs, vec, dist = ctx.saved_tensors
         n = ctx.n
         if torch.is_grad_enabled() and ((g_vec is not None and g_vec.requires_grad) or (g_dist is not None and g_dist.requires_grad)):
@@ -129,8 +137,8 @@ class _NeighborPairsFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pos, batch, box, use_periodic, lo, hi, loop, transpose, max_pairs):
-        _, nbr_i, nbr_j, _, num_pairs, vec, dist = _build(pos, batch, box, use_periodic, lo, hi, loop, transpose,
-                                                          max_pairs, False)
+        _, nbr_i, nbr_j, _, num_pairs, vec, dist, _, _ = _build(pos, batch, box, use_periodic, lo, hi, loop, transpose,
+                                                                max_pairs, False)
         neighbors = torch.stack([nbr_i, nbr_j]).to(torch.long)
         ctx.save_for_backward(neighbors, vec, dist)
         ctx.n = pos.shape[0]

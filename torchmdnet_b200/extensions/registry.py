@@ -31,7 +31,7 @@ def _op(name):
 # ------------------------------------------------------------------------------------------ neighbour list
 def _neighbor_fwd(positions, batch, box_vectors, use_periodic, cutoff_lower, cutoff_upper, max_num_pairs, loop,
                   include_transpose) -> List[Tensor]:
-    _, nbr_i, nbr_j, _, num_pairs, vec, dist = _build(positions, batch, box_vectors if use_periodic else None, use_periodic,
+    _, nbr_i, nbr_j, _, num_pairs, vec, dist, _, _ = _build(positions, batch, box_vectors if use_periodic else None, use_periodic,
                                                       cutoff_lower, cutoff_upper, loop, include_transpose, max_num_pairs, False)
     return [torch.stack([nbr_i, nbr_j]).to(torch.long), vec, dist, num_pairs]
 

@@ -83,7 +83,7 @@ class TensorEmbedding(nn.Module):
             Z = self.emb(z)
             U = torch.nn.functional.linear(Z, self.emb2.weight[:, :F_])
             V = torch.nn.functional.linear(Z, self.emb2.weight[:, F_:], self.emb2.bias)
-            dist, pair_r, pidx, rbf_mod, rbf_op = fast
+            dist, pair_r, pidx, rbf_mod, rbf_op, _plan = fast
             I, A, S = fused.embedding_message_passing(dist, rhat, U.detach(), V.detach(), pair_r, self.radial_chain(), rbf_mod,
                                                       self.cutoff.cutoff_lower, self.cutoff.cutoff_upper, g, pidx, rbf_op)
         else:
@@ -146,9 +146,9 @@ class Interaction(nn.Module):
         Y = fused.irreps_linear(Xn, self.node_linear(0)) if tc_lin else (lt[0](Xn[0]), lt[1](Xn[1]), lt[2](Xn[2]))
         if fast is not None:
             # fused path: f (and df/dr) once per unordered pair, message passing reads it through the pair index
-            dist, pair_r, pidx, rbf_mod, rbf_op = fast
+            dist, pair_r, pidx, rbf_mod, rbf_op, plan = fast
             M = fused.interaction_message_passing(Y, dist, pair_r, self.radial_chain(), rbf_mod, self.cutoff.cutoff_lower,
-                                                  self.cutoff.cutoff_upper, g, pidx, rbf_op)
+                                                  self.cutoff.cutoff_upper, g, pidx, rbf_op, plan)
         else:
             f = self.edge_weights(rbf, cut)
             # the neighbour list is symmetric and f depends on |r| only, so the CSC of the graph is
@@ -250,7 +250,9 @@ class TensorNet(nn.Module):
             chains = [self.tensor_embedding.radial_chain()] + [l.radial_chain() for l in self.layers]
             rbf_op = fused.shared_rbf_operand(chains, pair_r, pidx.num_unique, self.distance_expansion,
                                               self.cutoff_lower, self.cutoff_upper, dist.requires_grad)
-            fast = (dist, pair_r, pidx, self.distance_expansion, rbf_op)
+            # one plan per frame for the message passing of all layers (row groups + their neighbour unions, csrc/mp_coop.cu)
+            plan = fused.MessagePassingPlan(g, pidx, self.hidden_channels) if self.num_layers > 0 else None
+            fast = (dist, pair_r, pidx, self.distance_expansion, rbf_op, plan)
             X = self.tensor_embedding(z, g, None, None, None, rhat, None, fast=fast)
             for layer in self.layers:
                 X = layer(X, g, None, None, qf, fast=fast)
