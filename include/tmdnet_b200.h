@@ -225,6 +225,23 @@ int tmd_embed_bwd(const float* rhat, const float* dist, const float* dp, const f
                   const int* nbr_j, const int* indptr, const float* U, const float* V, double lo, double hi, int n,
                   int F, const float* dI, const float* dA, const float* dS, float* g_dist, float* g_rhat, void* stream);
 
+/* ---- a10 + a11: TensorNet tail + Scalar head + per-molecule reduction (csrc/head.cu) -------------------------------------
+ * Replaces tensor_norm3 -> LayerNorm(3F) -> Linear(3F->F) -> SiLU (models/tensornet.py:394-402), Scalar.pre_reduce = MLP
+ * Linear(F->H) -> SiLU -> Linear(H->1) (models/output_modules.py:79-117, models/utils.py:531-580), * std, + atomref[z]
+ * (priors/atomref.py:66), OutputModel.reduce = scatter-sum over batch (output_modules.py:43-73) and + mean (model.py:606).
+ * tmd_head_fwd: e[N] per-atom energies; saves (mu, rstd)[N,2] of the LayerNorm and the pre-activations z1[N,F], z2[N,H].
+ * W1T [3F,F], W2T [F,H] are the transposed nn.Linear weights; atomref [n_ref] may be NULL.  F, H multiples of 32, <= 256.
+ * tmd_segment_sum: y[m] = mean + sum of e over the atoms of molecule m (deterministic; `flag` is one int of scratch).
+ * tmd_head_bwd: dI, dA, dS for the upstream gradient gy[M] (forces: ones); W1 [F,3F], W2 [H,F] untransposed. */
+int tmd_head_fwd(const float* I, const float* A, const float* S, int N, int F, int H, const float* ln_w, const float* ln_b,
+                 double eps, const float* W1T, const float* b1, const float* W2T, const float* b2, const float* w3,
+                 const float* b3, const float* std_, const int64_t* z, const float* atomref, int n_ref, float* e,
+                 float* mu_rstd, float* z1, float* z2, void* stream);
+int tmd_segment_sum(const float* e, const int64_t* batch, int N, int M, const float* mean, int* flag, float* y, void* stream);
+int tmd_head_bwd(const float* I, const float* A, const float* S, int N, int F, int H, const float* ln_w, double eps,
+                 const float* W1, const float* W2, const float* w3, const float* std_, const float* gy, const int64_t* batch,
+                 int M, const float* mu_rstd, const float* z1, const float* z2, float* dI, float* dA, float* dS, void* stream);
+
 /* ---- a14: Equivariant-Transformer attention message --------------------------------------------------------------------
  * Replaces EquivariantMultiHeadAttention.propagate/message/aggregate (models/torchmd_et.py:355-426: 4 index_select gathers,
  * ~10 elementwise launches on [E,H,3hd] tensors, 2 scatter-adds).  One warp per target atom of the sorted symmetric CSR;

@@ -295,9 +295,9 @@ def test_cooperative_message_passing_overflow_fallback():
     from torchmdnet_b200.extensions import fused
     from torchmdnet_b200.extensions.neighbors import neighbor_graph
     torch.manual_seed(1)
-    n, F = 3000, 64
+    n, F = 1000, 64
     g0 = torch.Generator().manual_seed(5)
-    pos = torch.rand(n, 3, generator=g0) * 6.0          # everything within the 12 A cutoff of everything: rows of 3000 neighbours
+    pos = torch.rand(n, 3, generator=g0) * 6.0          # everything within the 12 A cutoff of everything: rows of 1000 neighbours
     batch = torch.zeros(n, dtype=torch.long)
     g = neighbor_graph(pos.to(dev), batch.to(dev), None, False, 0.0, 12.0, True, n * n)
     pidx = fused.build_pair_index(g)

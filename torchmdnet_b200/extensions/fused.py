@@ -587,3 +587,82 @@ class _IrrepsLinear(torch.autograd.Function):
 def irreps_linear(X, weights: IrrepsLinearWeights):
     """(W0 I, W1 A, W2 S) as one grouped tensor-core GEMM (row a9); gradients flow to I/A/S only (frozen weights)."""
     return _IrrepsLinear.apply(X[0], X[1], X[2], weights)
+
+
+# ------------------------------------------------------------------------------------------ tail + head + reduce (rows a10, a11)
+class HeadWeights:
+    """Contiguous (and transposed) copies of the weights behind norm3 -> LayerNorm -> Linear -> SiLU -> MLP(F -> F/2 -> 1), cached
+    per weight version (csrc/head.cu reads W k-major in the forward and untransposed in the backward)."""
+
+    def __init__(self, out_norm: torch.nn.LayerNorm, linear: torch.nn.Linear, lin_a: torch.nn.Linear, lin_b: torch.nn.Linear):
+        self.mods = (out_norm, linear, lin_a, lin_b)
+        self._key = None
+
+    def params(self):
+        return [t for m in self.mods for t in (m.weight, m.bias)]
+
+    def frozen(self) -> bool:
+        return not any(t.requires_grad for t in self.params())
+
+    def supported(self) -> bool:
+        out_norm, linear, lin_a, lin_b = self.mods
+        F, H = linear.out_features, lin_a.out_features
+        return (linear.in_features == 3 * F and lin_a.in_features == F and lin_b.in_features == H and lin_b.out_features == 1 and
+                F % 32 == 0 and H % 32 == 0 and F <= 256 and H <= 256 and out_norm.elementwise_affine and
+                tuple(out_norm.normalized_shape) == (3 * F,) and all(t.dtype == torch.float32 for t in self.params()))
+
+    def tensors(self):
+        key = tuple((t.data_ptr(), t._version) for t in self.params())
+        if key != self._key:
+            out_norm, linear, lin_a, lin_b = self.mods
+            d = lambda t: t.detach().contiguous()
+            self._t = dict(ln_w=d(out_norm.weight), ln_b=d(out_norm.bias), W1=d(linear.weight), W1T=d(linear.weight.detach().t()),
+                           b1=d(linear.bias), W2=d(lin_a.weight), W2T=d(lin_a.weight.detach().t()), b2=d(lin_a.bias),
+                           w3=d(lin_b.weight).view(-1), b3=d(lin_b.bias).view(-1), eps=float(out_norm.eps),
+                           F=linear.out_features, H=lin_a.out_features)
+            self._key = key
+        return self._t
+
+
+class _TailHead(torch.autograd.Function):
+    """y[m] = mean + sum_{i in m} ((w3 . SiLU(W2 SiLU(W1 LN(norm3(X_i)) + b1) + b2) + b3) * std + atomref[z_i]); backward w.r.t.
+    the node tensors only (frozen weights)."""
+
+    @staticmethod
+    def forward(ctx, I, A, S, z, batch, M, hw, std, mean, atomref):
+        I, A, S = I.contiguous(), A.contiguous(), S.contiguous()
+        t = hw.tensors()
+        N, F, H, dev = I.shape[0], t["F"], t["H"], I.device
+        e = torch.empty(N, device=dev, dtype=torch.float32)
+        mu_rstd = torch.empty(N, 2, device=dev, dtype=torch.float32)
+        z1 = torch.empty(N, F, device=dev, dtype=torch.float32)
+        z2 = torch.empty(N, H, device=dev, dtype=torch.float32)
+        y = torch.empty(M, 1, device=dev, dtype=torch.float32)
+        flag = torch.empty(1, device=dev, dtype=torch.int32)
+        batch_c, z_c = batch.contiguous(), z.contiguous()
+        std_c, mean_c = std.detach().reshape(1).contiguous(), mean.detach().reshape(1).contiguous()
+        aref = None if atomref is None else atomref.detach().contiguous()
+        _lib.call("tmd_head_fwd", p(I), p(A), p(S), N, F, H, p(t["ln_w"]), p(t["ln_b"]), t["eps"], p(t["W1T"]), p(t["b1"]), p(t["W2T"]),
+                  p(t["b2"]), p(t["w3"]), p(t["b3"]), p(std_c), p(z_c), p(aref), 0 if aref is None else aref.shape[0], p(e), p(mu_rstd),
+                  p(z1), p(z2), device=dev)
+        _lib.call("tmd_segment_sum", p(e), p(batch_c), N, M, p(mean_c), p(flag), p(y), device=dev)
+        ctx.save_for_backward(I, A, S, batch_c, mu_rstd, z1, z2, std_c)
+        ctx.hw, ctx.M = t, M
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        I, A, S, batch, mu_rstd, z1, z2, std_c = ctx.saved_tensors
+        t = ctx.hw
+        N, F, H = I.shape[0], t["F"], t["H"]
+        gy = gy.contiguous()
+        dX = _triple(N, F, I.device)
+        _lib.call("tmd_head_bwd", p(I), p(A), p(S), N, F, H, p(t["ln_w"]), t["eps"], p(t["W1"]), p(t["W2"]), p(t["w3"]), p(std_c), p(gy),
+                  p(batch), ctx.M, p(mu_rstd), p(z1), p(z2), p(dX[0]), p(dX[1]), p(dX[2]), device=I.device)
+        return dX[0], dX[1], dX[2], None, None, None, None, None, None, None
+
+
+def tail_head_energy(X, z, batch, num_systems: int, hw: HeadWeights, std, mean, atomref=None):
+    """per-molecule energies [M,1] from the final node tensors X = (I, A, S): rows a10 + a11 in three launches."""
+    return _TailHead.apply(X[0], X[1], X[2], z, batch, int(num_systems), hw, std, mean, atomref)

@@ -196,6 +196,32 @@ class TorchMD_Net(nn.Module):
             for prior in self.prior_model:
                 prior.reset_parameters()
 
+    fused_head_path = None   # None: automatic; False: always the torch-op tail / head
+
+    def _fused_head(self):
+        """(HeadWeights, atomref weight or None) when the frame ends in the configuration csrc/head.cu implements -- TensorNet on its
+        fused inference path, `Scalar` head with the default 2-layer SiLU MLP, sum reduction, no prior or Atomref only, frozen
+        weights -- else None (torch-op tail and head, which also provide weight gradients)."""
+        from .tensornet import TensorNet
+        rep, out = self.representation_model, self.output_model
+        if self.fused_head_path is False or type(rep) is not TensorNet or type(out) is not output_modules.Scalar:
+            return None
+        if rep.activation != "silu" or out.reduce_op not in ("add", "sum") or self.mean is None or self.std is None:
+            return None
+        layers = out.output_network.layers
+        if len(layers) != 3 or not isinstance(layers[1], nn.SiLU) or self.mean.dtype != torch.float32:
+            return None
+        atomref = None
+        if self.prior_model is not None and len(self.prior_model) > 0:
+            if len(self.prior_model) != 1 or type(self.prior_model[0]) is not priors.Atomref or self.prior_model[0].atomref.weight.requires_grad:
+                return None
+            if self.prior_model[0].enable:
+                atomref = self.prior_model[0].atomref.weight
+        hw = rep.head_weights(out.output_network)
+        if not (hw.supported() and hw.frozen() and rep._fused_path_ok()):
+            return None
+        return hw, atomref
+
     def forward(self, z: Tensor, pos: Tensor, batch: Optional[Tensor] = None, box: Optional[Tensor] = None,
                 q: Optional[Tensor] = None, s: Optional[Tensor] = None, extra_args: Optional[Dict[str, Tensor]] = None,
                 num_systems: Optional[int] = None) -> Tuple[Tensor, Tensor]:
@@ -205,20 +231,30 @@ class TorchMD_Net(nn.Module):
         batch = torch.zeros_like(z) if batch is None else batch
         if self.derivative:
             pos.requires_grad_(True)
-        x, v, z, pos, batch = self.representation_model(z, pos, batch, box=box, q=q, s=s)
-        x = self.output_model.pre_reduce(x, v, z, pos, batch, box=box)
-        if self.std is not None:
-            x = x * self.std
-        if self.prior_model is not None:
-            for prior in self.prior_model:
-                x = prior.pre_reduce(x, z, pos, batch, extra_args)
-        x = self.output_model.reduce(x, batch, num_systems=num_systems)
-        if self.mean is not None:
-            x = x + self.mean
-        y = self.output_model.post_reduce(x)
-        if self.prior_model is not None:
-            for prior in self.prior_model:
-                y = prior.post_reduce(y, z, pos, batch, box, extra_args)
+        fused_head = self._fused_head()
+        if fused_head is not None:
+            # rows a10 + a11 as three launches (csrc/head.cu): norm3 -> LayerNorm -> Linear -> SiLU -> MLP -> * std -> + atomref ->
+            # per-molecule sum -> + mean, with a hand-written backward to the node tensors
+            from ..extensions import fused
+            hw, atomref = fused_head
+            X = self.representation_model.forward_irreps(z, pos, batch, box=box, q=q, s=s)
+            m = self.output_model.resolve_num_systems(batch, num_systems)
+            y = fused.tail_head_energy(X, z, batch, m, hw, self.std, self.mean, atomref)
+        else:
+            x, v, z, pos, batch = self.representation_model(z, pos, batch, box=box, q=q, s=s)
+            x = self.output_model.pre_reduce(x, v, z, pos, batch, box=box)
+            if self.std is not None:
+                x = x * self.std
+            if self.prior_model is not None:
+                for prior in self.prior_model:
+                    x = prior.pre_reduce(x, z, pos, batch, extra_args)
+            x = self.output_model.reduce(x, batch, num_systems=num_systems)
+            if self.mean is not None:
+                x = x + self.mean
+            y = self.output_model.post_reduce(x)
+            if self.prior_model is not None:
+                for prior in self.prior_model:
+                    y = prior.post_reduce(y, z, pos, batch, box, extra_args)
         if self.derivative:
             dy = torch.autograd.grad([y], [pos], grad_outputs=[torch.ones_like(y)], create_graph=self.training,
                                      retain_graph=self.training)[0]

@@ -32,8 +32,11 @@ class OutputModel(nn.Module):
     def reduce(self, x, batch, num_systems: Optional[int] = None):
         """Per-molecule reduction.  `num_systems` avoids the host read of batch.max(); without it the size is
         read once per call outside CUDA-graph capture and frozen inside capture (reference :43-73)."""
+        return scatter(x, batch, dim=0, dim_size=self.resolve_num_systems(batch, num_systems), reduce=self.reduce_op)
+
+    def resolve_num_systems(self, batch, num_systems: Optional[int] = None) -> int:
         if num_systems is None:
-            capturing = x.is_cuda and torch.cuda.is_current_stream_capturing()
+            capturing = batch.is_cuda and torch.cuda.is_current_stream_capturing()
             if not capturing:
                 self.dim_size = int(batch.max().item()) + 1
             else:
@@ -41,7 +44,7 @@ class OutputModel(nn.Module):
                 warn(f"CUDA graph capture will lock the batch to the current number of samples ({self.dim_size}). "
                      "Changing this will result in a crash")
             num_systems = self.dim_size
-        return scatter(x, batch, dim=0, dim_size=num_systems, reduce=self.reduce_op)
+        return int(num_systems)
 
     def post_reduce(self, x):
         return x

@@ -221,8 +221,24 @@ class TensorNet(nn.Module):
                           "inference path")
         return False
 
+    def head_weights(self, output_network) -> "fused.HeadWeights":
+        """weights of the fused tail + head kernel (csrc/head.cu): out_norm, linear and the two Linear layers of the Scalar MLP"""
+        lin_a, lin_b = output_network.layers[0], output_network.layers[-1]
+        hw = getattr(self, "_head_w", None)
+        if hw is None or hw.mods[2] is not lin_a or hw.mods[3] is not lin_b:
+            hw = self._head_w = fused.HeadWeights(self.out_norm, self.linear, lin_a, lin_b)
+        return hw
+
     def forward(self, z: Tensor, pos: Tensor, batch: Tensor, box: Optional[Tensor] = None, q: Optional[Tensor] = None,
                 s: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor], Tensor, Tensor, Tensor]:
+        X = self.forward_irreps(z, pos, batch, box=box, q=q, s=s)
+        x = self.out_norm(ops.norm3_compact(*X))
+        x = self.act(self.linear(x))
+        return x, None, z, pos, batch
+
+    def forward_irreps(self, z: Tensor, pos: Tensor, batch: Tensor, box: Optional[Tensor] = None, q: Optional[Tensor] = None,
+                       s: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
+        """node tensors X = (I, A, S) after the last interaction layer (everything of `forward` but the tail)"""
         if pos.dtype != torch.float32:
             raise RuntimeError("torchmdnet_b200 TensorNet kernels are fp32 (precision: 32)")
         g = self.distance.graph(pos, batch, box)
@@ -264,6 +280,4 @@ class TensorNet(nn.Module):
             X = self.tensor_embedding(z, g, li, lj, cut, rhat, rbf)
             for layer in self.layers:
                 X = layer(X, g, rbf, cut, qf)
-        x = self.out_norm(ops.norm3_compact(*X))
-        x = self.act(self.linear(x))
-        return x, None, z, pos, batch
+        return X
