@@ -218,12 +218,16 @@ int tmd_mp_coop_bwd(const float* YI, const float* YA, const float* YS, const flo
                     int max_pairs, int n, int F, const int* rows, const int* union_j, const unsigned char* ucount,
                     const unsigned short* upos, const int* goff, const int* gcnt, float* dYI, float* dYA, float* dYS,
                     float* g_dist, void* stream);
-int tmd_embed_fwd(const float* rhat, const float* dist, const float* dp, const int* pid, const int* nbr_j,
-                  const int* indptr, const float* U, const float* V, double lo, double hi, int n, int F, float* oI,
-                  float* oA, float* oS, void* stream);
-int tmd_embed_bwd(const float* rhat, const float* dist, const float* dp, const float* dpp, const int* pid,
-                  const int* nbr_j, const int* indptr, const float* U, const float* V, double lo, double hi, int n,
-                  int F, const float* dI, const float* dA, const float* dS, float* g_dist, float* g_rhat, void* stream);
+/* embedding message passing on pair-indexed radial projections dp[P_u,3F] (and their d/dr dpp): the unit vector is formed in the
+ * kernel from (vec, dist) of the neighbour list (0 for the self loop, tensornet.py:363-366); U, V are per-atom rows [n,F] when
+ * zidx == NULL, else per-element tables [max_z,F] indexed through the atomic numbers zidx[n] (U_i = U[z_i], V_j = V[z_j]).
+ * Backward w.r.t. geometry: g_dist[E] and g_vec[E,3]. */
+int tmd_embed_fwd(const float* vec, const float* dist, const float* dp, const int* pid, const int* nbr_j,
+                  const int* indptr, const float* U, const float* V, const int64_t* zidx, double lo, double hi, int n, int F,
+                  float* oI, float* oA, float* oS, void* stream);
+int tmd_embed_bwd(const float* vec, const float* dist, const float* dp, const float* dpp, const int* pid,
+                  const int* nbr_j, const int* indptr, const float* U, const float* V, const int64_t* zidx, double lo, double hi,
+                  int n, int F, const float* dI, const float* dA, const float* dS, float* g_dist, float* g_vec, void* stream);
 
 /* ---- a10 + a11: TensorNet tail + Scalar head + per-molecule reduction (csrc/head.cu) -------------------------------------
  * Replaces tensor_norm3 -> LayerNorm(3F) -> Linear(3F->F) -> SiLU (models/tensornet.py:394-402), Scalar.pre_reduce = MLP

@@ -142,7 +142,14 @@ def test_fused_embedding():
     dist, vec = g.dist[:E], g.vec[:E]
     rhat = vec / dist.masked_fill(dist == 0, 1).unsqueeze(1)
     pair_r = fused.pair_distances(dist, pidx, P)
-    out = fused.embedding_message_passing(dist, rhat, U, V, pair_r, chain, rbf, 0.0, 5.0, g, pidx)
+    out = fused.embedding_message_passing(dist, vec, U, V, pair_r, chain, rbf, 0.0, 5.0, g, pidx)
+    # the same through per-element tables: U_i = T_u[z_i], V_j = T_v[z_j]
+    zz = torch.randint(0, 7, (n,), device=dev)
+    TU, TV = torch.randn(7, F, device=dev), torch.randn(7, F, device=dev)
+    out_t = fused.embedding_message_passing(dist, vec, TU, TV, pair_r, chain, rbf, 0.0, 5.0, g, pidx, zidx=zz)
+    out_r = fused.embedding_message_passing(dist, vec, TU[zz], TV[zz], pair_r, chain, rbf, 0.0, 5.0, g, pidx)
+    for a, b in zip(out_t, out_r):
+        assert torch.equal(a, b)
     i, j = g.nbr_i[:E].long(), g.nbr_j[:E].long()
     x = rbf(dist)
     w = (CosineCutoff(0.0, 5.0)(dist).unsqueeze(-1) * (U[i] + V[j])).unsqueeze(1) * torch.stack([l(x) for l in lins], 1)

@@ -70,8 +70,8 @@ SIGNATURES = {
     "tmd_head_fwd": ([P, P, P, I, I, I, P, P, D] + [P] * 9 + [I] + [P] * 4 + [P], 1),
     "tmd_segment_sum": ([P, P, I, I, P, P, P, P], 2),
     "tmd_head_bwd": ([P, P, P, I, I, I, P, D] + [P] * 6 + [I] + [P] * 6 + [P], 1),
-    "tmd_embed_fwd": ([P] * 8 + [D, D, I, I] + [P] * 3 + [P], 1),
-    "tmd_embed_bwd": ([P] * 9 + [D, D, I, I] + [P] * 5 + [P], 1),
+    "tmd_embed_fwd": ([P] * 9 + [D, D, I, I] + [P] * 3 + [P], 1),
+    "tmd_embed_bwd": ([P] * 10 + [D, D, I, I] + [P] * 5 + [P], 1),
 }
 
 

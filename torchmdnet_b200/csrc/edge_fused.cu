@@ -429,25 +429,37 @@ __global__ void __launch_bounds__(256, 2) mp_edge_bwd_kernel(CIrr Y, CIrr dM, co
 }
 
 // embedding: w_e[k,:] = C(r_e) (U_i + V_j) dp_p[k,:]  accumulated into I/A/S of atom i  (tensornet.py:554-585)
-__global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict__ rhat, const float* __restrict__ dist,
+// The unit vector rhat = vec / |vec| (0 for the self loop, tensornet.py:363-366) is formed in the kernel from the neighbour
+// list's (vec, dist); U / V are either per-atom rows (zidx == NULL) or per-element tables indexed through the atomic numbers
+// zidx (U_i = U[z_i], V_j = V[z_j]): emb2([Z_i ; Z_j]) = W_u emb(z_i) + W_v emb(z_j) + b depends on the elements only, so
+// for frozen weights it is two [max_z, F] tables built once per model (the analogue of the reference's Zij table,
+// TensorEmbedding.setup_for_inference, tensornet.py:509-533) -- 64 KB, L1-resident.
+__device__ __forceinline__ void unit_vec(const float* __restrict__ vec, const float* __restrict__ dist, int k, float* r, float* inv) {
+  const float d = __ldg(dist + k);
+  *inv = d == 0.f ? 1.f : 1.f / d;
+  r[0] = __ldg(vec + 3 * k) * *inv; r[1] = __ldg(vec + 3 * k + 1) * *inv; r[2] = __ldg(vec + 3 * k + 2) * *inv;
+}
+__global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict__ vec, const float* __restrict__ dist,
                                                         const float* __restrict__ dp, const int* __restrict__ pid,
                                                         const int* __restrict__ nbr_j, const int* __restrict__ indptr,
                                                         const float* __restrict__ U, const float* __restrict__ V,
-                                                        float lo, float hi, int n, int F, MIrr out) {
+                                                        const int64_t* __restrict__ zidx, float lo, float hi, int n, int F, MIrr out) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < n; b += gridDim.x * wpb) {
     const int k0 = indptr[b], k1 = indptr[b + 1];
+    const long long ub_row = zidx ? zidx[b] : b;
     for (int h = lane * 4; h < F; h += 128) {
       float4 acc[9];
 #pragma unroll
       for (int c = 0; c < 9; ++c) acc[c] = zero4();
-      const float4 ub = ldg4(U + (long long)b * F + h);
+      const float4 ub = ldg4(U + ub_row * F + h);
       for (int k = k0; k < k1; ++k) {
         const long long j = nbr_j[k], p = pid[k];
-        const float r[3] = {__ldg(rhat + 3 * k), __ldg(rhat + 3 * k + 1), __ldg(rhat + 3 * k + 2)};
+        float r[3], inv;
+        unit_vec(vec, dist, k, r, &inv);
         float cut, dcut;
         tn::cosine_cutoff(__ldg(dist + k), lo, hi, &cut, &dcut);
-        float4 zc = add4(ub, ldg4(V + j * F + h));
+        float4 zc = add4(ub, ldg4(V + (zidx ? zidx[j] : j) * F + h));
         zc = make_float4(zc.x * cut, zc.y * cut, zc.z * cut, zc.w * cut);
         const float* de = dp + p * 3 * (long long)F + h;
         const float4 w1 = mul4(zc, ldg4(de)), w2 = mul4(zc, ldg4(de + F)), w3 = mul4(zc, ldg4(de + 2 * F));
@@ -463,32 +475,37 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict_
     }
   }
 }
-// backward wrt geometry only (U, V, weights are inference constants): g_dist[e], g_rhat[e,3]
+// backward wrt geometry only (U, V, weights are inference constants): g_dist[e] (through the cutoff, the radial projections
+// and the normalisation of rhat) and g_vec[e,3] = g_rhat / |vec|
 template <bool ONE_CHUNK>
-__global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict__ rhat, const float* __restrict__ dist,
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict__ vec, const float* __restrict__ dist,
                                                         const float* __restrict__ dp, const float* __restrict__ dpp,
                                                         const int* __restrict__ pid, const int* __restrict__ nbr_j,
                                                         const int* __restrict__ indptr, const float* __restrict__ U,
-                                                        const float* __restrict__ V, float lo, float hi, int n, int F,
-                                                        CIrr dout, float* __restrict__ g_dist, float* __restrict__ g_rhat) {
+                                                        const float* __restrict__ V, const int64_t* __restrict__ zidx, float lo,
+                                                        float hi, int n, int F, CIrr dout, float* __restrict__ g_dist,
+                                                        float* __restrict__ g_vec) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < n; b += gridDim.x * wpb) {
     const int k0 = indptr[b], k1 = indptr[b + 1];
+    const long long ub_row = zidx ? zidx[b] : b;
     // ONE_CHUNK (F <= 128): the row's own dOut and U are loaded once, not once per edge
     float4 d[9], ub = zero4();
-    if (ONE_CHUNK && lane * 4 < F) { ld9(dout, b, F, lane * 4, d); ub = ldg4(U + (long long)b * F + lane * 4); }
+    if (ONE_CHUNK && lane * 4 < F) { ld9(dout, b, F, lane * 4, d); ub = ldg4(U + ub_row * F + lane * 4); }
     for (int k = k0; k < k1; ++k) {
       const long long j = nbr_j[k], p = pid[k];
-      const float r[3] = {__ldg(rhat + 3 * k), __ldg(rhat + 3 * k + 1), __ldg(rhat + 3 * k + 2)};
+      float r[3], inv;
+      unit_vec(vec, dist, k, r, &inv);
       float cut, dcut;
       tn::cosine_cutoff(__ldg(dist + k), lo, hi, &cut, &dcut);
       float a[3], s[5];
       tn::skew_compact(r, a); tn::sym_basis(r, s);
       float gr[3] = {0.f, 0.f, 0.f};
       float gd = 0.f;
+      const long long vrow = zidx ? zidx[j] : j;
       for (int h = lane * 4; h < F; h += 128) {
-        if (!ONE_CHUNK) { ld9(dout, b, F, h, d); ub = ldg4(U + (long long)b * F + h); }
-        const float4 z = add4(ub, ldg4(V + j * F + h));
+        if (!ONE_CHUNK) { ld9(dout, b, F, h, d); ub = ldg4(U + ub_row * F + h); }
+        const float4 z = add4(ub, ldg4(V + vrow * F + h));
         const float* de = dp + p * 3 * (long long)F + h;
         const float* dde = dpp + p * 3 * (long long)F + h;
         const float4 q1 = ldg4(de), q2 = ldg4(de + F), q3 = ldg4(de + 2 * F);
@@ -518,7 +535,13 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict_
         }
       }
       gd = warp_sum(gd); gr[0] = warp_sum(gr[0]); gr[1] = warp_sum(gr[1]); gr[2] = warp_sum(gr[2]);
-      if (lane == 0) { g_dist[k] = gd; g_rhat[3 * k] = gr[0]; g_rhat[3 * k + 1] = gr[1]; g_rhat[3 * k + 2] = gr[2]; }
+      if (lane == 0) {
+        // rhat = vec * inv with inv = 1/dist (1 for the self loop, whose vec is 0): d/dvec = g_rhat * inv,
+        // d/ddist = -(g_rhat . rhat) * inv (0 for the self loop: the masked denominator is a constant there)
+        const bool self = __ldg(dist + k) == 0.f;
+        g_dist[k] = gd - (self ? 0.f : (gr[0] * r[0] + gr[1] * r[1] + gr[2] * r[2]) * inv);
+        g_vec[3 * k] = gr[0] * inv; g_vec[3 * k + 1] = gr[1] * inv; g_vec[3 * k + 2] = gr[2] * inv;
+      }
     }
   }
 }
@@ -616,28 +639,28 @@ int tmd_mp_edge_bwd(const float* YI, const float* YA, const float* YS, const flo
   return tmd_check_launch("mp_edge_bwd");
 }
 
-int tmd_embed_fwd(const float* rhat, const float* dist, const float* dp, const int* pid, const int* nbr_j,
-                  const int* indptr, const float* U, const float* V, double lo, double hi, int n, int F, float* oI,
-                  float* oA, float* oS, void* stream) {
+int tmd_embed_fwd(const float* vec, const float* dist, const float* dp, const int* pid, const int* nbr_j,
+                  const int* indptr, const float* U, const float* V, const int64_t* zidx, double lo, double hi, int n, int F,
+                  float* oI, float* oA, float* oS, void* stream) {
   TMD_REQUIRE(F > 0 && F % 4 == 0, "embed_fwd: F must be a positive multiple of 4");
-  TMD_REQUIRE(rhat && dist && dp && pid && nbr_j && indptr && U && V && oI && oA && oS, "embed_fwd: null pointer");
+  TMD_REQUIRE(vec && dist && dp && pid && nbr_j && indptr && U && V && oI && oA && oS, "embed_fwd: null pointer");
   if (n == 0) return TMD_OK;
   embed_fwd_kernel<<<tmd_blocks_for((long long)n * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-      rhat, dist, dp, pid, nbr_j, indptr, U, V, (float)lo, (float)hi, n, F, MIrr{oI, oA, oS});
+      vec, dist, dp, pid, nbr_j, indptr, U, V, zidx, (float)lo, (float)hi, n, F, MIrr{oI, oA, oS});
   return tmd_check_launch("embed_fwd");
 }
-int tmd_embed_bwd(const float* rhat, const float* dist, const float* dp, const float* dpp, const int* pid,
-                  const int* nbr_j, const int* indptr, const float* U, const float* V, double lo, double hi, int n,
-                  int F, const float* dI, const float* dA, const float* dS, float* g_dist, float* g_rhat, void* stream) {
+int tmd_embed_bwd(const float* vec, const float* dist, const float* dp, const float* dpp, const int* pid,
+                  const int* nbr_j, const int* indptr, const float* U, const float* V, const int64_t* zidx, double lo, double hi,
+                  int n, int F, const float* dI, const float* dA, const float* dS, float* g_dist, float* g_vec, void* stream) {
   TMD_REQUIRE(F > 0 && F % 4 == 0, "embed_bwd: F must be a positive multiple of 4");
-  TMD_REQUIRE(rhat && dist && dp && dpp && pid && nbr_j && indptr && U && V && dI && dA && dS && g_dist && g_rhat, "embed_bwd: null pointer");
+  TMD_REQUIRE(vec && dist && dp && dpp && pid && nbr_j && indptr && U && V && dI && dA && dS && g_dist && g_vec, "embed_bwd: null pointer");
   if (n == 0) return TMD_OK;
   if (F <= 128)
     embed_bwd_kernel<true><<<tmd_blocks_for((long long)n * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-        rhat, dist, dp, dpp, pid, nbr_j, indptr, U, V, (float)lo, (float)hi, n, F, CIrr{dI, dA, dS}, g_dist, g_rhat);
+        vec, dist, dp, dpp, pid, nbr_j, indptr, U, V, zidx, (float)lo, (float)hi, n, F, CIrr{dI, dA, dS}, g_dist, g_vec);
   else
     embed_bwd_kernel<false><<<tmd_blocks_for((long long)n * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-        rhat, dist, dp, dpp, pid, nbr_j, indptr, U, V, (float)lo, (float)hi, n, F, CIrr{dI, dA, dS}, g_dist, g_rhat);
+        vec, dist, dp, dpp, pid, nbr_j, indptr, U, V, zidx, (float)lo, (float)hi, n, F, CIrr{dI, dA, dS}, g_dist, g_vec);
   return tmd_check_launch("embed_bwd");
 }
 

@@ -454,37 +454,40 @@ def interaction_message_passing(Y, dist, pair_r, chain, rbf_mod, lo, hi, g, pidx
 
 
 class _EmbeddingMP(torch.autograd.Function):
-    """I/A/S of the TensorNet embedding from (dist, rhat) with w = C(r)(U_i+V_j)(W_k rbf + b_k) built in-kernel (row a5)."""
+    """I/A/S of the TensorNet embedding from the neighbour list's (dist, vec) with w = C(r)(U_i+V_j)(W_k rbf + b_k) built in-kernel
+    (row a5).  U, V: per-atom rows [N,F] (zidx None) or per-element tables [max_z,F] read through the atomic numbers zidx [N]."""
 
     @staticmethod
-    def forward(ctx, dist, rhat, U, V, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op):
-        need = dist.requires_grad or rhat.requires_grad
+    def forward(ctx, dist, vec, U, V, zidx, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op):
+        need = dist.requires_grad or vec.requires_grad
         dp, dpp = run_chain(chain, pair_r.detach(), pidx.num_unique, rbf_mod, lo, hi, need, rbf_op)
-        dist_c, rhat_c, U, V = dist.detach().contiguous(), rhat.detach().contiguous(), U.contiguous(), V.contiguous()
-        N, F = U.shape[0], U.shape[-1]
+        dist_c, vec_c, U, V = dist.detach().contiguous(), vec.detach().contiguous(), U.contiguous(), V.contiguous()
+        zidx = None if zidx is None else zidx.contiguous()
+        N, F = g.indptr.shape[0] - 1, U.shape[-1]
         out = _triple(N, F, U.device)
-        _lib.call("tmd_embed_fwd", p(rhat_c), p(dist_c), p(dp), p(pidx.pid), p(g.nbr_j), p(g.indptr), p(U), p(V), float(lo),
+        _lib.call("tmd_embed_fwd", p(vec_c), p(dist_c), p(dp), p(pidx.pid), p(g.nbr_j), p(g.indptr), p(U), p(V), p(zidx), float(lo),
                   float(hi), N, F, p(out[0]), p(out[1]), p(out[2]), device=U.device)
-        ctx.save_for_backward(dist_c, rhat_c, dp, dpp if dpp is not None else dp, pidx.pid, g.nbr_j, g.indptr, U, V)
-        ctx.has_tangent, ctx.lo, ctx.hi = dpp is not None, float(lo), float(hi)
+        ctx.save_for_backward(dist_c, vec_c, dp, dpp if dpp is not None else dp, pidx.pid, g.nbr_j, g.indptr, U, V,
+                              zidx if zidx is not None else pidx.pid)
+        ctx.has_tangent, ctx.has_z, ctx.lo, ctx.hi, ctx.N = dpp is not None, zidx is not None, float(lo), float(hi), N
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dI, dA, dS):
-        dist, rhat, dp, dpp, pid, nbr_j, indptr, U, V = ctx.saved_tensors
+        dist, vec, dp, dpp, pid, nbr_j, indptr, U, V, zidx = ctx.saved_tensors
         if not ctx.has_tangent:
-            return (None,) * 12
-        N, F = U.shape[0], U.shape[-1]
-        g_dist, g_rhat = torch.zeros_like(dist), torch.zeros_like(rhat)
+            return (None,) * 13
+        N, F = ctx.N, U.shape[-1]
+        g_dist, g_vec = torch.zeros_like(dist), torch.zeros_like(vec)
         dI, dA, dS = dI.contiguous(), dA.contiguous(), dS.contiguous()
-        _lib.call("tmd_embed_bwd", p(rhat), p(dist), p(dp), p(dpp), p(pid), p(nbr_j), p(indptr), p(U), p(V), ctx.lo, ctx.hi,
-                  N, F, p(dI), p(dA), p(dS), p(g_dist), p(g_rhat), device=U.device)
-        return g_dist, g_rhat, None, None, None, None, None, None, None, None, None, None
+        _lib.call("tmd_embed_bwd", p(vec), p(dist), p(dp), p(dpp), p(pid), p(nbr_j), p(indptr), p(U), p(V), p(zidx) if ctx.has_z else None,
+                  ctx.lo, ctx.hi, N, F, p(dI), p(dA), p(dS), p(g_dist), p(g_vec), device=U.device)
+        return (g_dist, g_vec) + (None,) * 11
 
 
-def embedding_message_passing(dist, rhat, U, V, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op=None):
-    return _EmbeddingMP.apply(dist, rhat, U, V, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op)
+def embedding_message_passing(dist, vec, U, V, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op=None, zidx=None):
+    return _EmbeddingMP.apply(dist, vec, U, V, zidx, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op)
 
 
 class _ETMessage(torch.autograd.Function):

@@ -76,16 +76,28 @@ class TensorEmbedding(nn.Module):
             self._nl = fused.IrrepsLinearWeights(self.linears_tensor)
         return self._nl
 
+    def element_tables(self):
+        """(U, V) [max_z, F]: emb2([Z_i ; Z_j]) = U[z_i] + V[z_j] with U = emb W_u^T, V = emb W_v^T + b.  The pair embedding depends
+        on the two ELEMENTS only, so for frozen weights it is two small tables built once per weight version -- what the reference's
+        `setup_for_inference` Zij table is for (tensornet.py:509-533), at max_z rows instead of max_z^2."""
+        ws = (self.emb.weight, self.emb2.weight, self.emb2.bias)
+        key = tuple((t.data_ptr(), t._version) for t in ws)
+        if getattr(self, "_uv_key", None) != key:
+            F_ = self.hidden_channels
+            with torch.no_grad():
+                E = self.emb.weight.detach()
+                U = torch.nn.functional.linear(E, self.emb2.weight.detach()[:, :F_]).contiguous()
+                V = torch.nn.functional.linear(E, self.emb2.weight.detach()[:, F_:], self.emb2.bias.detach()).contiguous()
+            self._uv, self._uv_key = (U, V), key
+        return self._uv
+
     def forward(self, z, g, nbr_i, nbr_j, cut, rhat, rbf, fast=None):
         if fast is not None:
             # fused path: U/V per atom, radial projections per pair (with d/dr), w assembled inside the kernel
-            F_ = self.hidden_channels
-            Z = self.emb(z)
-            U = torch.nn.functional.linear(Z, self.emb2.weight[:, :F_])
-            V = torch.nn.functional.linear(Z, self.emb2.weight[:, F_:], self.emb2.bias)
             dist, pair_r, pidx, rbf_mod, rbf_op, _plan = fast
-            I, A, S = fused.embedding_message_passing(dist, rhat, U.detach(), V.detach(), pair_r, self.radial_chain(), rbf_mod,
-                                                      self.cutoff.cutoff_lower, self.cutoff.cutoff_upper, g, pidx, rbf_op)
+            UT, VT = self.element_tables()
+            I, A, S = fused.embedding_message_passing(dist, g.vec[: dist.shape[0]], UT, VT, pair_r, self.radial_chain(), rbf_mod,
+                                                      self.cutoff.cutoff_lower, self.cutoff.cutoff_upper, g, pidx, rbf_op, zidx=z)
         else:
             w = self.pair_weights(z, nbr_i, nbr_j, cut, rbf)
             I, A, S = ops.fn_radial_message_passing(rhat, w, None, g.indptr)
@@ -258,8 +270,6 @@ class TensorNet(nn.Module):
             E = min(E, dist.shape[0])
             nbr_i, nbr_j, dist, vec = nbr_i[:E], nbr_j[:E], dist[:E], vec[:E]
         qf = torch.ones(z.shape[0], device=pos.device, dtype=pos.dtype) if q is None else 1 + 0.1 * q[batch].to(pos.dtype)
-        # unit vectors; self loops (dist == 0) keep a zero vector (tensornet.py:363-366)
-        rhat = vec / dist.masked_fill(dist == 0, 1).unsqueeze(1)
         if use_fused:
             pair_r = pidx.pair_r[:P]   # per-pair distances (no autograd: every fused op differentiates w.r.t. the per-slot dist)
             # rbf(r) and d rbf/dr once per frame: the layer-0 tensor-core operand of every radial chain
@@ -269,12 +279,14 @@ class TensorNet(nn.Module):
             # one plan per frame for the message passing of all layers (row groups + their neighbour unions, csrc/mp_coop.cu)
             plan = fused.MessagePassingPlan(g, pidx, self.hidden_channels) if self.num_layers > 0 else None
             fast = (dist, pair_r, pidx, self.distance_expansion, rbf_op, plan)
-            X = self.tensor_embedding(z, g, None, None, None, rhat, None, fast=fast)
+            X = self.tensor_embedding(z, g, None, None, None, None, None, fast=fast)
             for layer in self.layers:
                 X = layer(X, g, None, None, qf, fast=fast)
         else:
             # padded slots (static shapes) belong to no CSR row; clamp their indices so gathers stay in range
             li, lj = nbr_i.clamp(min=0).long(), nbr_j.clamp(min=0).long()
+            # unit vectors; self loops (dist == 0) keep a zero vector (tensornet.py:363-366)
+            rhat = vec / dist.masked_fill(dist == 0, 1).unsqueeze(1)
             rbf = self.distance_expansion(dist)
             cut = self.cutoff(dist)
             X = self.tensor_embedding(z, g, li, lj, cut, rhat, rbf)
