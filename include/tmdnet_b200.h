@@ -199,13 +199,15 @@ int tmd_mp_edge_bwd(const float* YI, const float* YA, const float* YS, const flo
                     const float* dMS, const float* f, const float* fp, const int* pid, const int* nbr_j,
                     const int* indptr, int n, int F, float* dYI, float* dYA, float* dYS, float* g_dist, void* stream);
 /* ---- a7, cooperative form (csrc/mp_coop.cu): the same message passing (tensornet_mp.py:42-131) with the neighbour rows of a
- * GROUP of 16 spatially adjacent atoms staged once per group in shared memory (bulk async copies into an mbarrier ring) and the
+ * GROUP of tmd_mp_group_size() (15) spatially adjacent atoms staged once per group in shared memory (bulk async copies into an mbarrier ring) and the
  * per-pair radial rows streamed through per-warp async rings.  Bit-identical to tmd_mp_fwd / tmd_mp_edge_bwd.
- * tmd_mp_plan builds the per-frame plan shared by all launches of a frame: rows[n] (atom of slot r; group g = rows[16g..16g+16):
+ * tmd_mp_plan builds the per-frame plan shared by all launches of a frame: rows[n] (atom of slot r; group g = rows[G g .. G g + G),
+ * G = tmd_mp_group_size():
  * `order` when given and *order_flag != 0, else 0..n-1), union_j / ucount [max_pairs] (sorted distinct neighbours of each group
  * and the number of its rows containing them, at goff[g] .. goff[g] + gcnt[g]), upos[max_pairs] (position of nbr_j[k] in its
  * group's union, bit 15 = self loop), gcnt[g] = -1 for a group over the staged capacity (it is gathered directly).
  * cursor: one int of scratch.  F % 4 == 0, F <= 128. */
+int tmd_mp_group_size(void);
 int tmd_mp_plan(const int* indptr, const int* nbr_j, const int* num_pairs, int max_pairs, int n, const int* order,
                 const int* order_flag, int* rows, int* cursor, int* union_j, unsigned char* ucount, unsigned short* upos,
                 int* goff, int* gcnt, void* stream);

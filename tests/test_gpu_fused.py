@@ -284,7 +284,7 @@ def test_cooperative_message_passing_bit_exact(case, monkeypatch):
     assert torch.equal(torch.sort(rows).values, torch.arange(n, device=dev))
     gcnt = plan.gcnt.long()
     assert (gcnt >= 0).all(), "no group may overflow the staged path on these inputs"
-    grp_of_row = torch.empty(n, dtype=torch.long, device=dev); grp_of_row[rows] = torch.arange(n, device=dev) // 16
+    grp_of_row = torch.empty(n, dtype=torch.long, device=dev); grp_of_row[rows] = torch.arange(n, device=dev) // plan.group
     ge = grp_of_row[g.nbr_i[:E].long()]
     up = plan.upos[:E].to(torch.int32) & 0xFFFF
     t = (up & 0x7FFF).long()

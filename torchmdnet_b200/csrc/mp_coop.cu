@@ -2,12 +2,12 @@
 //
 // The warp-per-atom kernels of message_passing.cu / edge_fused.cu gather the neighbour's node row (9 F-vectors = 4.6 KB at
 // F = 128) once per EDGE; atoms that sit next to each other share most of their neighbours, and the kernels were limited by
-// L2->SM bytes (8-9 TB/s of ~12), not by HBM (profiles/r01_mp_ncu.md).  Here a CTA owns a GROUP of G = 16 rows that are
+// L2->SM bytes (8-9 TB/s of ~12), not by HBM (profiles/r01_mp_ncu.md).  Here a CTA owns a GROUP of G = 15 rows that are
 // spatial neighbours (consecutive entries of the neighbour list's cell order), and
 //   * every DISTINCT neighbour row of the group is staged ONCE in shared memory: a producer warp walks the group's sorted
 //     neighbour union and issues three bulk async copies (cp.async.bulk, I / A / S segments) per row into an mbarrier ring;
-//     the 16 consumer warps (one row each) read it with LDS.  On the C4 water box 16 rows have ~210 distinct neighbours for
-//     ~860 edges, so gather traffic drops from 4.6 KB to ~1.1 KB per edge;
+//     the 15 consumer warps (one row each) read it with LDS.  On the C4 water box 15 rows have ~200 distinct neighbours for
+//     ~800 edges, so gather traffic drops from 4.6 KB to ~1.1 KB per edge;
 //   * the per-pair radial rows f_p (and f'_p in the backward) are streamed through a private per-warp ring of bulk async
 //     copies issued D edges ahead, so bytes in flight are bounded by shared memory (170-220 KB per SM), not by registers;
 //   * a consumer only synchronises on the union elements its own row contains: the plan stores, per edge, the position of
@@ -22,7 +22,8 @@
 
 namespace {
 
-constexpr int G = 16;            // rows per group = consumer warps per CTA
+constexpr int G = 15;            // rows per group = consumer warps per CTA (+ 1 producer warp = 16 warps: registers are
+                                 // allocated per 4 warps, so 17 warps would be charged as 20 and cap the kernel at 96 registers)
 constexpr int UMAX = 2048;       // distinct neighbours of a group the staged path handles (else: direct-gather fallback)
 constexpr int GCAP = 4096;       // edges of a group the plan kernel sorts (else: fallback)
 constexpr int PLAN_THREADS = 256;
@@ -255,7 +256,7 @@ __device__ __forceinline__ void producer_loop(uint64_t* full, uint64_t* empty, f
 
 // forward: M_b = sum_{k in row b} f[pid[k]] (x) Y[nbr_j[k]]      (F <= 128, F % 4 == 0)
 template <int S, int D>
-__global__ void __maxnreg__(120) mp_coop_fwd_kernel(CIrr Y, const float* __restrict__ f, const int* __restrict__ pid,
+__global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_fwd_kernel(CIrr Y, const float* __restrict__ f, const int* __restrict__ pid,
                                                                      const int* __restrict__ nbr_j, const int* __restrict__ indptr,
                                                                      const int* __restrict__ num_pairs, int max_pairs, int n, int F,
                                                                      const int* __restrict__ rows, const int* __restrict__ union_j,
@@ -354,7 +355,7 @@ __global__ void __maxnreg__(120) mp_coop_fwd_kernel(CIrr Y, const float* __restr
 
 // backward: dY_b = sum_k f_p dM_j,   g_dist[k] = < f'_p , dM_j * Y_b >  (0 for the self loop), slot k = (b, j)
 template <int S, int D>
-__global__ void __maxnreg__(120) mp_coop_bwd_kernel(CIrr Y, CIrr dM, const float* __restrict__ f,
+__global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_bwd_kernel(CIrr Y, CIrr dM, const float* __restrict__ f,
                                                                      const float* __restrict__ fp, const int* __restrict__ pid,
                                                                      const int* __restrict__ nbr_j, const int* __restrict__ indptr,
                                                                      const int* __restrict__ num_pairs, int max_pairs, int n, int F,
@@ -494,8 +495,11 @@ __global__ void __maxnreg__(120) mp_coop_bwd_kernel(CIrr Y, CIrr dM, const float
 
 extern "C" {
 
+// rows per cooperative group (the plan arrays goff / gcnt have ceil(n / this) entries)
+int tmd_mp_group_size(void) { return G; }
+
 // workspace sizes (elements): rows[n] int, union_j[max_pairs] int, ucount[max_pairs] u8, upos[max_pairs] u16,
-// goff / gcnt [ceil(n / 16)] int, cursor[1] int (zeroed by this call)
+// goff / gcnt [ceil(n / tmd_mp_group_size())] int, cursor[1] int (zeroed by this call)
 int tmd_mp_plan(const int* indptr, const int* nbr_j, const int* num_pairs, int max_pairs, int n, const int* order,
                 const int* order_flag, int* rows, int* cursor, int* union_j, unsigned char* ucount, unsigned short* upos,
                 int* goff, int* gcnt, void* stream) {

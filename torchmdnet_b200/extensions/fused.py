@@ -353,7 +353,7 @@ class MessagePassingPlan:
     through `pid`): `forward(Y, f) -> M`, `backward(Y, dM, f, fp) -> (dY, g_dist)`.  bench.py times these two entry points for
     the `roofline` / `roofline_secondary` keys, so the benchmark and the model share one launch path.
 
-    Cooperative path (F <= 128): one `tmd_mp_plan` launch per frame groups the rows 16 by 16 in the neighbour search's cell order
+    Cooperative path (F <= 128): one `tmd_mp_plan` launch per frame groups the rows 15 by 15 in the neighbour search's cell order
     (spatially adjacent atoms share most neighbours) and lists each group's distinct neighbours; the forward / backward kernels
     stage every distinct neighbour row once per group in shared memory.  Results are bit-identical to the warp-per-atom kernels."""
 
@@ -363,7 +363,8 @@ class MessagePassingPlan:
         self.coop = bool(USE_MP_COOP and self.N > 0 and (F is None or (F % 4 == 0 and F <= 128)))
         if self.coop:
             dev, cap, n = g.dist.device, g.dist.shape[0], self.N
-            ng = -(-n // 16)
+            self.group = int(_lib.library().tmd_mp_group_size())
+            ng = -(-n // self.group)
             i32 = dict(device=dev, dtype=torch.int32)
             self.rows = torch.empty(n, **i32)
             self.union_j = torch.empty(cap, **i32)
