@@ -217,18 +217,22 @@ __global__ void __launch_bounds__(PLAN_THREADS) mp_plan_kernel(const int* __rest
 //   [0, 8 S)                    full[S]   mbarriers (tx-count: one staged node row)
 //   [8 S, 16 S)                 empty[S]  mbarriers (count G: one arrival per row of the group)
 //   [16 S, 16 S + 8 G D)        fbar[G][D] mbarriers (tx-count: the radial row(s) of one edge)
+//   then issued[S] ints: number of uses of slot s the producer has issued so far.  A consumer skips the union elements its
+//   row does not contain, so it can be several uses of a slot ahead of the slot's current one; mbarrier parity waits only
+//   tell adjacent phases apart, so before waiting for use n of slot s it first spins until issued[s] > n (the producer issues
+//   use n only after every consumer of use n-1 has released the slot, i.e. the barrier is then in phase n).
 //   ring  S x 9F floats, then per-warp radial rings G x D x (3F or 6F) floats
 template <int S, int D, bool BWD>
 struct CoopSmem {
   static constexpr int kBars = 2 * S + G * D;
-  static __host__ __device__ size_t bar_bytes() { return ((size_t)kBars * 8 + 127) / 128 * 128; }
+  static __host__ __device__ size_t bar_bytes() { return ((size_t)kBars * 8 + (size_t)S * 4 + 127) / 128 * 128; }   // + issued[S]
   static __host__ __device__ size_t ring_bytes(int F) { return (size_t)S * 9 * F * 4; }
   static __host__ __device__ size_t fring_bytes(int F) { return (size_t)G * D * (BWD ? 6 : 3) * F * 4; }
   static __host__ __device__ size_t total(int F) { return bar_bytes() + ring_bytes(F) + fring_bytes(F); }
 };
 
 template <int S>
-__device__ __forceinline__ void producer_loop(uint64_t* full, uint64_t* empty, float* ring, const CIrr& T, int F,
+__device__ __forceinline__ void producer_loop(uint64_t* full, uint64_t* empty, volatile int* issued, float* ring, const CIrr& T, int F,
                                               const int* __restrict__ union_j, const unsigned char* __restrict__ ucount,
                                               int off, int U, int lane) {
   const uint32_t row_bytes = 9u * F * 4u;
@@ -249,6 +253,7 @@ __device__ __forceinline__ void producer_loop(uint64_t* full, uint64_t* empty, f
         bulk_g2s(dst + F, T.A + j * 3 * F, 3u * F * 4u, full + s);
         bulk_g2s(dst + 4 * F, T.S + j * 5 * F, 5u * F * 4u, full + s);
         if (c < G) mbar_arrive_n(empty + s, (uint32_t)(G - c));   // rows of the group that do not contain j
+        issued[s] = t / S + 1;
       }
     }
   }
@@ -269,19 +274,20 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_fwd_kernel(CIrr Y, co
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + S;
   uint64_t* fbar = empty + S;
+  volatile int* issued = reinterpret_cast<volatile int*>(fbar + G * D);
   float* ring = reinterpret_cast<float*>(smem + L::bar_bytes());
   float* fring = ring + (size_t)S * 9 * F;
   const int g = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int U = gcnt[g], off = goff[g];
   const int E = min(*num_pairs, max_pairs);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, G); }
+    for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, G); issued[s] = 0; }
     for (int i = 0; i < G * D; ++i) mbar_init(fbar + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (wid == G) {   // ---------------------------------------------------------------- producer warp
-    if (U > 0) producer_loop<S>(full, empty, ring, Y, F, union_j, ucount, off, U, lane);
+    if (U > 0) producer_loop<S>(full, empty, issued, ring, Y, F, union_j, ucount, off, U, lane);
     return;
   }
   // ------------------------------------------------------------------------------------ consumer warp = one row
@@ -328,6 +334,7 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_fwd_kernel(CIrr Y, co
       const int t = __shfl_sync(0xffffffffu, up_l, i) & (int)(SELF_BIT - 1);
       const int s = t % S;
       mbar_wait(mybar + d, (e / D) & 1);
+      while (issued[s] <= t / S) {}
       mbar_wait(full + s, (t / S) & 1);
       if (on) {
         const float* fe = myf + (size_t)d * 3 * F + h;
@@ -369,19 +376,20 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_bwd_kernel(CIrr Y, CI
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + S;
   uint64_t* fbar = empty + S;
+  volatile int* issued = reinterpret_cast<volatile int*>(fbar + G * D);
   float* ring = reinterpret_cast<float*>(smem + L::bar_bytes());
   float* fring = ring + (size_t)S * 9 * F;
   const int g = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int U = gcnt[g], off = goff[g];
   const int E = min(*num_pairs, max_pairs);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, G); }
+    for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, G); issued[s] = 0; }
     for (int i = 0; i < G * D; ++i) mbar_init(fbar + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (wid == G) {
-    if (U > 0) producer_loop<S>(full, empty, ring, dM, F, union_j, ucount, off, U, lane);
+    if (U > 0) producer_loop<S>(full, empty, issued, ring, dM, F, union_j, ucount, off, U, lane);
     return;
   }
   const int r = g * G + wid;
@@ -445,6 +453,7 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_bwd_kernel(CIrr Y, CI
       const int t_ = up & (int)(SELF_BIT - 1);
       const int s = t_ % S;
       mbar_wait(mybar + d, (e / D) & 1);
+      while (issued[s] <= t_ / S) {}
       mbar_wait(full + s, (t_ / S) & 1);
       float t = 0.f;
       if (on) {
