@@ -18,6 +18,7 @@
 //
 // The per-frame plan (tmd_mp_plan) is one launch shared by the 3 forward + 3 backward launches of a 3-layer frame.
 // Reference semantics: torchmdnet/extensions/warp_kernels/tensornet_mp.py:42-131 (message_passing_fwd / _bwd).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -231,31 +232,26 @@ struct CoopSmem {
   static __host__ __device__ size_t total(int F) { return bar_bytes() + ring_bytes(F) + fring_bytes(F); }
 };
 
+// producer warp: lane s owns ring slot s and fills it with the union elements t = s, s + S, s + 2S, ... (the slots are independent,
+// so 16-24 lanes issue their barrier operations and bulk copies side by side instead of one lane walking the union serially)
 template <int S>
 __device__ __forceinline__ void producer_loop(uint64_t* full, uint64_t* empty, volatile int* issued, float* ring, const CIrr& T, int F,
                                               const int* __restrict__ union_j, const unsigned char* __restrict__ ucount,
                                               int off, int U, int lane) {
+  static_assert(S <= 32, "one producer lane per ring slot");
+  if (lane >= S) return;
   const uint32_t row_bytes = 9u * F * 4u;
-  for (int t0 = 0; t0 < U; t0 += 32) {
-    const int tl = t0 + lane;
-    const int jl = tl < U ? union_j[off + tl] : 0;
-    const int cl = tl < U ? (int)ucount[off + tl] : G;
-    const int m = min(32, U - t0);
-    for (int i = 0; i < m; ++i) {
-      const int t = t0 + i, s = t % S;
-      const long long j = __shfl_sync(0xffffffffu, jl, i);
-      const int c = __shfl_sync(0xffffffffu, cl, i);
-      if (t >= S) mbar_wait(empty + s, ((t / S) - 1) & 1);
-      if (lane == 0) {
-        float* dst = ring + (size_t)s * 9 * F;
-        mbar_expect_tx(full + s, row_bytes);
-        bulk_g2s(dst, T.I + j * F, (uint32_t)F * 4u, full + s);
-        bulk_g2s(dst + F, T.A + j * 3 * F, 3u * F * 4u, full + s);
-        bulk_g2s(dst + 4 * F, T.S + j * 5 * F, 5u * F * 4u, full + s);
-        if (c < G) mbar_arrive_n(empty + s, (uint32_t)(G - c));   // rows of the group that do not contain j
-        issued[s] = t / S + 1;
-      }
-    }
+  float* dst = ring + (size_t)lane * 9 * F;
+  for (int t = lane, n = 0; t < U; t += S, ++n) {
+    const long long j = union_j[off + t];
+    const int c = (int)ucount[off + t];
+    if (n > 0) mbar_wait(empty + lane, (n - 1) & 1);
+    mbar_expect_tx(full + lane, row_bytes);
+    bulk_g2s(dst, T.I + j * F, (uint32_t)F * 4u, full + lane);
+    bulk_g2s(dst + F, T.A + j * 3 * F, 3u * F * 4u, full + lane);
+    bulk_g2s(dst + 4 * F, T.S + j * 5 * F, 5u * F * 4u, full + lane);
+    if (c < G) mbar_arrive_n(empty + lane, (uint32_t)(G - c));   // rows of the group that do not contain j
+    issued[lane] = n + 1;
   }
 }
 
@@ -529,11 +525,19 @@ int tmd_mp_coop_fwd(const float* YI, const float* YA, const float* YS, const flo
   TMD_REQUIRE(YI && YA && YS && f && pid && nbr_j && indptr && num_pairs && rows && union_j && ucount && upos && goff && gcnt && MI && MA && MS,
               "mp_coop_fwd: null pointer");
   if (n == 0) return TMD_OK;
-  constexpr int S = 16, D = 4;
-  const size_t smem = CoopSmem<S, D, false>::total(F);
-  cudaFuncSetAttribute(mp_coop_fwd_kernel<S, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  mp_coop_fwd_kernel<S, D><<<(n + G - 1) / G, COOP_THREADS, smem, (cudaStream_t)stream>>>(
-      CIrr{YI, YA, YS}, f, pid, nbr_j, indptr, num_pairs, max_pairs, n, F, rows, union_j, ucount, upos, goff, gcnt, MIrr{MI, MA, MS});
+  static const int cfg = getenv("TMD_COOP_FWD") ? atoi(getenv("TMD_COOP_FWD")) : 0;
+#define TMD_COOP_FWD_LAUNCH(S_, D_)                                                                                                   \
+  do {                                                                                                                              \
+    const size_t smem = CoopSmem<S_, D_, false>::total(F);                                                                          \
+    cudaFuncSetAttribute(mp_coop_fwd_kernel<S_, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                        \
+    mp_coop_fwd_kernel<S_, D_><<<(n + G - 1) / G, COOP_THREADS, smem, (cudaStream_t)stream>>>(                                       \
+        CIrr{YI, YA, YS}, f, pid, nbr_j, indptr, num_pairs, max_pairs, n, F, rows, union_j, ucount, upos, goff, gcnt, MIrr{MI, MA, MS}); \
+  } while (0)
+  if (cfg == 1) TMD_COOP_FWD_LAUNCH(16, 4);
+  else if (cfg == 2) TMD_COOP_FWD_LAUNCH(24, 4);
+  else if (cfg == 3) TMD_COOP_FWD_LAUNCH(12, 7);
+  else TMD_COOP_FWD_LAUNCH(16, 6);
+#undef TMD_COOP_FWD_LAUNCH
   return tmd_check_launch("mp_coop_fwd");
 }
 
@@ -547,12 +551,20 @@ int tmd_mp_coop_bwd(const float* YI, const float* YA, const float* YS, const flo
               "mp_coop_bwd: null pointer");
   TMD_REQUIRE(!fp || g_dist, "mp_coop_bwd: fp given without g_dist");
   if (n == 0) return TMD_OK;
-  constexpr int S = 12, D = 3;
-  const size_t smem = CoopSmem<S, D, true>::total(F);
-  cudaFuncSetAttribute(mp_coop_bwd_kernel<S, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  mp_coop_bwd_kernel<S, D><<<(n + G - 1) / G, COOP_THREADS, smem, (cudaStream_t)stream>>>(
-      CIrr{YI, YA, YS}, CIrr{dMI, dMA, dMS}, f, fp, pid, nbr_j, indptr, num_pairs, max_pairs, n, F, rows, union_j, ucount, upos,
-      goff, gcnt, MIrr{dYI, dYA, dYS}, g_dist);
+  static const int cfg = getenv("TMD_COOP_BWD") ? atoi(getenv("TMD_COOP_BWD")) : 0;
+#define TMD_COOP_BWD_LAUNCH(S_, D_)                                                                                                   \
+  do {                                                                                                                              \
+    const size_t smem = CoopSmem<S_, D_, true>::total(F);                                                                           \
+    cudaFuncSetAttribute(mp_coop_bwd_kernel<S_, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                        \
+    mp_coop_bwd_kernel<S_, D_><<<(n + G - 1) / G, COOP_THREADS, smem, (cudaStream_t)stream>>>(                                       \
+        CIrr{YI, YA, YS}, CIrr{dMI, dMA, dMS}, f, fp, pid, nbr_j, indptr, num_pairs, max_pairs, n, F, rows, union_j, ucount, upos,      \
+        goff, gcnt, MIrr{dYI, dYA, dYS}, g_dist);                                                                                   \
+  } while (0)
+  if (cfg == 1) TMD_COOP_BWD_LAUNCH(8, 4);
+  else if (cfg == 2) TMD_COOP_BWD_LAUNCH(16, 2);
+  else if (cfg == 3) TMD_COOP_BWD_LAUNCH(16, 3);
+  else TMD_COOP_BWD_LAUNCH(12, 3);
+#undef TMD_COOP_BWD_LAUNCH
   return tmd_check_launch("mp_coop_bwd");
 }
 

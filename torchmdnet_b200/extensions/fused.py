@@ -438,7 +438,7 @@ class _InteractionMP(torch.autograd.Function):
             plan = MessagePassingPlan(g, pidx, YI.shape[-1])
         M = plan.forward((YI, YA, YS), f)
         ctx.save_for_backward(YI, YA, YS, f, fp if fp is not None else f)
-        ctx.has_fp, ctx.plan = fp is not None, plan
+        ctx.has_fp, ctx.plan, ctx.E = fp is not None, plan, dist.shape[0]
         return M
 
     @staticmethod
@@ -447,6 +447,8 @@ class _InteractionMP(torch.autograd.Function):
         YI, YA, YS, f, fp = ctx.saved_tensors
         dM = (dI.contiguous(), dA.contiguous(), dS.contiguous())   # bound to a local: the copies outlive the launch
         dY, g_dist = ctx.plan.backward((YI, YA, YS), dM, f, fp if ctx.has_fp else None)
+        if g_dist is not None and g_dist.shape[0] != ctx.E:     # dynamic shapes: `dist` is the exact-size prefix of the capacity buffer
+            g_dist = g_dist[: ctx.E]
         return dY[0], dY[1], dY[2], g_dist, None, None, None, None, None, None, None, None, None
 
 
@@ -611,8 +613,9 @@ class HeadWeights:
     def supported(self) -> bool:
         out_norm, linear, lin_a, lin_b = self.mods
         F, H = linear.out_features, lin_a.out_features
+        smem_bwd = 32 * (2 * (3 * F + 4) + (F + 4) + (H + 4)) * 4      # tile buffers of head_bwd_kernel (csrc/head.cu)
         return (linear.in_features == 3 * F and lin_a.in_features == F and lin_b.in_features == H and lin_b.out_features == 1 and
-                F % 32 == 0 and H % 32 == 0 and F <= 256 and H <= 256 and out_norm.elementwise_affine and
+                F % 32 == 0 and H % 32 == 0 and F <= 256 and H <= 256 and smem_bwd <= 227 * 1024 and out_norm.elementwise_affine and
                 tuple(out_norm.normalized_shape) == (3 * F,) and all(t.dtype == torch.float32 for t in self.params()))
 
     def tensors(self):
