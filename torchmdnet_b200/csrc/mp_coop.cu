@@ -56,6 +56,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
+// non-blocking probe of a phase (test_wait never suspends the thread) and a pure polling wait built on it
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+template <bool POLL>
+__device__ __forceinline__ void mbar_wait_c(uint64_t* bar, uint32_t parity) {
+  if (POLL) { while (!mbar_test(bar, parity)) {} }
+  else mbar_wait(bar, parity);
+}
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -233,30 +249,39 @@ struct CoopSmem {
 };
 
 // producer warp: lane s owns ring slot s and fills it with the union elements t = s, s + S, s + 2S, ... (the slots are independent,
-// so 16-24 lanes issue their barrier operations and bulk copies side by side instead of one lane walking the union serially)
+// so 16-24 lanes issue their barrier operations and bulk copies side by side instead of one lane walking the union serially).
+// The lanes poll their slot's "empty" barrier with the non-blocking test_wait in ONE converged loop: a blocking try_wait in
+// divergent lanes would park the whole warp on one lane's barrier while other lanes' slots are already free.
 template <int S>
 __device__ __forceinline__ void producer_loop(uint64_t* full, uint64_t* empty, volatile int* issued, float* ring, const CIrr& T, int F,
                                               const int* __restrict__ union_j, const unsigned char* __restrict__ ucount,
                                               int off, int U, int lane) {
   static_assert(S <= 32, "one producer lane per ring slot");
-  if (lane >= S) return;
   const uint32_t row_bytes = 9u * F * 4u;
-  float* dst = ring + (size_t)lane * 9 * F;
-  for (int t = lane, n = 0; t < U; t += S, ++n) {
-    const long long j = union_j[off + t];
-    const int c = (int)ucount[off + t];
-    if (n > 0) mbar_wait(empty + lane, (n - 1) & 1);
-    mbar_expect_tx(full + lane, row_bytes);
-    bulk_g2s(dst, T.I + j * F, (uint32_t)F * 4u, full + lane);
-    bulk_g2s(dst + F, T.A + j * 3 * F, 3u * F * 4u, full + lane);
-    bulk_g2s(dst + 4 * F, T.S + j * 5 * F, 5u * F * 4u, full + lane);
-    if (c < G) mbar_arrive_n(empty + lane, (uint32_t)(G - c));   // rows of the group that do not contain j
-    issued[lane] = n + 1;
+  const int sl = lane < S ? lane : 0;
+  float* dst = ring + (size_t)sl * 9 * F;
+  int t = lane, n = 0;
+  bool active = lane < S && t < U;
+  long long j = active ? union_j[off + t] : 0;
+  int c = active ? (int)ucount[off + t] : G;
+  while (__any_sync(0xffffffffu, active)) {
+    const bool ready = active && (n == 0 || mbar_test(empty + sl, (n - 1) & 1));
+    if (ready) {
+      mbar_expect_tx(full + sl, row_bytes);
+      bulk_g2s(dst, T.I + j * F, (uint32_t)F * 4u, full + sl);
+      bulk_g2s(dst + F, T.A + j * 3 * F, 3u * F * 4u, full + sl);
+      bulk_g2s(dst + 4 * F, T.S + j * 5 * F, 5u * F * 4u, full + sl);
+      if (c < G) mbar_arrive_n(empty + sl, (uint32_t)(G - c));   // rows of the group that do not contain j
+      issued[sl] = n + 1;
+      t += S; ++n;
+      active = t < U;
+      if (active) { j = union_j[off + t]; c = (int)ucount[off + t]; }
+    }
   }
 }
 
 // forward: M_b = sum_{k in row b} f[pid[k]] (x) Y[nbr_j[k]]      (F <= 128, F % 4 == 0)
-template <int S, int D>
+template <int S, int D, bool POLL>
 __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_fwd_kernel(CIrr Y, const float* __restrict__ f, const int* __restrict__ pid,
                                                                      const int* __restrict__ nbr_j, const int* __restrict__ indptr,
                                                                      const int* __restrict__ num_pairs, int max_pairs, int n, int F,
@@ -329,9 +354,9 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_fwd_kernel(CIrr Y, co
       const int e = e0 + i, d = e % D;
       const int t = __shfl_sync(0xffffffffu, up_l, i) & (int)(SELF_BIT - 1);
       const int s = t % S;
-      mbar_wait(mybar + d, (e / D) & 1);
+      mbar_wait_c<POLL>(mybar + d, (e / D) & 1);
       while (issued[s] <= t / S) {}
-      mbar_wait(full + s, (t / S) & 1);
+      mbar_wait_c<POLL>(full + s, (t / S) & 1);
       if (on) {
         const float* fe = myf + (size_t)d * 3 * F + h;
         const float* row = ring + (size_t)s * 9 * F + h;
@@ -357,7 +382,7 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_fwd_kernel(CIrr Y, co
 }
 
 // backward: dY_b = sum_k f_p dM_j,   g_dist[k] = < f'_p , dM_j * Y_b >  (0 for the self loop), slot k = (b, j)
-template <int S, int D>
+template <int S, int D, bool POLL>
 __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_bwd_kernel(CIrr Y, CIrr dM, const float* __restrict__ f,
                                                                      const float* __restrict__ fp, const int* __restrict__ pid,
                                                                      const int* __restrict__ nbr_j, const int* __restrict__ indptr,
@@ -448,9 +473,9 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_bwd_kernel(CIrr Y, CI
       const int up = __shfl_sync(0xffffffffu, up_l, i);
       const int t_ = up & (int)(SELF_BIT - 1);
       const int s = t_ % S;
-      mbar_wait(mybar + d, (e / D) & 1);
+      mbar_wait_c<POLL>(mybar + d, (e / D) & 1);
       while (issued[s] <= t_ / S) {}
-      mbar_wait(full + s, (t_ / S) & 1);
+      mbar_wait_c<POLL>(full + s, (t_ / S) & 1);
       float t = 0.f;
       if (on) {
         const float* fe = myf + (size_t)d * 6 * F + h;
@@ -526,17 +551,17 @@ int tmd_mp_coop_fwd(const float* YI, const float* YA, const float* YS, const flo
               "mp_coop_fwd: null pointer");
   if (n == 0) return TMD_OK;
   static const int cfg = getenv("TMD_COOP_FWD") ? atoi(getenv("TMD_COOP_FWD")) : 0;
-#define TMD_COOP_FWD_LAUNCH(S_, D_)                                                                                                   \
+#define TMD_COOP_FWD_LAUNCH(S_, D_, P_)                                                                                                  \
   do {                                                                                                                              \
     const size_t smem = CoopSmem<S_, D_, false>::total(F);                                                                          \
-    cudaFuncSetAttribute(mp_coop_fwd_kernel<S_, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                        \
-    mp_coop_fwd_kernel<S_, D_><<<(n + G - 1) / G, COOP_THREADS, smem, (cudaStream_t)stream>>>(                                       \
+    cudaFuncSetAttribute(mp_coop_fwd_kernel<S_, D_, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                    \
+    mp_coop_fwd_kernel<S_, D_, P_><<<(n + G - 1) / G, COOP_THREADS, smem, (cudaStream_t)stream>>>(                                       \
         CIrr{YI, YA, YS}, f, pid, nbr_j, indptr, num_pairs, max_pairs, n, F, rows, union_j, ucount, upos, goff, gcnt, MIrr{MI, MA, MS}); \
   } while (0)
-  if (cfg == 1) TMD_COOP_FWD_LAUNCH(16, 4);
-  else if (cfg == 2) TMD_COOP_FWD_LAUNCH(24, 4);
-  else if (cfg == 3) TMD_COOP_FWD_LAUNCH(12, 7);
-  else TMD_COOP_FWD_LAUNCH(16, 6);
+  if (cfg == 1) TMD_COOP_FWD_LAUNCH(24, 4, false);
+  else if (cfg == 2) TMD_COOP_FWD_LAUNCH(16, 4, true);
+  else if (cfg == 3) TMD_COOP_FWD_LAUNCH(32, 3, true);
+  else TMD_COOP_FWD_LAUNCH(24, 4, true);
 #undef TMD_COOP_FWD_LAUNCH
   return tmd_check_launch("mp_coop_fwd");
 }
@@ -552,18 +577,18 @@ int tmd_mp_coop_bwd(const float* YI, const float* YA, const float* YS, const flo
   TMD_REQUIRE(!fp || g_dist, "mp_coop_bwd: fp given without g_dist");
   if (n == 0) return TMD_OK;
   static const int cfg = getenv("TMD_COOP_BWD") ? atoi(getenv("TMD_COOP_BWD")) : 0;
-#define TMD_COOP_BWD_LAUNCH(S_, D_)                                                                                                   \
+#define TMD_COOP_BWD_LAUNCH(S_, D_, P_)                                                                                                  \
   do {                                                                                                                              \
     const size_t smem = CoopSmem<S_, D_, true>::total(F);                                                                           \
-    cudaFuncSetAttribute(mp_coop_bwd_kernel<S_, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                        \
-    mp_coop_bwd_kernel<S_, D_><<<(n + G - 1) / G, COOP_THREADS, smem, (cudaStream_t)stream>>>(                                       \
+    cudaFuncSetAttribute(mp_coop_bwd_kernel<S_, D_, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                    \
+    mp_coop_bwd_kernel<S_, D_, P_><<<(n + G - 1) / G, COOP_THREADS, smem, (cudaStream_t)stream>>>(                                       \
         CIrr{YI, YA, YS}, CIrr{dMI, dMA, dMS}, f, fp, pid, nbr_j, indptr, num_pairs, max_pairs, n, F, rows, union_j, ucount, upos,      \
         goff, gcnt, MIrr{dYI, dYA, dYS}, g_dist);                                                                                   \
   } while (0)
-  if (cfg == 1) TMD_COOP_BWD_LAUNCH(8, 4);
-  else if (cfg == 2) TMD_COOP_BWD_LAUNCH(16, 2);
-  else if (cfg == 3) TMD_COOP_BWD_LAUNCH(16, 3);
-  else TMD_COOP_BWD_LAUNCH(12, 3);
+  if (cfg == 1) TMD_COOP_BWD_LAUNCH(16, 2, false);
+  else if (cfg == 2) TMD_COOP_BWD_LAUNCH(16, 3, true);
+  else if (cfg == 3) TMD_COOP_BWD_LAUNCH(24, 2, true);
+  else TMD_COOP_BWD_LAUNCH(16, 2, true);
 #undef TMD_COOP_BWD_LAUNCH
   return tmd_check_launch("mp_coop_bwd");
 }
