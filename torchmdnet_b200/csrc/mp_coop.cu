@@ -341,18 +341,24 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_fwd_kernel(CIrr Y, co
   float* myf = fring + (size_t)wid * D * 3 * F;
   uint64_t* mybar = fbar + wid * D;
   const uint32_t frow_bytes = 3u * F * 4u;
-  if (lane == 0) {
-    for (int d = 0; d < D && d < nE; ++d) {
+  // edge metadata (pair id, union position) lives in registers, 32 edges per lane-parallel load and one chunk ahead: no global
+  // load sits on the per-edge critical path (the refill of the radial ring needs pid[e + D], possibly from the next chunk)
+  int pid_c = lane < nE ? pid[k0 + lane] : 0, up_c = lane < nE ? (int)upos[k0 + lane] : 0;
+  int pid_n = 32 + lane < nE ? pid[k0 + 32 + lane] : 0, up_n = 32 + lane < nE ? (int)upos[k0 + 32 + lane] : 0;
+  for (int d = 0; d < D && d < nE; ++d) {
+    const long long p0 = __shfl_sync(0xffffffffu, pid_c, d);
+    if (lane == 0) {
       mbar_expect_tx(mybar + d, frow_bytes);
-      bulk_g2s(myf + (size_t)d * 3 * F, f + (long long)pid[k0 + d] * 3 * F, frow_bytes, mybar + d);
+      bulk_g2s(myf + (size_t)d * 3 * F, f + p0 * 3 * F, frow_bytes, mybar + d);
     }
   }
   for (int e0 = 0; e0 < nE; e0 += 32) {
-    const int up_l = (e0 + lane < nE) ? (int)upos[k0 + e0 + lane] : 0;
     const int m = min(32, nE - e0);
     for (int i = 0; i < m; ++i) {
       const int e = e0 + i, d = e % D;
-      const int t = __shfl_sync(0xffffffffu, up_l, i) & (int)(SELF_BIT - 1);
+      const int t = __shfl_sync(0xffffffffu, up_c, i) & (int)(SELF_BIT - 1);
+      const int q = i + D;
+      const long long pn = q < 32 ? __shfl_sync(0xffffffffu, pid_c, q & 31) : __shfl_sync(0xffffffffu, pid_n, q & 31);
       const int s = t % S;
       mbar_wait_c<POLL>(mybar + d, (e / D) & 1);
       while (issued[s] <= t / S) {}
@@ -373,10 +379,13 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_fwd_kernel(CIrr Y, co
         mbar_arrive(empty + s);
         if (e + D < nE) {
           mbar_expect_tx(mybar + d, frow_bytes);
-          bulk_g2s(myf + (size_t)d * 3 * F, f + (long long)pid[k0 + e + D] * 3 * F, frow_bytes, mybar + d);
+          bulk_g2s(myf + (size_t)d * 3 * F, f + pn * 3 * F, frow_bytes, mybar + d);
         }
       }
     }
+    pid_c = pid_n; up_c = up_n;
+    pid_n = e0 + 64 + lane < nE ? pid[k0 + e0 + 64 + lane] : 0;
+    up_n = e0 + 64 + lane < nE ? (int)upos[k0 + e0 + 64 + lane] : 0;
   }
   if (on) st9(M, b, F, h, acc);
 }
@@ -451,26 +460,27 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_bwd_kernel(CIrr Y, CI
     if (on) st9(dY, b, F, h, acc);
     return;
   }
-  const int fw = fp ? 6 : 3;                      // floats per channel of one ring slot: f (3F) [+ f' (3F)]
   float* myf = fring + (size_t)wid * D * 6 * F;
   uint64_t* mybar = fbar + wid * D;
   const uint32_t frow_bytes = 3u * F * 4u;
-  if (lane == 0) {
-    for (int d = 0; d < D && d < nE; ++d) {
-      const long long p = pid[k0 + d];
+  int pid_c = lane < nE ? pid[k0 + lane] : 0, up_c = lane < nE ? (int)upos[k0 + lane] : 0;
+  int pid_n = 32 + lane < nE ? pid[k0 + 32 + lane] : 0, up_n = 32 + lane < nE ? (int)upos[k0 + 32 + lane] : 0;
+  for (int d = 0; d < D && d < nE; ++d) {
+    const long long p0 = __shfl_sync(0xffffffffu, pid_c, d);
+    if (lane == 0) {
       mbar_expect_tx(mybar + d, frow_bytes * (fp ? 2u : 1u));
-      bulk_g2s(myf + (size_t)d * 6 * F, f + p * 3 * F, frow_bytes, mybar + d);
-      if (fp) bulk_g2s(myf + (size_t)d * 6 * F + 3 * F, fp + p * 3 * F, frow_bytes, mybar + d);
+      bulk_g2s(myf + (size_t)d * 6 * F, f + p0 * 3 * F, frow_bytes, mybar + d);
+      if (fp) bulk_g2s(myf + (size_t)d * 6 * F + 3 * F, fp + p0 * 3 * F, frow_bytes, mybar + d);
     }
   }
-  (void)fw;
   for (int e0 = 0; e0 < nE; e0 += 32) {
-    const int up_l = (e0 + lane < nE) ? (int)upos[k0 + e0 + lane] : 0;
     const int m = min(32, nE - e0);
     float keep = 0.f;                              // lane i keeps g_dist of edge e0 + i: one coalesced store per 32 edges
     for (int i = 0; i < m; ++i) {
       const int e = e0 + i, d = e % D;
-      const int up = __shfl_sync(0xffffffffu, up_l, i);
+      const int up = __shfl_sync(0xffffffffu, up_c, i);
+      const int q = i + D;
+      const long long pn = q < 32 ? __shfl_sync(0xffffffffu, pid_c, q & 31) : __shfl_sync(0xffffffffu, pid_n, q & 31);
       const int t_ = up & (int)(SELF_BIT - 1);
       const int s = t_ % S;
       mbar_wait_c<POLL>(mybar + d, (e / D) & 1);
@@ -505,10 +515,9 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_bwd_kernel(CIrr Y, CI
       if (lane == 0) {
         mbar_arrive(empty + s);
         if (e + D < nE) {
-          const long long p = pid[k0 + e + D];
           mbar_expect_tx(mybar + d, frow_bytes * (fp ? 2u : 1u));
-          bulk_g2s(myf + (size_t)d * 6 * F, f + p * 3 * F, frow_bytes, mybar + d);
-          if (fp) bulk_g2s(myf + (size_t)d * 6 * F + 3 * F, fp + p * 3 * F, frow_bytes, mybar + d);
+          bulk_g2s(myf + (size_t)d * 6 * F, f + pn * 3 * F, frow_bytes, mybar + d);
+          if (fp) bulk_g2s(myf + (size_t)d * 6 * F + 3 * F, fp + pn * 3 * F, frow_bytes, mybar + d);
         }
       }
       if (fp) {
@@ -517,6 +526,9 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_bwd_kernel(CIrr Y, CI
       }
     }
     if (fp && lane < m) g_dist[k0 + e0 + lane] = keep;
+    pid_c = pid_n; up_c = up_n;
+    pid_n = e0 + 64 + lane < nE ? pid[k0 + e0 + 64 + lane] : 0;
+    up_n = e0 + 64 + lane < nE ? (int)upos[k0 + e0 + 64 + lane] : 0;
   }
   if (on) st9(dY, b, F, h, acc);
 }
@@ -558,10 +570,10 @@ int tmd_mp_coop_fwd(const float* YI, const float* YA, const float* YS, const flo
     mp_coop_fwd_kernel<S_, D_, P_><<<(n + G - 1) / G, COOP_THREADS, smem, (cudaStream_t)stream>>>(                                       \
         CIrr{YI, YA, YS}, f, pid, nbr_j, indptr, num_pairs, max_pairs, n, F, rows, union_j, ucount, upos, goff, gcnt, MIrr{MI, MA, MS}); \
   } while (0)
-  if (cfg == 1) TMD_COOP_FWD_LAUNCH(24, 4, false);
-  else if (cfg == 2) TMD_COOP_FWD_LAUNCH(16, 4, true);
-  else if (cfg == 3) TMD_COOP_FWD_LAUNCH(32, 3, true);
-  else TMD_COOP_FWD_LAUNCH(24, 4, true);
+  if (cfg == 1) TMD_COOP_FWD_LAUNCH(16, 6, false);
+  else if (cfg == 2) TMD_COOP_FWD_LAUNCH(32, 3, false);
+  else if (cfg == 3) TMD_COOP_FWD_LAUNCH(16, 4, false);
+  else TMD_COOP_FWD_LAUNCH(24, 4, false);
 #undef TMD_COOP_FWD_LAUNCH
   return tmd_check_launch("mp_coop_fwd");
 }
@@ -585,10 +597,10 @@ int tmd_mp_coop_bwd(const float* YI, const float* YA, const float* YS, const flo
         CIrr{YI, YA, YS}, CIrr{dMI, dMA, dMS}, f, fp, pid, nbr_j, indptr, num_pairs, max_pairs, n, F, rows, union_j, ucount, upos,      \
         goff, gcnt, MIrr{dYI, dYA, dYS}, g_dist);                                                                                   \
   } while (0)
-  if (cfg == 1) TMD_COOP_BWD_LAUNCH(16, 2, false);
-  else if (cfg == 2) TMD_COOP_BWD_LAUNCH(16, 3, true);
-  else if (cfg == 3) TMD_COOP_BWD_LAUNCH(24, 2, true);
-  else TMD_COOP_BWD_LAUNCH(16, 2, true);
+  if (cfg == 1) TMD_COOP_BWD_LAUNCH(16, 3, false);
+  else if (cfg == 2) TMD_COOP_BWD_LAUNCH(24, 2, false);
+  else if (cfg == 3) TMD_COOP_BWD_LAUNCH(12, 3, false);
+  else TMD_COOP_BWD_LAUNCH(16, 2, false);
 #undef TMD_COOP_BWD_LAUNCH
   return tmd_check_launch("mp_coop_bwd");
 }
