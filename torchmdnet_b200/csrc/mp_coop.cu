@@ -86,6 +86,14 @@ __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.
 
 struct CIrr { const float* I; const float* A; const float* S; };
 struct MIrr { float* I; float* A; float* S; };
+#ifdef TMD_COOP_PROF
+__device__ long long* g_prof = nullptr;   // [groups][16 warps][8]: total, issued spin, full wait, f wait, lane-0 tail, edges, start, end
+#define PROF_T0() const long long _t0 = clock64()
+#define PROF_ADD(var) (var) += clock64() - _t0
+#else
+#define PROF_T0()
+#define PROF_ADD(var)
+#endif
 __device__ __forceinline__ void ld9(const CIrr& T, long long n, int F, int h, float4* c) {
   c[0] = ldg4(T.I + n * F + h);
 #pragma unroll
@@ -314,6 +322,10 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_fwd_kernel(CIrr Y, co
   // ------------------------------------------------------------------------------------ consumer warp = one row
   const int r = g * G + wid;
   if (r >= n) return;
+#ifdef TMD_COOP_PROF
+  long long p_f = 0, p_iss = 0, p_full = 0, p_tail = 0;
+  const long long p_start = clock64();
+#endif
   const int b = rows[r];
   const int k0 = min(indptr[b], E), nE = min(indptr[b + 1], E) - k0;
   const int h = lane * 4;
@@ -360,9 +372,9 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_fwd_kernel(CIrr Y, co
       const int q = i + D;
       const long long pn = q < 32 ? __shfl_sync(0xffffffffu, pid_c, q & 31) : __shfl_sync(0xffffffffu, pid_n, q & 31);
       const int s = t % S;
-      mbar_wait_c<POLL>(mybar + d, (e / D) & 1);
-      while (issued[s] <= t / S) {}
-      mbar_wait_c<POLL>(full + s, (t / S) & 1);
+      { PROF_T0(); mbar_wait_c<POLL>(mybar + d, (e / D) & 1); PROF_ADD(p_f); }
+      { PROF_T0(); while (issued[s] <= t / S) __nanosleep(64); PROF_ADD(p_iss); }
+      { PROF_T0(); mbar_wait_c<POLL>(full + s, (t / S) & 1); PROF_ADD(p_full); }
       if (on) {
         const float* fe = myf + (size_t)d * 3 * F + h;
         const float* row = ring + (size_t)s * 9 * F + h;
@@ -375,6 +387,7 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_fwd_kernel(CIrr Y, co
         for (int c = 4; c < 9; ++c) acc[c] = fma4(w3, *reinterpret_cast<const float4*>(row + c * F), acc[c]);
       }
       __syncwarp();
+      { PROF_T0();
       if (lane == 0) {
         mbar_arrive(empty + s);
         if (e + D < nE) {
@@ -382,12 +395,20 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_fwd_kernel(CIrr Y, co
           bulk_g2s(myf + (size_t)d * 3 * F, f + pn * 3 * F, frow_bytes, mybar + d);
         }
       }
+      __syncwarp(); PROF_ADD(p_tail); }
     }
     pid_c = pid_n; up_c = up_n;
     pid_n = e0 + 64 + lane < nE ? pid[k0 + e0 + 64 + lane] : 0;
     up_n = e0 + 64 + lane < nE ? (int)upos[k0 + e0 + 64 + lane] : 0;
   }
   if (on) st9(M, b, F, h, acc);
+#ifdef TMD_COOP_PROF
+  if (g_prof && lane == 0) {
+    long long* o = g_prof + ((long long)g * 16 + wid) * 8;
+    const long long p_end = clock64();
+    o[0] = p_end - p_start; o[1] = p_iss; o[2] = p_full; o[3] = p_f; o[4] = p_tail; o[5] = nE; o[6] = p_start; o[7] = p_end;
+  }
+#endif
 }
 
 // backward: dY_b = sum_k f_p dM_j,   g_dist[k] = < f'_p , dM_j * Y_b >  (0 for the self loop), slot k = (b, j)
@@ -484,7 +505,7 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_bwd_kernel(CIrr Y, CI
       const int t_ = up & (int)(SELF_BIT - 1);
       const int s = t_ % S;
       mbar_wait_c<POLL>(mybar + d, (e / D) & 1);
-      while (issued[s] <= t_ / S) {}
+      while (issued[s] <= t_ / S) __nanosleep(64);
       mbar_wait_c<POLL>(full + s, (t_ / S) & 1);
       float t = 0.f;
       if (on) {
@@ -537,6 +558,10 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_bwd_kernel(CIrr Y, CI
 
 extern "C" {
 
+#ifdef TMD_COOP_PROF
+int tmd_mp_coop_set_profile(long long* buf) { cudaMemcpyToSymbol(g_prof, &buf, sizeof(buf)); return 0; }
+#endif
+
 // rows per cooperative group (the plan arrays goff / gcnt have ceil(n / this) entries)
 int tmd_mp_group_size(void) { return G; }
 
@@ -570,9 +595,9 @@ int tmd_mp_coop_fwd(const float* YI, const float* YA, const float* YS, const flo
     mp_coop_fwd_kernel<S_, D_, P_><<<(n + G - 1) / G, COOP_THREADS, smem, (cudaStream_t)stream>>>(                                       \
         CIrr{YI, YA, YS}, f, pid, nbr_j, indptr, num_pairs, max_pairs, n, F, rows, union_j, ucount, upos, goff, gcnt, MIrr{MI, MA, MS}); \
   } while (0)
-  if (cfg == 1) TMD_COOP_FWD_LAUNCH(16, 6, false);
+  if (cfg == 1) TMD_COOP_FWD_LAUNCH(32, 2, false);
   else if (cfg == 2) TMD_COOP_FWD_LAUNCH(32, 3, false);
-  else if (cfg == 3) TMD_COOP_FWD_LAUNCH(16, 4, false);
+  else if (cfg == 3) TMD_COOP_FWD_LAUNCH(28, 3, false);
   else TMD_COOP_FWD_LAUNCH(24, 4, false);
 #undef TMD_COOP_FWD_LAUNCH
   return tmd_check_launch("mp_coop_fwd");
@@ -597,10 +622,10 @@ int tmd_mp_coop_bwd(const float* YI, const float* YA, const float* YS, const flo
         CIrr{YI, YA, YS}, CIrr{dMI, dMA, dMS}, f, fp, pid, nbr_j, indptr, num_pairs, max_pairs, n, F, rows, union_j, ucount, upos,      \
         goff, gcnt, MIrr{dYI, dYA, dYS}, g_dist);                                                                                   \
   } while (0)
-  if (cfg == 1) TMD_COOP_BWD_LAUNCH(16, 3, false);
-  else if (cfg == 2) TMD_COOP_BWD_LAUNCH(24, 2, false);
-  else if (cfg == 3) TMD_COOP_BWD_LAUNCH(12, 3, false);
-  else TMD_COOP_BWD_LAUNCH(16, 2, false);
+  if (cfg == 1) TMD_COOP_BWD_LAUNCH(28, 2, false);
+  else if (cfg == 2) TMD_COOP_BWD_LAUNCH(20, 2, false);
+  else if (cfg == 3) TMD_COOP_BWD_LAUNCH(16, 3, false);
+  else TMD_COOP_BWD_LAUNCH(24, 2, false);
 #undef TMD_COOP_BWD_LAUNCH
   return tmd_check_launch("mp_coop_bwd");
 }
