@@ -30,29 +30,58 @@ __device__ __forceinline__ void ld_c(const CI& t, long long n, int F, int h, flo
   for (int k = 0; k < 5; ++k) c[4 + k] = t.S[(n * 5 + k) * F + h];
 }
 
-// acc[q][c] += sum_k in_s[(4 wy + q) * ld + k] * W[k * ldw + lane + 32 c]   for c < ncol  (K % 4 == 0)
+// acc[q][c] += sum_k in_s[(4 wy + q) * ld + k] * W[k * ldw + lane + 32 c]   for c < ncol  (K % KC == 0)
+// W is streamed through shared memory in chunks of KC rows with cp.async double buffering: every CTA reads each weight row
+// once, coalesced, KC rows ahead of its use.  (Reading W straight from global in the inner loop made all ~300 CTAs hit the same
+// 512-byte row of L2 at the same time with the full L2 latency exposed per k-step: 220 us instead of ~20 us for the forward.)
+constexpr int KC = 16;
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void stage_w(float* wb, const float* __restrict__ W, int ldw, int k0, int nc4, int tid) {
+  // KC rows x nc4 float4 columns of W -> wb [KC][4 nc4]
+  for (int i = tid; i < KC * nc4; i += HT) {
+    const int r = i / nc4, c = i - r * nc4;
+    cp_async16(wb + (size_t)r * 4 * nc4 + 4 * c, W + (size_t)(k0 + r) * ldw + 4 * c);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ void tile_gemm(const float* __restrict__ in_s, int ld, int K, const float* __restrict__ W, int ldw,
-                                          int ncol, float (&acc)[4][MAXC], int wy, int lane) {
+                                          int ncol, float (&acc)[4][MAXC], float* wbuf, int wy, int lane, int tid) {
+  const int NC = 32 * ncol, nc4 = NC >> 2;
   const float* a0 = in_s + (4 * wy) * ld;
-  for (int k = 0; k < K; k += 4) {
-    float4 a[4];
+  stage_w(wbuf, W, ldw, 0, nc4, tid);
+  for (int k0 = 0, it = 0; k0 < K; k0 += KC, ++it) {
+    float* cur = wbuf + (size_t)(it & 1) * KC * NC;
+    if (k0 + KC < K) {
+      stage_w(wbuf + (size_t)((it + 1) & 1) * KC * NC, W, ldw, k0 + KC, nc4, tid);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) a[q] = *reinterpret_cast<const float4*>(a0 + q * ld + k);
+    for (int k = 0; k < KC; k += 4) {
+      float4 a[4];
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const float* wrow = W + (size_t)(k + kk) * ldw + lane;
+      for (int q = 0; q < 4; ++q) a[q] = *reinterpret_cast<const float4*>(a0 + q * ld + k0 + k);
 #pragma unroll
-      for (int c = 0; c < MAXC; ++c) {
-        if (c < ncol) {
-          const float b = __ldg(wrow + 32 * c);
+      for (int kk = 0; kk < 4; ++kk) {
+        const float* wrow = cur + (size_t)(k + kk) * NC + lane;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float x = kk == 0 ? a[q].x : kk == 1 ? a[q].y : kk == 2 ? a[q].z : a[q].w;
-            acc[q][c] = fmaf(x, b, acc[q][c]);
+        for (int c = 0; c < MAXC; ++c) {
+          if (c < ncol) {
+            const float b = wrow[32 * c];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float x = kk == 0 ? a[q].x : kk == 1 ? a[q].y : kk == 2 ? a[q].z : a[q].w;
+              acc[q][c] = fmaf(x, b, acc[q][c]);
+            }
           }
         }
       }
     }
+    __syncthreads();   // the buffer is refilled two chunks later
   }
 }
 
@@ -66,13 +95,13 @@ struct HeadW {
   float eps;
 };
 
-// shared memory: xs [TA][3F+4] | h1s [TA][F+4] | h2s [TA][H+4]
+// shared memory: xs [TA][3F+4] | h1s [TA][F+4] | h2s [TA][H+4] | wbuf [2][KC][256] (weight staging)
 __global__ void __launch_bounds__(HT) head_fwd_kernel(CI X, int N, int F, int H, HeadW P, const int64_t* __restrict__ z,
                                                       const float* __restrict__ atomref, int n_ref, float* __restrict__ e_out,
                                                       float* __restrict__ mu_rstd, float* __restrict__ z1, float* __restrict__ z2) {
   extern __shared__ __align__(16) float sm[];
   const int ldx = 3 * F + 4, ld1 = F + 4, ld2 = H + 4;
-  float* xs = sm; float* h1s = xs + TA * ldx; float* h2s = h1s + TA * ld1;
+  float* xs = sm; float* h1s = xs + TA * ldx; float* h2s = h1s + TA * ld1; float* wbuf = h2s + TA * ld2;
   const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
   const long long a0 = (long long)blockIdx.x * TA;
   // 1. norm3 of the node tensors
@@ -107,7 +136,7 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(CI X, int N, int F, int H,
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[q][c] = b;
     }
-    tile_gemm(xs, ldx, 3 * F, P.W1T, F, ncol, acc, wy, lane);
+    tile_gemm(xs, ldx, 3 * F, P.W1T, F, ncol, acc, wbuf, wy, lane, tid);
 #pragma unroll
     for (int c = 0; c < MAXC; ++c)
       if (c < ncol)
@@ -129,7 +158,7 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(CI X, int N, int F, int H,
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[q][c] = b;
     }
-    tile_gemm(h1s, ld1, F, P.W2T, H, ncol, acc, wy, lane);
+    tile_gemm(h1s, ld1, F, P.W2T, H, ncol, acc, wbuf, wy, lane, tid);
 #pragma unroll
     for (int c = 0; c < MAXC; ++c)
       if (c < ncol)
@@ -155,13 +184,13 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(CI X, int N, int F, int H,
   }
 }
 
-// shared memory: x0 [TA][3F+4] (pre-LN norms) | dxs [TA][3F+4] | d1s [TA][F+4] | d2s [TA][H+4]
+// shared memory: x0 [TA][3F+4] (pre-LN norms) | dxs [TA][3F+4] | d1s [TA][F+4] | d2s [TA][H+4] | wbuf [2][KC][256]
 __global__ void __launch_bounds__(HT) head_bwd_kernel(CI X, int N, int F, int H, HeadW P, const float* __restrict__ gy,
                                                       const int64_t* __restrict__ batch, int M, const float* __restrict__ mu_rstd,
                                                       const float* __restrict__ z1, const float* __restrict__ z2, MI dX) {
   extern __shared__ __align__(16) float sm[];
   const int ldx = 3 * F + 4, ld1 = F + 4, ld2 = H + 4;
-  float* x0 = sm; float* dxs = x0 + TA * ldx; float* d1s = dxs + TA * ldx; float* d2s = d1s + TA * ld1;
+  float* x0 = sm; float* dxs = x0 + TA * ldx; float* d1s = dxs + TA * ldx; float* d2s = d1s + TA * ld1; float* wbuf = d2s + TA * ld2;
   const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
   const long long a0 = (long long)blockIdx.x * TA;
   // pre-LN norms (LayerNorm backward needs xhat) and dz2 = de * w3 * SiLU'(z2)
@@ -191,7 +220,7 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(CI X, int N, int F, int H,
     for (int c = 0; c < MAXC; ++c)
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[q][c] = 0.f;
-    tile_gemm(d2s, ld2, H, P.W2, F, ncol, acc, wy, lane);
+    tile_gemm(d2s, ld2, H, P.W2, F, ncol, acc, wbuf, wy, lane, tid);
 #pragma unroll
     for (int c = 0; c < MAXC; ++c)
       if (c < ncol)
@@ -211,7 +240,7 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(CI X, int N, int F, int H,
     for (int c = 0; c < MAXC; ++c)
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[q][c] = 0.f;
-    tile_gemm(d1s, ld1, F, P.W1 + blk * F, 3 * F, ncol, acc, wy, lane);
+    tile_gemm(d1s, ld1, F, P.W1 + blk * F, 3 * F, ncol, acc, wbuf, wy, lane, tid);
 #pragma unroll
     for (int c = 0; c < MAXC; ++c)
       if (c < ncol)
@@ -297,12 +326,12 @@ int tmd_head_fwd(const float* I, const float* A, const float* S, int N, int F, i
                  double eps, const float* W1T, const float* b1, const float* W2T, const float* b2, const float* w3,
                  const float* b3, const float* std_, const int64_t* z, const float* atomref, int n_ref, float* e,
                  float* mu_rstd, float* z1, float* z2, void* stream) {
-  TMD_REQUIRE(F > 0 && F % 32 == 0 && F <= 256 && H > 0 && H % 32 == 0 && H <= 256, "head_fwd: F, H must be multiples of 32, <= 256");
+  TMD_REQUIRE(F > 0 && F % 32 == 0 && F <= 256 && H > 0 && H % 32 == 0 && H <= 256 && H % KC == 0, "head_fwd: F, H must be multiples of 32, <= 256");
   TMD_REQUIRE(I && A && S && ln_w && ln_b && W1T && b1 && W2T && b2 && w3 && b3 && std_ && e && mu_rstd && z1 && z2, "head_fwd: null pointer");
   TMD_REQUIRE(!atomref || z, "head_fwd: atomref without z");
   if (N == 0) return TMD_OK;
   HeadW P{ln_w, ln_b, W1T, b1, W2T, b2, w3, b3, nullptr, nullptr, std_, (float)eps};
-  const size_t smem = (size_t)TA * ((3 * F + 4) + (F + 4) + (H + 4)) * sizeof(float);
+  const size_t smem = ((size_t)TA * ((3 * F + 4) + (F + 4) + (H + 4)) + 2 * KC * 256) * sizeof(float);
   cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   head_fwd_kernel<<<(N + TA - 1) / TA, HT, smem, (cudaStream_t)stream>>>(CI{I, A, S}, N, F, H, P, z, atomref, n_ref, e, mu_rstd, z1, z2);
   return tmd_check_launch("head_fwd");
@@ -327,7 +356,7 @@ int tmd_head_bwd(const float* I, const float* A, const float* S, int N, int F, i
   TMD_REQUIRE(I && A && S && ln_w && W1 && W2 && w3 && std_ && gy && batch && mu_rstd && z1 && z2 && dI && dA && dS, "head_bwd: null pointer");
   if (N == 0) return TMD_OK;
   HeadW P{ln_w, nullptr, nullptr, nullptr, nullptr, nullptr, w3, nullptr, W1, W2, std_, (float)eps};
-  const size_t smem = (size_t)TA * (2 * (3 * F + 4) + (F + 4) + (H + 4)) * sizeof(float);
+  const size_t smem = ((size_t)TA * (2 * (3 * F + 4) + (F + 4) + (H + 4)) + 2 * KC * 256) * sizeof(float);
   TMD_REQUIRE(smem <= 227 * 1024, "head_bwd: F too large for the tile buffers");
   cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   head_bwd_kernel<<<(N + TA - 1) / TA, HT, smem, (cudaStream_t)stream>>>(CI{I, A, S}, N, F, H, P, gy, batch, M, mu_rstd, z1, z2, MI{dI, dA, dS});

@@ -613,7 +613,7 @@ class HeadWeights:
     def supported(self) -> bool:
         out_norm, linear, lin_a, lin_b = self.mods
         F, H = linear.out_features, lin_a.out_features
-        smem_bwd = 32 * (2 * (3 * F + 4) + (F + 4) + (H + 4)) * 4      # tile buffers of head_bwd_kernel (csrc/head.cu)
+        smem_bwd = (32 * (2 * (3 * F + 4) + (F + 4) + (H + 4)) + 2 * 16 * 256) * 4      # tile + weight-staging buffers of head_bwd_kernel (csrc/head.cu)
         return (linear.in_features == 3 * F and lin_a.in_features == F and lin_b.in_features == H and lin_b.out_features == 1 and
                 F % 32 == 0 and H % 32 == 0 and F <= 256 and H <= 256 and smem_bwd <= 227 * 1024 and out_norm.elementwise_affine and
                 tuple(out_norm.normalized_shape) == (3 * F,) and all(t.dtype == torch.float32 for t in self.params()))
