@@ -434,11 +434,27 @@ __global__ void __launch_bounds__(256, 2) mp_edge_bwd_kernel(CIrr Y, CIrr dM, co
 // zidx (U_i = U[z_i], V_j = V[z_j]): emb2([Z_i ; Z_j]) = W_u emb(z_i) + W_v emb(z_j) + b depends on the elements only, so
 // for frozen weights it is two [max_z, F] tables built once per model (the analogue of the reference's Zij table,
 // TensorEmbedding.setup_for_inference, tensornet.py:509-533) -- 64 KB, L1-resident.
-__device__ __forceinline__ void unit_vec(const float* __restrict__ vec, const float* __restrict__ dist, int k, float* r, float* inv) {
-  const float d = __ldg(dist + k);
-  *inv = d == 0.f ? 1.f : 1.f / d;
-  r[0] = __ldg(vec + 3 * k) * *inv; r[1] = __ldg(vec + 3 * k + 1) * *inv; r[2] = __ldg(vec + 3 * k + 2) * *inv;
+// Per-edge scalars are prepared LANE-PARALLEL for 32 edges at a time (pair id, element row of the neighbour, unit vector,
+// cutoff and its derivative -- one sincos per EDGE instead of one per lane) and broadcast with shuffles, so no dependent
+// index -> gather chain sits on the per-edge critical path; the radial rows of the next edge are prefetched into registers.
+struct EdgeMeta { int p; int zj; float r0, r1, r2, cut, dcut, inv; };
+__device__ __forceinline__ EdgeMeta load_edge_meta(const float* __restrict__ vec, const float* __restrict__ dist,
+                                                   const int* __restrict__ pid, const int* __restrict__ nbr_j,
+                                                   const int64_t* __restrict__ zidx, int k, bool valid, float lo, float hi) {
+  EdgeMeta m{0, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
+  if (valid) {
+    m.p = pid[k];
+    const int j = nbr_j[k];
+    m.zj = zidx ? (int)zidx[j] : j;
+    const float d = __ldg(dist + k);
+    m.inv = d == 0.f ? 1.f : 1.f / d;     // self loop: vec = 0 -> rhat = 0 (tensornet.py:363-366)
+    m.r0 = __ldg(vec + 3 * (size_t)k) * m.inv; m.r1 = __ldg(vec + 3 * (size_t)k + 1) * m.inv; m.r2 = __ldg(vec + 3 * (size_t)k + 2) * m.inv;
+    tn::cosine_cutoff(d, lo, hi, &m.cut, &m.dcut);
+  }
+  return m;
 }
+__device__ __forceinline__ float4 splat4(float x) { return make_float4(x, x, x, x); }
+
 __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict__ vec, const float* __restrict__ dist,
                                                         const float* __restrict__ dp, const int* __restrict__ pid,
                                                         const int* __restrict__ nbr_j, const int* __restrict__ indptr,
@@ -453,23 +469,32 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict_
 #pragma unroll
       for (int c = 0; c < 9; ++c) acc[c] = zero4();
       const float4 ub = ldg4(U + ub_row * F + h);
-      for (int k = k0; k < k1; ++k) {
-        const long long j = nbr_j[k], p = pid[k];
-        float r[3], inv;
-        unit_vec(vec, dist, k, r, &inv);
-        float cut, dcut;
-        tn::cosine_cutoff(__ldg(dist + k), lo, hi, &cut, &dcut);
-        float4 zc = add4(ub, ldg4(V + (zidx ? zidx[j] : j) * F + h));
-        zc = make_float4(zc.x * cut, zc.y * cut, zc.z * cut, zc.w * cut);
-        const float* de = dp + p * 3 * (long long)F + h;
-        const float4 w1 = mul4(zc, ldg4(de)), w2 = mul4(zc, ldg4(de + F)), w3 = mul4(zc, ldg4(de + 2 * F));
-        float a[3], s[5];
-        tn::skew_compact(r, a); tn::sym_basis(r, s);
-        acc[0] = add4(acc[0], w1);
+      for (int e0 = k0; e0 < k1; e0 += 32) {
+        const EdgeMeta me = load_edge_meta(vec, dist, pid, nbr_j, zidx, e0 + lane, e0 + lane < k1, lo, hi);
+        const int m = min(32, k1 - e0);
+        const float* de = dp + (long long)__shfl_sync(0xffffffffu, me.p, 0) * 3 * F + h;
+        float4 q1 = ldg4(de), q2 = ldg4(de + F), q3 = ldg4(de + 2 * F);
+        for (int i = 0; i < m; ++i) {
+          const int zj = __shfl_sync(0xffffffffu, me.zj, i);
+          const float cut = __shfl_sync(0xffffffffu, me.cut, i);
+          const float r[3] = {__shfl_sync(0xffffffffu, me.r0, i), __shfl_sync(0xffffffffu, me.r1, i), __shfl_sync(0xffffffffu, me.r2, i)};
+          const int pn = __shfl_sync(0xffffffffu, me.p, (i + 1) & 31);
+          const float4 c1 = q1, c2 = q2, c3 = q3;
+          if (i + 1 < m) {   // prefetch the next edge's radial row
+            const float* dn = dp + (long long)pn * 3 * F + h;
+            q1 = ldg4(dn); q2 = ldg4(dn + F); q3 = ldg4(dn + 2 * F);
+          }
+          float4 zc = add4(ub, ldg4(V + (long long)zj * F + h));
+          zc = mul4(zc, splat4(cut));
+          const float4 w1 = mul4(zc, c1), w2 = mul4(zc, c2), w3 = mul4(zc, c3);
+          float a[3], sb[5];
+          tn::skew_compact(r, a); tn::sym_basis(r, sb);
+          acc[0] = add4(acc[0], w1);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) acc[1 + c] = fma4(make_float4(a[c], a[c], a[c], a[c]), w2, acc[1 + c]);
+          for (int c = 0; c < 3; ++c) acc[1 + c] = fma4(splat4(a[c]), w2, acc[1 + c]);
 #pragma unroll
-        for (int c = 0; c < 5; ++c) acc[4 + c] = fma4(make_float4(s[c], s[c], s[c], s[c]), w3, acc[4 + c]);
+          for (int c = 0; c < 5; ++c) acc[4 + c] = fma4(splat4(sb[c]), w3, acc[4 + c]);
+        }
       }
       st9(out, b, F, h, acc);
     }
@@ -478,7 +503,7 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict_
 // backward wrt geometry only (U, V, weights are inference constants): g_dist[e] (through the cutoff, the radial projections
 // and the normalisation of rhat) and g_vec[e,3] = g_rhat / |vec|
 template <bool ONE_CHUNK>
-__global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict__ vec, const float* __restrict__ dist,
+__global__ void __launch_bounds__(256, 2) embed_bwd_kernel(const float* __restrict__ vec, const float* __restrict__ dist,
                                                         const float* __restrict__ dp, const float* __restrict__ dpp,
                                                         const int* __restrict__ pid, const int* __restrict__ nbr_j,
                                                         const int* __restrict__ indptr, const float* __restrict__ U,
@@ -492,55 +517,81 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict_
     // ONE_CHUNK (F <= 128): the row's own dOut and U are loaded once, not once per edge
     float4 d[9], ub = zero4();
     if (ONE_CHUNK && lane * 4 < F) { ld9(dout, b, F, lane * 4, d); ub = ldg4(U + ub_row * F + lane * 4); }
-    for (int k = k0; k < k1; ++k) {
-      const long long j = nbr_j[k], p = pid[k];
-      float r[3], inv;
-      unit_vec(vec, dist, k, r, &inv);
-      float cut, dcut;
-      tn::cosine_cutoff(__ldg(dist + k), lo, hi, &cut, &dcut);
-      float a[3], s[5];
-      tn::skew_compact(r, a); tn::sym_basis(r, s);
-      float gr[3] = {0.f, 0.f, 0.f};
-      float gd = 0.f;
-      const long long vrow = zidx ? zidx[j] : j;
-      for (int h = lane * 4; h < F; h += 128) {
-        if (!ONE_CHUNK) { ld9(dout, b, F, h, d); ub = ldg4(U + ub_row * F + h); }
-        const float4 z = add4(ub, ldg4(V + vrow * F + h));
-        const float* de = dp + p * 3 * (long long)F + h;
-        const float* dde = dpp + p * 3 * (long long)F + h;
-        const float4 q1 = ldg4(de), q2 = ldg4(de + F), q3 = ldg4(de + 2 * F);
-        // dL/dw_k
-        float4 g2 = zero4(), g3 = zero4();
+    for (int e0 = k0; e0 < k1; e0 += 32) {
+      const EdgeMeta me = load_edge_meta(vec, dist, pid, nbr_j, zidx, e0 + lane, e0 + lane < k1, lo, hi);
+      const int m = min(32, k1 - e0);
+      float keep_gd = 0.f, keep_g0 = 0.f, keep_g1 = 0.f, keep_g2 = 0.f;   // lane i keeps the results of edge e0 + i
+      float4 q1 = zero4(), q2 = zero4(), q3 = zero4(), t1 = zero4(), t2 = zero4(), t3 = zero4();
+      if (ONE_CHUNK && lane * 4 < F) {
+        const long long p0 = __shfl_sync(0xffffffffu, me.p, 0);
+        const float* de = dp + p0 * 3 * F + lane * 4; const float* dde = dpp + p0 * 3 * F + lane * 4;
+        q1 = ldg4(de); q2 = ldg4(de + F); q3 = ldg4(de + 2 * F); t1 = ldg4(dde); t2 = ldg4(dde + F); t3 = ldg4(dde + 2 * F);
+      } else if (ONE_CHUNK) {
+        (void)__shfl_sync(0xffffffffu, me.p, 0);
+      }
+      for (int i = 0; i < m; ++i) {
+        const int zj = __shfl_sync(0xffffffffu, me.zj, i);
+        const float cut = __shfl_sync(0xffffffffu, me.cut, i), dcut = __shfl_sync(0xffffffffu, me.dcut, i);
+        const float inv = __shfl_sync(0xffffffffu, me.inv, i);
+        const float r[3] = {__shfl_sync(0xffffffffu, me.r0, i), __shfl_sync(0xffffffffu, me.r1, i), __shfl_sync(0xffffffffu, me.r2, i)};
+        const long long pc = __shfl_sync(0xffffffffu, me.p, i);
+        const long long pn = __shfl_sync(0xffffffffu, me.p, (i + 1) & 31);
+        float a[3], sb[5];
+        tn::skew_compact(r, a); tn::sym_basis(r, sb);
+        float gr[3] = {0.f, 0.f, 0.f};
+        float gd = 0.f;
+        for (int h = lane * 4; h < F; h += 128) {
+          float4 c1, c2, c3, u1, u2, u3;
+          if (ONE_CHUNK) {
+            c1 = q1; c2 = q2; c3 = q3; u1 = t1; u2 = t2; u3 = t3;
+            if (i + 1 < m) {   // prefetch the next edge's radial rows (value and d/dr)
+              const float* de = dp + pn * 3 * F + h; const float* dde = dpp + pn * 3 * F + h;
+              q1 = ldg4(de); q2 = ldg4(de + F); q3 = ldg4(de + 2 * F); t1 = ldg4(dde); t2 = ldg4(dde + F); t3 = ldg4(dde + 2 * F);
+            }
+          } else {
+            ld9(dout, b, F, h, d); ub = ldg4(U + ub_row * F + h);
+            const float* de = dp + pc * 3 * F + h; const float* dde = dpp + pc * 3 * F + h;
+            c1 = ldg4(de); c2 = ldg4(de + F); c3 = ldg4(de + 2 * F); u1 = ldg4(dde); u2 = ldg4(dde + F); u3 = ldg4(dde + 2 * F);
+          }
+          const float4 z = add4(ub, ldg4(V + (long long)zj * F + h));
+          // dL/dw_k
+          float4 g2 = zero4(), g3 = zero4();
 #pragma unroll
-        for (int c = 0; c < 3; ++c) g2 = fma4(make_float4(a[c], a[c], a[c], a[c]), d[1 + c], g2);
+          for (int c = 0; c < 3; ++c) g2 = fma4(splat4(a[c]), d[1 + c], g2);
 #pragma unroll
-        for (int c = 0; c < 5; ++c) g3 = fma4(make_float4(s[c], s[c], s[c], s[c]), d[4 + c], g3);
-        // w_k = cut * z * q_k  ->  dw_k/dr = dcut * z * q_k + cut * z * q'_k
-        const float4 t1 = fma4(make_float4(dcut, dcut, dcut, dcut), q1, mul4(make_float4(cut, cut, cut, cut), ldg4(dde)));
-        const float4 t2 = fma4(make_float4(dcut, dcut, dcut, dcut), q2, mul4(make_float4(cut, cut, cut, cut), ldg4(dde + F)));
-        const float4 t3 = fma4(make_float4(dcut, dcut, dcut, dcut), q3, mul4(make_float4(cut, cut, cut, cut), ldg4(dde + 2 * F)));
-        gd += dot4(mul4(z, t1), d[0]) + dot4(mul4(z, t2), g2) + dot4(mul4(z, t3), g3);
-        // d/d rhat through skew and the symmetric-traceless basis
-        const float4 w2 = mul4(make_float4(cut, cut, cut, cut), mul4(z, q2));
-        const float4 w3 = mul4(make_float4(cut, cut, cut, cut), mul4(z, q3));
-        gr[0] -= dot4(w2, d[3]); gr[1] += dot4(w2, d[2]); gr[2] -= dot4(w2, d[1]);
-        const float w3v[4] = {w3.x, w3.y, w3.z, w3.w};
-        const float dSv[5][4] = {{d[4].x, d[4].y, d[4].z, d[4].w}, {d[5].x, d[5].y, d[5].z, d[5].w},
-                                 {d[6].x, d[6].y, d[6].z, d[6].w}, {d[7].x, d[7].y, d[7].z, d[7].w},
-                                 {d[8].x, d[8].y, d[8].z, d[8].w}};
+          for (int c = 0; c < 5; ++c) g3 = fma4(splat4(sb[c]), d[4 + c], g3);
+          // w_k = cut * z * q_k  ->  dw_k/dr = dcut * z * q_k + cut * z * q'_k
+          const float4 s1 = fma4(splat4(dcut), c1, mul4(splat4(cut), u1));
+          const float4 s2 = fma4(splat4(dcut), c2, mul4(splat4(cut), u2));
+          const float4 s3 = fma4(splat4(dcut), c3, mul4(splat4(cut), u3));
+          gd += dot4(mul4(z, s1), d[0]) + dot4(mul4(z, s2), g2) + dot4(mul4(z, s3), g3);
+          // d/d rhat through skew and the symmetric-traceless basis
+          const float4 w2 = mul4(splat4(cut), mul4(z, c2));
+          const float4 w3 = mul4(splat4(cut), mul4(z, c3));
+          gr[0] -= dot4(w2, d[3]); gr[1] += dot4(w2, d[2]); gr[2] -= dot4(w2, d[1]);
+          const float w3v[4] = {w3.x, w3.y, w3.z, w3.w};
+          const float dSv[5][4] = {{d[4].x, d[4].y, d[4].z, d[4].w}, {d[5].x, d[5].y, d[5].z, d[5].w},
+                                   {d[6].x, d[6].y, d[6].z, d[6].w}, {d[7].x, d[7].y, d[7].z, d[7].w},
+                                   {d[8].x, d[8].y, d[8].z, d[8].w}};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float dS[5] = {dSv[0][q], dSv[1][q], dSv[2][q], dSv[3][q], dSv[4][q]};
-          tn::sym_basis_bwd_acc(r, dS, w3v[q], gr);
+          for (int q = 0; q < 4; ++q) {
+            const float dS[5] = {dSv[0][q], dSv[1][q], dSv[2][q], dSv[3][q], dSv[4][q]};
+            tn::sym_basis_bwd_acc(r, dS, w3v[q], gr);
+          }
+        }
+        gd = warp_sum(gd); gr[0] = warp_sum(gr[0]); gr[1] = warp_sum(gr[1]); gr[2] = warp_sum(gr[2]);
+        if (lane == i) {
+          // rhat = vec * inv with inv = 1/dist (1 for the self loop, whose vec is 0): d/dvec = g_rhat * inv,
+          // d/ddist = -(g_rhat . rhat) * inv (0 for the self loop: the masked denominator is a constant there)
+          const bool self = (r[0] == 0.f && r[1] == 0.f && r[2] == 0.f) && inv == 1.f;
+          keep_gd = gd - (self ? 0.f : (gr[0] * r[0] + gr[1] * r[1] + gr[2] * r[2]) * inv);
+          keep_g0 = gr[0] * inv; keep_g1 = gr[1] * inv; keep_g2 = gr[2] * inv;
         }
       }
-      gd = warp_sum(gd); gr[0] = warp_sum(gr[0]); gr[1] = warp_sum(gr[1]); gr[2] = warp_sum(gr[2]);
-      if (lane == 0) {
-        // rhat = vec * inv with inv = 1/dist (1 for the self loop, whose vec is 0): d/dvec = g_rhat * inv,
-        // d/ddist = -(g_rhat . rhat) * inv (0 for the self loop: the masked denominator is a constant there)
-        const bool self = __ldg(dist + k) == 0.f;
-        g_dist[k] = gd - (self ? 0.f : (gr[0] * r[0] + gr[1] * r[1] + gr[2] * r[2]) * inv);
-        g_vec[3 * k] = gr[0] * inv; g_vec[3 * k + 1] = gr[1] * inv; g_vec[3 * k + 2] = gr[2] * inv;
+      if (lane < m) {
+        const size_t k = (size_t)e0 + lane;
+        g_dist[k] = keep_gd;
+        g_vec[3 * k] = keep_g0; g_vec[3 * k + 1] = keep_g1; g_vec[3 * k + 2] = keep_g2;
       }
     }
   }
