@@ -263,6 +263,14 @@ int tmd_et_msg_bwd(const float* q, const float* kk, const float* v, const float*
                    int F, int head_dim, float* gq, float* gk, float* gv_out, float* gvec, float* g_dist, float* g_rhat,
                    void* stream);
 
+/* ---- a13: ET NeighborEmbedding (models/utils.py:45-117): out[i] = sum over the neighbours j != i of C(r)(W_d rbf(r) + b) * T[z_j].
+ * wp / wpp [P_u,F]: the radial factor per unordered pair and its d/dr (tmd_pair_chain_tc / tmd_radial_table); table [max_z,F] the
+ * neighbour embedding; z int64 [n].  Backward w.r.t. geometry: g_dist[E] (self-loop slots get 0). */
+int tmd_nbr_embed_fwd(const float* wp, const float* table, const int64_t* z, const int* pid, const int* nbr_j, const int* indptr,
+                      int n, int F, float* out, void* stream);
+int tmd_nbr_embed_bwd(const float* wpp, const float* table, const int64_t* z, const int* pid, const int* nbr_j, const int* indptr,
+                      int n, int F, const float* gout, float* g_dist, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -545,7 +545,7 @@ def gated_equivariant_block(sd, key, x, v, out_channels, act, scalar_activation)
 # --------------------------------------------------------------------------------------
 def energy_and_forces(sd: StateDict, hp: dict, z: Tensor, pos: Tensor, batch: Optional[Tensor] = None,
                       box: Optional[Tensor] = None, q: Optional[Tensor] = None, derivative: bool = True,
-                      edge_chunks: int = 0, graph=None):
+                      edge_chunks: int = 0, graph=None, create_graph: bool = False):
     """models/model.py:530-631 (TorchMD_Net.forward): representation -> output head
     (output_modules.py:79-163) -> *std -> (Atomref prior, priors/atomref.py) -> scatter-sum
     per molecule (output_modules.py:43-73, utils.py:671-701) -> +mean -> F = -dE/dpos."""
@@ -581,6 +581,9 @@ def energy_and_forces(sd: StateDict, hp: dict, z: Tensor, pos: Tensor, batch: Op
     y = y + sd["mean"]
     if not derivative:
         return y.detach(), None
+    if create_graph:   # training with a force loss (models/model.py:618-628: create_graph=self.training): outputs stay differentiable
+        (dy,) = torch.autograd.grad([y], [pos], grad_outputs=[torch.ones_like(y)], create_graph=True)
+        return y, -dy
     (dy,) = torch.autograd.grad([y], [pos], grad_outputs=[torch.ones_like(y)])
     return y.detach(), -dy
 

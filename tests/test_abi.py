@@ -58,7 +58,7 @@ def test_op_registry_names():
             "nvtnet::convert_to_sparse_primitive"]
     for op in ["compose_tensor", "decompose_tensor", "tensor_matmul_o3_3x3", "tensor_matmul_so3_3x3", "tensor_norm3",
                "message_passing", "radial_message_passing"]:
-        want += [f"tensornet::{op}_fwd_primitive", f"tensornet::{op}_bwd_primitive"]
+        want += [f"tensornet::{op}_fwd_primitive", f"tensornet::{op}_bwd_primitive", f"tensornet::{op}_bwd_bwd_primitive"]   # all 25
     assert sorted(want) == sorted(registry.REGISTERED)
     with pytest.raises((RuntimeError, NotImplementedError)):
         torch.ops.tensornet.tensor_norm3_fwd_primitive(torch.rand(2, 3, 3, 8))  # no CPU kernel registered

@@ -302,3 +302,25 @@ def test_ase_calculator_caffeine_known_answer(with_ase_stub, compile_, monkeypat
     finally:
         monkeypatch.undo()
         importlib.reload(C)
+
+
+def test_et_static_shapes_cuda_graph():
+    """the ET frame without host reads (static_shapes=True on the fused path) == the dynamic-shape frame, and
+    replays from a CUDA graph with changing positions"""
+    from torchmdnet_b200.calculators import CUDAGraphForceField
+    z, pos, batch, _ = systems.molecule_batch(n_mol=6, seed=3)
+    outs = []
+    for static in (False, True):
+        hp = systems.et_hparams(num_layers=2, F=64, R=32, H=4, cutoff=5.0, max_nb=64, static_shapes=static)
+        m = freeze(seeded_model(hp, 9).eval().to(dev))
+        assert m.representation_model._fused_path_ok()
+        outs.append(m(z.to(dev), pos.to(dev), batch.to(dev), num_systems=6))
+    assert rel(outs[1][0], outs[0][0].double().cpu()) < 1e-6 and relF(outs[1][1], outs[0][1].double().cpu()) < 1e-5
+    ff = CUDAGraphForceField(m, z.to(dev), batch.to(dev), num_systems=6)
+    e, f = ff(pos.to(dev))
+    assert rel(e.clone(), outs[0][0].double().cpu()) < 1e-6 and relF(f.clone(), outs[0][1].double().cpu()) < 1e-5
+    pos2 = pos + 0.03 * torch.randn_like(pos)
+    e2, f2 = ff(pos2.to(dev))
+    e2, f2 = e2.clone(), f2.clone()
+    y, g = m(z.to(dev), pos2.to(dev), batch.to(dev), num_systems=6)
+    assert rel(e2, y.double().cpu()) < 1e-6 and relF(f2, g.double().cpu()) < 1e-5

@@ -63,6 +63,8 @@ SIGNATURES = {
     "tmd_mp_pair_bwd": ([P] * 11 + [I, I] + [P] * 4 + [P], 1),
     "tmd_et_msg_fwd": ([P] * 10 + [D, D, I, I, I, I, P, P, P], 1),
     "tmd_et_msg_bwd": ([P] * 13 + [D, D, I, I, I, I] + [P] * 6 + [P], 2),
+    "tmd_nbr_embed_fwd": ([P] * 6 + [I, I, P, P], 1),
+    "tmd_nbr_embed_bwd": ([P] * 6 + [I, I, P, P, P], 1),
     "tmd_mp_edge_bwd": ([P] * 11 + [I, I] + [P] * 4 + [P], 1),
     "tmd_mp_group_size": ([], 0),
     "tmd_mp_plan": ([P, P, P, I, I, P, P, P, P, P, P, P, P, P, P], 1),

@@ -464,22 +464,26 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict_
   for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < n; b += gridDim.x * wpb) {
     const int k0 = indptr[b], k1 = indptr[b + 1];
     const long long ub_row = zidx ? zidx[b] : b;
-    for (int h = lane * 4; h < F; h += 128) {
+    for (int hh = 0; hh < F; hh += 128) {      // every lane runs the loop (the shuffles below need the whole warp); lanes past F idle
+      const int h = hh + lane * 4;
+      const bool on = h < F;
       float4 acc[9];
 #pragma unroll
       for (int c = 0; c < 9; ++c) acc[c] = zero4();
-      const float4 ub = ldg4(U + ub_row * F + h);
+      const float4 ub = on ? ldg4(U + ub_row * F + h) : zero4();
       for (int e0 = k0; e0 < k1; e0 += 32) {
         const EdgeMeta me = load_edge_meta(vec, dist, pid, nbr_j, zidx, e0 + lane, e0 + lane < k1, lo, hi);
         const int m = min(32, k1 - e0);
-        const float* de = dp + (long long)__shfl_sync(0xffffffffu, me.p, 0) * 3 * F + h;
-        float4 q1 = ldg4(de), q2 = ldg4(de + F), q3 = ldg4(de + 2 * F);
+        const long long p0 = __shfl_sync(0xffffffffu, me.p, 0);
+        float4 q1 = zero4(), q2 = zero4(), q3 = zero4();
+        if (on) { const float* de = dp + p0 * 3 * F + h; q1 = ldg4(de); q2 = ldg4(de + F); q3 = ldg4(de + 2 * F); }
         for (int i = 0; i < m; ++i) {
           const int zj = __shfl_sync(0xffffffffu, me.zj, i);
           const float cut = __shfl_sync(0xffffffffu, me.cut, i);
           const float r[3] = {__shfl_sync(0xffffffffu, me.r0, i), __shfl_sync(0xffffffffu, me.r1, i), __shfl_sync(0xffffffffu, me.r2, i)};
           const int pn = __shfl_sync(0xffffffffu, me.p, (i + 1) & 31);
           const float4 c1 = q1, c2 = q2, c3 = q3;
+          if (!on) continue;
           if (i + 1 < m) {   // prefetch the next edge's radial row
             const float* dn = dp + (long long)pn * 3 * F + h;
             q1 = ldg4(dn); q2 = ldg4(dn + F); q3 = ldg4(dn + 2 * F);
@@ -496,7 +500,7 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict_
           for (int c = 0; c < 5; ++c) acc[4 + c] = fma4(splat4(sb[c]), w3, acc[4 + c]);
         }
       }
-      st9(out, b, F, h, acc);
+      if (on) st9(out, b, F, h, acc);
     }
   }
 }
@@ -522,12 +526,10 @@ __global__ void __launch_bounds__(256, 2) embed_bwd_kernel(const float* __restri
       const int m = min(32, k1 - e0);
       float keep_gd = 0.f, keep_g0 = 0.f, keep_g1 = 0.f, keep_g2 = 0.f;   // lane i keeps the results of edge e0 + i
       float4 q1 = zero4(), q2 = zero4(), q3 = zero4(), t1 = zero4(), t2 = zero4(), t3 = zero4();
+      const long long p0 = __shfl_sync(0xffffffffu, me.p, 0);
       if (ONE_CHUNK && lane * 4 < F) {
-        const long long p0 = __shfl_sync(0xffffffffu, me.p, 0);
         const float* de = dp + p0 * 3 * F + lane * 4; const float* dde = dpp + p0 * 3 * F + lane * 4;
         q1 = ldg4(de); q2 = ldg4(de + F); q3 = ldg4(de + 2 * F); t1 = ldg4(dde); t2 = ldg4(dde + F); t3 = ldg4(dde + 2 * F);
-      } else if (ONE_CHUNK) {
-        (void)__shfl_sync(0xffffffffu, me.p, 0);
       }
       for (int i = 0; i < m; ++i) {
         const int zj = __shfl_sync(0xffffffffu, me.zj, i);

@@ -233,6 +233,62 @@ inline bool et_dims_ok(int F, int hd) {
   return (lph & (lph - 1)) == 0 && lph <= 32;
 }
 
+// ------------------------------------------------------------------------------------------------ a13: NeighborEmbedding
+// x_nb[i] = sum_{e = (i, j), j != i} W_p(e) * T[z_j]        (reference models/utils.py:83-117: boolean-mask removal of the self
+// loops, Linear(rbf) * C(r) per edge, embedding gather, index_add).  W_p = C(r) (W_d rbf(r) + b) is a function of r only: it
+// comes per unordered pair from the radial chain (value + d/dr, tables for frozen weights); T is the neighbour embedding table
+// [max_z, F] (64 KB, L1-resident).  One warp per atom, lanes over channels; backward w.r.t. geometry: g_dist[k] = <g_i, W'_p T[z_j]>.
+__global__ void __launch_bounds__(256) nbr_embed_fwd_kernel(const float* __restrict__ wp, const float* __restrict__ table,
+                                                            const int64_t* __restrict__ z, const int* __restrict__ pid,
+                                                            const int* __restrict__ nbr_j, const int* __restrict__ indptr, int n, int F,
+                                                            float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+    const int k0 = indptr[i], k1 = indptr[i + 1];
+    for (int f = lane * 4; f < F; f += 128) {
+      float4 acc = f4z();
+      for (int e0 = k0; e0 < k1; e0 += 32) {
+        const int k = e0 + lane;
+        int j = -1, p = 0, zj = 0;
+        if (k < k1) { j = nbr_j[k]; p = pid[k]; zj = (int)z[j]; }
+        const int m = min(32, k1 - e0);
+        for (int t = 0; t < m; ++t) {
+          const int jj = __shfl_sync(0xffffffffu, j, t), pp = __shfl_sync(0xffffffffu, p, t), zz = __shfl_sync(0xffffffffu, zj, t);
+          if (jj == i) continue;   // warp-uniform
+          acc = f4fma(ldg4(wp + (long long)pp * F + f), ldg4(table + (long long)zz * F + f), acc);
+        }
+      }
+      st4(out + (long long)i * F + f, acc);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) nbr_embed_bwd_kernel(const float* __restrict__ wpp, const float* __restrict__ table,
+                                                            const int64_t* __restrict__ z, const int* __restrict__ pid,
+                                                            const int* __restrict__ nbr_j, const int* __restrict__ indptr, int n, int F,
+                                                            const float* __restrict__ gout, float* __restrict__ g_dist) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+    const int k0 = indptr[i], k1 = indptr[i + 1];
+    for (int e0 = k0; e0 < k1; e0 += 32) {
+      const int k = e0 + lane;
+      int j = -1, p = 0, zj = 0;
+      if (k < k1) { j = nbr_j[k]; p = pid[k]; zj = (int)z[j]; }
+      const int m = min(32, k1 - e0);
+      float keep = 0.f;
+      for (int t = 0; t < m; ++t) {
+        const int jj = __shfl_sync(0xffffffffu, j, t), pp = __shfl_sync(0xffffffffu, p, t), zz = __shfl_sync(0xffffffffu, zj, t);
+        float s = 0.f;
+        if (jj != i)
+          for (int f = lane * 4; f < F; f += 128)
+            s += f4dot(ldg4(gout + (long long)i * F + f), f4mul(ldg4(wpp + (long long)pp * F + f), ldg4(table + (long long)zz * F + f)));
+        s = warp_sum(s);
+        if (lane == t) keep = s;
+      }
+      if (lane < m) g_dist[e0 + lane] = keep;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -269,6 +325,25 @@ int tmd_et_msg_bwd(const float* q, const float* kk, const float* v, const float*
   et_msg_bwd_source_kernel<<<grid, 256, 0, st>>>(q, kk, v, vec, dkv, gx, gv, pid, nbr_j, indptr, dist, rhat, (float)lo,
                                                  (float)hi, vector_cutoff, n, F, head_dim, gk, gv_out, gvec);
   return tmd_check_launch("et_msg_bwd");
+}
+
+// a13 (see the kernels): out [n,F] = neighbour embedding sum; wp / wpp [P_u,F] = C(r)(W_d rbf + b) per unordered pair and its d/dr;
+// table [max_z,F] = NeighborEmbedding.embedding.weight; z int64 atomic numbers.  F % 4 == 0.
+int tmd_nbr_embed_fwd(const float* wp, const float* table, const int64_t* z, const int* pid, const int* nbr_j, const int* indptr,
+                      int n, int F, float* out, void* stream) {
+  TMD_REQUIRE(F > 0 && F % 4 == 0, "nbr_embed_fwd: F must be a positive multiple of 4");
+  TMD_REQUIRE(wp && table && z && pid && nbr_j && indptr && out, "nbr_embed_fwd: null pointer");
+  if (n == 0) return TMD_OK;
+  nbr_embed_fwd_kernel<<<tmd_blocks_for((long long)n * 32, 256), 256, 0, (cudaStream_t)stream>>>(wp, table, z, pid, nbr_j, indptr, n, F, out);
+  return tmd_check_launch("nbr_embed_fwd");
+}
+int tmd_nbr_embed_bwd(const float* wpp, const float* table, const int64_t* z, const int* pid, const int* nbr_j, const int* indptr,
+                      int n, int F, const float* gout, float* g_dist, void* stream) {
+  TMD_REQUIRE(F > 0 && F % 4 == 0, "nbr_embed_bwd: F must be a positive multiple of 4");
+  TMD_REQUIRE(wpp && table && z && pid && nbr_j && indptr && gout && g_dist, "nbr_embed_bwd: null pointer");
+  if (n == 0) return TMD_OK;
+  nbr_embed_bwd_kernel<<<tmd_blocks_for((long long)n * 32, 256), 256, 0, (cudaStream_t)stream>>>(wpp, table, z, pid, nbr_j, indptr, n, F, gout, g_dist);
+  return tmd_check_launch("nbr_embed_bwd");
 }
 
 }  // extern "C"

@@ -534,6 +534,38 @@ def et_message(q, kk, v, vec, dist, rhat, pair_r, chain, rbf_mod, lo, hi, vector
     return _ETMessage.apply(q, kk, v, vec, dist, rhat, pair_r, chain, rbf_mod, lo, hi, vector_cutoff, head_dim, g, pidx, rbf_op)
 
 
+class _NbrEmbed(torch.autograd.Function):
+    """ET NeighborEmbedding sum (row a13): agg[i] = sum_{j != i} C(r)(W_d rbf(r) + b) * T[z_j], radial factor per unordered pair."""
+
+    @staticmethod
+    def forward(ctx, dist, pair_r, chain, rbf_mod, lo, hi, table, z, g, pidx, rbf_op):
+        need = dist.requires_grad
+        wp, wpp = run_chain(chain, pair_r.detach(), pidx.num_unique, rbf_mod, lo, hi, need, rbf_op)
+        table, z = table.detach().contiguous(), z.contiguous()
+        N, F = g.indptr.shape[0] - 1, table.shape[-1]
+        out = torch.empty(N, F, device=table.device, dtype=torch.float32)
+        _lib.call("tmd_nbr_embed_fwd", p(wp), p(table), p(z), p(pidx.pid), p(g.nbr_j), p(g.indptr), N, F, p(out), device=table.device)
+        ctx.save_for_backward(wpp if wpp is not None else wp, table, z, pidx.pid, g.nbr_j, g.indptr)
+        ctx.has_t, ctx.E, ctx.N = wpp is not None, dist.shape[0], N
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        wpp, table, z, pid, nbr_j, indptr = ctx.saved_tensors
+        if not ctx.has_t:
+            return (None,) * 11
+        gout = gout.contiguous()
+        g_dist = torch.zeros(ctx.E, device=gout.device, dtype=torch.float32)
+        _lib.call("tmd_nbr_embed_bwd", p(wpp), p(table), p(z), p(pid), p(nbr_j), p(indptr), ctx.N, table.shape[-1], p(gout), p(g_dist),
+                  device=gout.device)
+        return (g_dist,) + (None,) * 10
+
+
+def neighbor_embedding_sum(dist, pair_r, chain, rbf_mod, lo, hi, table, z, g, pidx, rbf_op=None):
+    return _NbrEmbed.apply(dist, pair_r, chain, rbf_mod, lo, hi, table, z, g, pidx, rbf_op)
+
+
 # ------------------------------------------------------------------------------------------ node linears on tensor cores
 def _tf32_split(w: Tensor):
     b = w.contiguous().view(torch.int32)

@@ -4,8 +4,10 @@ The reference registers 25 custom ops in the namespaces `torchmdnet::`, `nvtnet:
 (torchmdnet/extensions/warp_ops/*.py) so that TorchScript (`extensions/ops.py:66-92`),
 `torch.compile(fullgraph=True)` (`calculators.py:297-303`) and `torch.export` can resolve them.  Importing this module
 registers the forward and backward primitives under the SAME names and signatures (`mutates_args=()`, CUDA only --
-there is no CPU path), with `register_fake` shape functions and `register_autograd` chaining fwd -> bwd.  The seven
-`*_bwd_bwd_primitive` ops (double backward, training with a force loss) are not provided in this round.
+there is no CPU path), with `register_fake` shape functions and `register_autograd` chaining fwd -> bwd, plus the seven
+`*_bwd_bwd_primitive` ops (double backward: training with a force loss) with the reference's argument and result order; they
+evaluate the pull-back of the differentiable backward of tensornet_ops.py (kernel re-entry for the (bi)linear ops, torch
+restatements for the quadratic ones).
 
 Do not import it next to the reference's own `torchmdnet.extensions.warp_ops` (same op names).
 """
@@ -261,3 +263,100 @@ def radial_bwd(grad_output_I: Tensor, grad_output_A: Tensor, grad_output_S: Tens
 _pair("tensornet::radial_message_passing_fwd_primitive", "tensornet::radial_message_passing_bwd_primitive", None, None,
       lambda r, w, rd, rp: [w.new_empty(rp.shape[0] - 1, k, w.shape[-1]) for k in (1, 3, 5)],
       lambda gi, ga, gs, r, w, rd, rp: [torch.empty_like(r), torch.empty_like(w)], 4, False)
+
+
+# ------------------------------------------------------------------------------------------ double backward primitives
+def _pullback(bwd_fn, grad_outs, inputs, cotangents):
+    """the reference's `*_bwd_bwd` contract: given the cotangents of the BACKWARD op's results, return (d/d grad_outs, d/d inputs).
+    `bwd_fn(grad_outs, inputs)` evaluates the backward op with differentiable operations (tensornet_ops.py)."""
+    with torch.enable_grad():
+        go = [t.detach().requires_grad_(True) for t in grad_outs]
+        xi = [t.detach().requires_grad_(True) for t in inputs]
+        res = list(bwd_fn(go, xi))
+        keep = [(r, c) for r, c in zip(res, cotangents) if r is not None and r.requires_grad]
+        g = torch.autograd.grad([r for r, _ in keep], go + xi, [c for _, c in keep], allow_unused=True) if keep else [None] * (len(go) + len(xi))
+    g = [torch.zeros_like(t) if gi is None else gi for gi, t in zip(g, go + xi)]
+    return g[: len(go)], g[len(go):]
+
+
+@_op("tensornet::compose_tensor_bwd_bwd_primitive")
+def compose_bwd_bwd(grad_output: Tensor, grad_grad_x: Tensor, grad_grad_y: Tensor, grad_grad_z: Tensor, x: Tensor, y: Tensor,
+                    z: Tensor) -> List[Tensor]:
+    dgo, _ = _pullback(lambda go, xi: T._ComposeT.apply(go[0]), [grad_output], [], [grad_grad_x, grad_grad_y, grad_grad_z])
+    return [dgo[0], torch.zeros_like(x), torch.zeros_like(y), torch.zeros_like(z)]     # linear op: no dependence on (x, y, z)
+
+
+torch.library.register_fake("tensornet::compose_tensor_bwd_bwd_primitive")(
+    lambda go, gx, gy, gz, x, y, z: [torch.empty_like(go), torch.empty_like(x), torch.empty_like(y), torch.empty_like(z)])
+
+
+@_op("tensornet::decompose_tensor_bwd_bwd_primitive")
+def decompose_bwd_bwd(grad_output_i: Tensor, grad_output_a: Tensor, grad_output_s: Tensor, grad_grad_x: Tensor, x: Tensor) -> List[Tensor]:
+    dgo, _ = _pullback(lambda go, xi: [T._DecomposeT.apply(*go)], [grad_output_i, grad_output_a, grad_output_s], [], [grad_grad_x])
+    return [dgo[0], dgo[1], dgo[2], torch.zeros_like(x)]
+
+
+torch.library.register_fake("tensornet::decompose_tensor_bwd_bwd_primitive")(
+    lambda gi, ga, gs, ggx, x: [torch.empty_like(gi), torch.empty_like(ga), torch.empty_like(gs), torch.empty_like(x)])
+
+
+def _register_matmul_bwd_bwd(kind):
+    fn = T._MatMulO3 if kind == "o3" else T._MatMulSO3
+    name = f"tensornet::tensor_matmul_{kind}_3x3_bwd_bwd_primitive"
+
+    @_op(name)
+    def mm_bwd_bwd(grad_output: Tensor, grad_grad_x: Tensor, grad_grad_y: Tensor, x: Tensor, y: Tensor) -> List[Tensor]:
+        dgo, dx = _pullback(lambda go, xi: [fn.apply(go[0], xi[1].transpose(1, 2)), fn.apply(xi[0].transpose(1, 2), go[0])],
+                            [grad_output], [x, y], [grad_grad_x, grad_grad_y])
+        return [dgo[0], dx[0], dx[1]]
+
+    torch.library.register_fake(name)(lambda go, gx, gy, x, y: [torch.empty_like(go), torch.empty_like(x), torch.empty_like(y)])
+
+
+_register_matmul_bwd_bwd("o3")
+_register_matmul_bwd_bwd("so3")
+
+
+@_op("tensornet::tensor_norm3_bwd_bwd_primitive")
+def norm3_bwd_bwd(grad_grad_x: Tensor, x: Tensor, grad_output: Tensor) -> List[Tensor]:
+    def bwd(go, xi):
+        n = torch.cat(T._t_norm3(*T._Decompose.apply(xi[0])), -1)
+        return torch.autograd.grad([n], [xi[0]], [go[0]], create_graph=True)
+    dgo, dx = _pullback(bwd, [grad_output], [x], [grad_grad_x])
+    return [dgo[0], dx[0]]
+
+
+torch.library.register_fake("tensornet::tensor_norm3_bwd_bwd_primitive")(lambda ggx, x, go: [torch.empty_like(go), torch.empty_like(x)])
+
+
+@_op("tensornet::message_passing_bwd_bwd_primitive")
+def mp_bwd_bwd(grad_output_x: Tensor, grad_output_y: Tensor, grad_output_z: Tensor, grad_grad_x: Tensor, grad_grad_y: Tensor,
+               grad_grad_z: Tensor, grad_grad_edge_attr: Tensor, x: Tensor, y: Tensor, z: Tensor, edge_attr: Tensor, row_data: Tensor,
+               row_indices: Tensor, row_indptr: Tensor, col_data: Tensor, col_indices: Tensor, col_indptr: Tensor) -> List[Tensor]:
+    graph = (row_data, row_indices, row_indptr, col_data, col_indices, col_indptr)
+    dgo, dx = _pullback(lambda go, xi: T._MPBwd.apply(xi[0], xi[1], xi[2], xi[3], go[0], go[1], go[2], *graph),
+                        [grad_output_x, grad_output_y, grad_output_z], [x, y, z, edge_attr],
+                        [grad_grad_x, grad_grad_y, grad_grad_z, grad_grad_edge_attr])
+    return [dgo[0], dgo[1], dgo[2], dx[0], dx[1], dx[2], dx[3]]
+
+
+torch.library.register_fake("tensornet::message_passing_bwd_bwd_primitive")(
+    lambda gx, gy, gz, ggx, ggy, ggz, ggw, x, y, z, w, *a: [torch.empty_like(gx), torch.empty_like(gy), torch.empty_like(gz),
+                                                           torch.empty_like(x), torch.empty_like(y), torch.empty_like(z), torch.empty_like(w)])
+
+
+@_op("tensornet::radial_message_passing_bwd_bwd_primitive")
+def radial_bwd_bwd(grad_output_I: Tensor, grad_output_A: Tensor, grad_output_S: Tensor, grad_grad_edge_vec_norm: Tensor,
+                   grad_grad_edge_attr: Tensor, edge_vec_norm: Tensor, edge_attr: Tensor, row_data: Tensor,
+                   row_indptr: Tensor) -> List[Tensor]:
+    def bwd(go, xi):
+        out = T._t_radial_mp(xi[0], xi[1], row_data, row_indptr)
+        return torch.autograd.grad(list(out), [xi[0], xi[1]], list(go), create_graph=True)
+    dgo, dx = _pullback(bwd, [grad_output_I, grad_output_A, grad_output_S], [edge_vec_norm, edge_attr],
+                        [grad_grad_edge_vec_norm, grad_grad_edge_attr])
+    return [dgo[0], dgo[1], dgo[2], dx[0], dx[1]]
+
+
+torch.library.register_fake("tensornet::radial_message_passing_bwd_bwd_primitive")(
+    lambda gi, ga, gs, ggv, ggw, v, w, rd, rp: [torch.empty_like(gi), torch.empty_like(ga), torch.empty_like(gs), torch.empty_like(v),
+                                                torch.empty_like(w)])

@@ -46,7 +46,7 @@ def create_model(args, prior_model=None, mean=None, std=None):
         representation = TorchMD_ET(attn_activation=args["attn_activation"], num_heads=args["num_heads"],
                                     distance_influence=args["distance_influence"],
                                     neighbor_embedding=args["neighbor_embedding"], vector_cutoff=args["vector_cutoff"],
-                                    **shared)
+                                    static_shapes=args["static_shapes"], **shared)
     elif kind == "tensornet2":
         from .tensornet2 import TensorNet2   # host structure + composed forward (see the module docstring)
         is_equivariant = False

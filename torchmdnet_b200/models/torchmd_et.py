@@ -109,7 +109,7 @@ class TorchMD_ET(nn.Module):
     def __init__(self, hidden_channels=128, num_layers=6, num_rbf=50, rbf_type="expnorm", trainable_rbf=True,
                  activation="silu", attn_activation="silu", neighbor_embedding=True, num_heads=8,
                  distance_influence="both", cutoff_lower=0.0, cutoff_upper=5.0, max_z=100, max_num_neighbors=32,
-                 box_vecs=None, vector_cutoff=False, dtype=torch.float32):
+                 box_vecs=None, vector_cutoff=False, dtype=torch.float32, static_shapes=False):
         super().__init__()
         assert distance_influence in ["keys", "values", "both", "none"]
         assert rbf_type in rbf_class_mapping, f'Unknown RBF type "{rbf_type}". Choose from {", ".join(rbf_class_mapping)}.'
@@ -133,6 +133,9 @@ class TorchMD_ET(nn.Module):
         self.out_norm = nn.LayerNorm(hidden_channels, dtype=dtype)
         self.cutoff = CosineCutoff(cutoff_lower, cutoff_upper)
         self.fused_edge_path = None  # None: automatic; False: force the torch-op message path
+        # static_shapes (not a reference argument of the ET): capacity-sized edge buffers + device-side counters on the fused path,
+        # i.e. no host read anywhere in the frame -> the ET frame is CUDA-graph capturable like TensorNet's
+        self.static_shapes = static_shapes
         self.reset_parameters()
 
     def _fused_path_ok(self) -> bool:
@@ -147,10 +150,14 @@ class TorchMD_ET(nn.Module):
         if F_ > 128 or F_ % 4 or hd % 4 or lph & (lph - 1):
             return False
         chains = [l.radial_chain() for l in self.attention_layers]
+        ne_frozen = True
+        if self.neighbor_embedding is not None:
+            chains.append(self.neighbor_embedding.radial_chain())
+            ne_frozen = not self.neighbor_embedding.embedding.weight.requires_grad
         if not all(c.supported_tc() for c in chains):
             return False
         rbf_frozen = not any(t.requires_grad for t in (self.distance_expansion.means, self.distance_expansion.betas))
-        frozen = rbf_frozen and all(c.frozen() for c in chains)
+        frozen = rbf_frozen and ne_frozen and all(c.frozen() for c in chains)
         if frozen or not torch.is_grad_enabled():
             return True
         if not self.training and not getattr(self, "_warned_unfrozen", False):
@@ -174,28 +181,42 @@ class TorchMD_ET(nn.Module):
         x = self.embedding(z)
         g = self.distance.graph(pos, batch, box)
         use_fused = self._fused_path_ok()
+        if self.static_shapes and not use_fused:
+            raise RuntimeError("TorchMD_ET(static_shapes=True) needs the fused inference path (frozen weights, F <= 128, distance_influence='both')")
         if use_fused:
             pidx = fused.build_pair_index(g)
-            E, P = torch.cat([g.num_pairs, pidx.num_unique]).tolist()
-            E, P = min(E, g.dist.shape[0]), min(P, g.dist.shape[0])
+            if self.static_shapes:     # capacity-sized views: padded slots belong to no CSR row, no host read
+                E = g.dist.shape[0]
+                P = min(E, (E + z.shape[0]) // 2 + 1)
+            else:
+                E, P = torch.cat([g.num_pairs, pidx.num_unique]).tolist()
+                E, P = min(E, g.dist.shape[0]), min(P, g.dist.shape[0])
+            dist, vec = g.dist[:E], g.vec[:E]
+            d_ij = vec / dist.masked_fill(dist == 0, 1).unsqueeze(1)
+            pair_r = pidx.pair_r[:P]
+            chains = [l.radial_chain() for l in self.attention_layers]
+            if self.neighbor_embedding is not None:
+                chains.append(self.neighbor_embedding.radial_chain())
+            # rbf(r) and d rbf/dr once per frame: the layer-0 tensor-core operand of every radial chain that is not read from a table
+            rbf_op = fused.shared_rbf_operand(chains, pair_r, pidx.num_unique, self.distance_expansion, self.cutoff_lower,
+                                              self.cutoff_upper, dist.requires_grad)
+            if self.neighbor_embedding is not None:   # row a13: per-pair radial factor + one gather kernel
+                x = self.neighbor_embedding.forward_fused(z, x, dist, pair_r, g, pidx, self.distance_expansion, rbf_op)
+            fast = (dist, d_ij, pair_r, g, pidx, self.distance_expansion, rbf_op)
+            a = b = cut = edge_attr = None
         else:
             E = min(int(g.num_pairs.item()), g.dist.shape[0])
-        a, b = g.nbr_i[:E].long(), g.nbr_j[:E].long()
-        dist, vec = g.dist[:E], g.vec[:E]
-        edge_attr = self.distance_expansion(dist)
-        d_ij = vec / dist.masked_fill(dist == 0, 1).unsqueeze(1)
-        cut = self.cutoff(dist)
-        if self.neighbor_embedding is not None:
-            x = self.neighbor_embedding(z, x, torch.stack([a, b]), dist, edge_attr)
+            # the list is symmetric, so pairing (src, dst) = (a, b) covers exactly the reference's edge set
+            # {(edge_index[0], edge_index[1])}; vec = pos_a - pos_b is the reference's d_ij for that edge
+            a, b = g.nbr_i[:E].long(), g.nbr_j[:E].long()
+            dist, vec = g.dist[:E], g.vec[:E]
+            edge_attr = self.distance_expansion(dist)
+            d_ij = vec / dist.masked_fill(dist == 0, 1).unsqueeze(1)
+            cut = self.cutoff(dist)
+            if self.neighbor_embedding is not None:
+                x = self.neighbor_embedding(z, x, torch.stack([a, b]), dist, edge_attr)
+            fast = None
         v = torch.zeros(x.size(0), 3, x.size(1), device=x.device, dtype=x.dtype)
-        # the list is symmetric, so pairing (src, dst) = (a, b) covers exactly the reference's edge set
-        # {(edge_index[0], edge_index[1])}; vec = pos_a - pos_b is the reference's d_ij for that edge
-        if use_fused:
-            pair_r = pidx.pair_r[:P]
-            rbf_op = fused.shared_rbf_operand([l.radial_chain() for l in self.attention_layers], pair_r,
-                                              pidx.num_unique, self.distance_expansion, self.cutoff_lower, self.cutoff_upper,
-                                              dist.requires_grad)
-            fast = (dist, d_ij, pair_r, g, pidx, self.distance_expansion, rbf_op)
         for attn in self.attention_layers:
             dx, dv = attn.forward_fused(x, v, fast) if use_fused else attn(x, v, a, b, cut, edge_attr, d_ij)
             x = x + dx

@@ -263,6 +263,20 @@ class NeighborEmbedding(nn.Module):
         self.distance_proj.bias.data.fill_(0)
         self.combine.bias.data.fill_(0)
 
+    def radial_chain(self):
+        from ..extensions import fused
+        if getattr(self, "_chain", None) is None:
+            self._chain = fused.RadialChain([[self.distance_proj]], act=False, mul_cutoff=True)
+        return self._chain
+
+    def forward_fused(self, z, x, dist, pair_r, g, pidx, rbf_mod, rbf_op):
+        """same sum with C(r)(W_d rbf + b) evaluated once per unordered pair (radial chain / table) and one gather kernel
+        (csrc/et_attention.cu: nbr_embed_fwd / _bwd) instead of rbf [E,R] -> Linear -> mask -> gather -> index_add"""
+        from ..extensions import fused
+        agg = fused.neighbor_embedding_sum(dist, pair_r, self.radial_chain(), rbf_mod, self.cutoff.cutoff_lower, self.cutoff.cutoff_upper,
+                                           self.embedding.weight, z, g, pidx, rbf_op)
+        return self.combine(torch.cat([x, agg], dim=1))
+
     def forward(self, z, x, edge_index, edge_weight, edge_attr):
         src, nbr = edge_index[0], edge_index[1]
         keep = (src != nbr).to(x.dtype)
