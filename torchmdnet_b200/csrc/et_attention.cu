@@ -245,7 +245,9 @@ __global__ void __launch_bounds__(256) nbr_embed_fwd_kernel(const float* __restr
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
     const int k0 = indptr[i], k1 = indptr[i + 1];
-    for (int f = lane * 4; f < F; f += 128) {
+    for (int ff = 0; ff < F; ff += 128) {      // all lanes iterate (the shuffles need the whole warp); lanes past F idle
+      const int f = ff + lane * 4;
+      const bool on = f < F;
       float4 acc = f4z();
       for (int e0 = k0; e0 < k1; e0 += 32) {
         const int k = e0 + lane;
@@ -254,11 +256,11 @@ __global__ void __launch_bounds__(256) nbr_embed_fwd_kernel(const float* __restr
         const int m = min(32, k1 - e0);
         for (int t = 0; t < m; ++t) {
           const int jj = __shfl_sync(0xffffffffu, j, t), pp = __shfl_sync(0xffffffffu, p, t), zz = __shfl_sync(0xffffffffu, zj, t);
-          if (jj == i) continue;   // warp-uniform
+          if (jj == i || !on) continue;
           acc = f4fma(ldg4(wp + (long long)pp * F + f), ldg4(table + (long long)zz * F + f), acc);
         }
       }
-      st4(out + (long long)i * F + f, acc);
+      if (on) st4(out + (long long)i * F + f, acc);
     }
   }
 }

@@ -266,6 +266,18 @@ _pair("tensornet::radial_message_passing_fwd_primitive", "tensornet::radial_mess
 
 
 # ------------------------------------------------------------------------------------------ double backward primitives
+# Registered as CompositeImplicitAutograd implementations (torch.library.Library.define / impl): they are compositions of the
+# differentiable backward of tensornet_ops.py (kernel re-entry for the (bi)linear ops, torch restatements for the quadratic ones)
+# and must run ABOVE the autograd dispatch key -- inside a backend `custom_op` body autograd is excluded and nothing would record.
+_LIB = torch.library.Library("tensornet", "FRAGMENT")
+
+
+def _composite(name, schema, fn):
+    _LIB.define(f"{name}{schema}")
+    _LIB.impl(name, fn, "CompositeImplicitAutograd")
+    REGISTERED.append(f"tensornet::{name}")
+
+
 def _pullback(bwd_fn, grad_outs, inputs, cotangents):
     """the reference's `*_bwd_bwd` contract: given the cotangents of the BACKWARD op's results, return (d/d grad_outs, d/d inputs).
     `bwd_fn(grad_outs, inputs)` evaluates the backward op with differentiable operations (tensornet_ops.py)."""
@@ -273,52 +285,49 @@ def _pullback(bwd_fn, grad_outs, inputs, cotangents):
         go = [t.detach().requires_grad_(True) for t in grad_outs]
         xi = [t.detach().requires_grad_(True) for t in inputs]
         res = list(bwd_fn(go, xi))
-        keep = [(r, c) for r, c in zip(res, cotangents) if r is not None and r.requires_grad]
+        keep = [(r, c.detach()) for r, c in zip(res, cotangents) if r is not None and r.requires_grad]
         g = torch.autograd.grad([r for r, _ in keep], go + xi, [c for _, c in keep], allow_unused=True) if keep else [None] * (len(go) + len(xi))
     g = [torch.zeros_like(t) if gi is None else gi for gi, t in zip(g, go + xi)]
     return g[: len(go)], g[len(go):]
 
 
-@_op("tensornet::compose_tensor_bwd_bwd_primitive")
-def compose_bwd_bwd(grad_output: Tensor, grad_grad_x: Tensor, grad_grad_y: Tensor, grad_grad_z: Tensor, x: Tensor, y: Tensor,
-                    z: Tensor) -> List[Tensor]:
+def _compose_bwd_bwd(grad_output, grad_grad_x, grad_grad_y, grad_grad_z, x, y, z):
     dgo, _ = _pullback(lambda go, xi: T._ComposeT.apply(go[0]), [grad_output], [], [grad_grad_x, grad_grad_y, grad_grad_z])
     return [dgo[0], torch.zeros_like(x), torch.zeros_like(y), torch.zeros_like(z)]     # linear op: no dependence on (x, y, z)
 
 
-torch.library.register_fake("tensornet::compose_tensor_bwd_bwd_primitive")(
-    lambda go, gx, gy, gz, x, y, z: [torch.empty_like(go), torch.empty_like(x), torch.empty_like(y), torch.empty_like(z)])
+_composite("compose_tensor_bwd_bwd_primitive",
+           "(Tensor grad_output, Tensor grad_grad_x, Tensor grad_grad_y, Tensor grad_grad_z, Tensor x, Tensor y, Tensor z) -> Tensor[]", _compose_bwd_bwd)
 
 
-@_op("tensornet::decompose_tensor_bwd_bwd_primitive")
-def decompose_bwd_bwd(grad_output_i: Tensor, grad_output_a: Tensor, grad_output_s: Tensor, grad_grad_x: Tensor, x: Tensor) -> List[Tensor]:
+def _decompose_bwd_bwd(grad_output_i, grad_output_a, grad_output_s, grad_grad_x, x):
     dgo, _ = _pullback(lambda go, xi: [T._DecomposeT.apply(*go)], [grad_output_i, grad_output_a, grad_output_s], [], [grad_grad_x])
     return [dgo[0], dgo[1], dgo[2], torch.zeros_like(x)]
 
 
-torch.library.register_fake("tensornet::decompose_tensor_bwd_bwd_primitive")(
-    lambda gi, ga, gs, ggx, x: [torch.empty_like(gi), torch.empty_like(ga), torch.empty_like(gs), torch.empty_like(x)])
+_composite("decompose_tensor_bwd_bwd_primitive",
+           "(Tensor grad_output_i, Tensor grad_output_a, Tensor grad_output_s, Tensor grad_grad_x, Tensor x) -> Tensor[]", _decompose_bwd_bwd)
 
 
 def _register_matmul_bwd_bwd(kind):
     fn = T._MatMulO3 if kind == "o3" else T._MatMulSO3
-    name = f"tensornet::tensor_matmul_{kind}_3x3_bwd_bwd_primitive"
 
-    @_op(name)
-    def mm_bwd_bwd(grad_output: Tensor, grad_grad_x: Tensor, grad_grad_y: Tensor, x: Tensor, y: Tensor) -> List[Tensor]:
+    def mm_bwd_bwd(grad_output, grad_grad_x, grad_grad_y, x, y):
+        if x.ndim != 4 or y.ndim != 4 or x.shape[1] != 3 or x.shape[2] != 3 or y.shape[1] != 3 or y.shape[2] != 3:
+            raise ValueError("x and y must be [N,3,3,F] tensors")
         dgo, dx = _pullback(lambda go, xi: [fn.apply(go[0], xi[1].transpose(1, 2)), fn.apply(xi[0].transpose(1, 2), go[0])],
                             [grad_output], [x, y], [grad_grad_x, grad_grad_y])
         return [dgo[0], dx[0], dx[1]]
 
-    torch.library.register_fake(name)(lambda go, gx, gy, x, y: [torch.empty_like(go), torch.empty_like(x), torch.empty_like(y)])
+    _composite(f"tensor_matmul_{kind}_3x3_bwd_bwd_primitive",
+               "(Tensor grad_output, Tensor grad_grad_x, Tensor grad_grad_y, Tensor x, Tensor y) -> Tensor[]", mm_bwd_bwd)
 
 
 _register_matmul_bwd_bwd("o3")
 _register_matmul_bwd_bwd("so3")
 
 
-@_op("tensornet::tensor_norm3_bwd_bwd_primitive")
-def norm3_bwd_bwd(grad_grad_x: Tensor, x: Tensor, grad_output: Tensor) -> List[Tensor]:
+def _norm3_bwd_bwd(grad_grad_x, x, grad_output):
     def bwd(go, xi):
         n = torch.cat(T._t_norm3(*T._Decompose.apply(xi[0])), -1)
         return torch.autograd.grad([n], [xi[0]], [go[0]], create_graph=True)
@@ -326,13 +335,11 @@ def norm3_bwd_bwd(grad_grad_x: Tensor, x: Tensor, grad_output: Tensor) -> List[T
     return [dgo[0], dx[0]]
 
 
-torch.library.register_fake("tensornet::tensor_norm3_bwd_bwd_primitive")(lambda ggx, x, go: [torch.empty_like(go), torch.empty_like(x)])
+_composite("tensor_norm3_bwd_bwd_primitive", "(Tensor grad_grad_x, Tensor x, Tensor grad_output) -> Tensor[]", _norm3_bwd_bwd)
 
 
-@_op("tensornet::message_passing_bwd_bwd_primitive")
-def mp_bwd_bwd(grad_output_x: Tensor, grad_output_y: Tensor, grad_output_z: Tensor, grad_grad_x: Tensor, grad_grad_y: Tensor,
-               grad_grad_z: Tensor, grad_grad_edge_attr: Tensor, x: Tensor, y: Tensor, z: Tensor, edge_attr: Tensor, row_data: Tensor,
-               row_indices: Tensor, row_indptr: Tensor, col_data: Tensor, col_indices: Tensor, col_indptr: Tensor) -> List[Tensor]:
+def _mp_bwd_bwd(grad_output_x, grad_output_y, grad_output_z, grad_grad_x, grad_grad_y, grad_grad_z, grad_grad_edge_attr, x, y, z, edge_attr,
+                row_data, row_indices, row_indptr, col_data, col_indices, col_indptr):
     graph = (row_data, row_indices, row_indptr, col_data, col_indices, col_indptr)
     dgo, dx = _pullback(lambda go, xi: T._MPBwd.apply(xi[0], xi[1], xi[2], xi[3], go[0], go[1], go[2], *graph),
                         [grad_output_x, grad_output_y, grad_output_z], [x, y, z, edge_attr],
@@ -340,15 +347,14 @@ def mp_bwd_bwd(grad_output_x: Tensor, grad_output_y: Tensor, grad_output_z: Tens
     return [dgo[0], dgo[1], dgo[2], dx[0], dx[1], dx[2], dx[3]]
 
 
-torch.library.register_fake("tensornet::message_passing_bwd_bwd_primitive")(
-    lambda gx, gy, gz, ggx, ggy, ggz, ggw, x, y, z, w, *a: [torch.empty_like(gx), torch.empty_like(gy), torch.empty_like(gz),
-                                                           torch.empty_like(x), torch.empty_like(y), torch.empty_like(z), torch.empty_like(w)])
+_composite("message_passing_bwd_bwd_primitive",
+           "(Tensor grad_output_x, Tensor grad_output_y, Tensor grad_output_z, Tensor grad_grad_x, Tensor grad_grad_y, Tensor grad_grad_z, "
+           "Tensor grad_grad_edge_attr, Tensor x, Tensor y, Tensor z, Tensor edge_attr, Tensor? row_data, Tensor row_indices, Tensor row_indptr, "
+           "Tensor? col_data, Tensor col_indices, Tensor col_indptr) -> Tensor[]", _mp_bwd_bwd)
 
 
-@_op("tensornet::radial_message_passing_bwd_bwd_primitive")
-def radial_bwd_bwd(grad_output_I: Tensor, grad_output_A: Tensor, grad_output_S: Tensor, grad_grad_edge_vec_norm: Tensor,
-                   grad_grad_edge_attr: Tensor, edge_vec_norm: Tensor, edge_attr: Tensor, row_data: Tensor,
-                   row_indptr: Tensor) -> List[Tensor]:
+def _radial_bwd_bwd(grad_output_I, grad_output_A, grad_output_S, grad_grad_edge_vec_norm, grad_grad_edge_attr, edge_vec_norm, edge_attr,
+                    row_data, row_indptr):
     def bwd(go, xi):
         out = T._t_radial_mp(xi[0], xi[1], row_data, row_indptr)
         return torch.autograd.grad(list(out), [xi[0], xi[1]], list(go), create_graph=True)
@@ -357,6 +363,6 @@ def radial_bwd_bwd(grad_output_I: Tensor, grad_output_A: Tensor, grad_output_S: 
     return [dgo[0], dgo[1], dgo[2], dx[0], dx[1]]
 
 
-torch.library.register_fake("tensornet::radial_message_passing_bwd_bwd_primitive")(
-    lambda gi, ga, gs, ggv, ggw, v, w, rd, rp: [torch.empty_like(gi), torch.empty_like(ga), torch.empty_like(gs), torch.empty_like(v),
-                                                torch.empty_like(w)])
+_composite("radial_message_passing_bwd_bwd_primitive",
+           "(Tensor grad_output_I, Tensor grad_output_A, Tensor grad_output_S, Tensor grad_grad_edge_vec_norm, Tensor grad_grad_edge_attr, "
+           "Tensor edge_vec_norm, Tensor edge_attr, Tensor? row_data, Tensor row_indptr) -> Tensor[]", _radial_bwd_bwd)
