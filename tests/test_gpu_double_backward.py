@@ -72,6 +72,26 @@ def test_compact_stages_double_backward():
     compare(T.gate_compact, lambda i, a, s, g: (i * g[:, 0:1], a * g[:, 1:2], s * g[:, 2:3]), lambda: c(80) + [leaf(N, 3, F, seed=83)])
 
 
+def test_dependent_inputs_double_backward():
+    """stage inputs that are functions of one another (the model's P2 gets (Y, M(Y)), P3 gets (X, dX(X))): the create_graph branch
+    must return PARTIAL derivatives per input, autograd adds the chain through the other input itself"""
+    from torchmdnet_b200.extensions import tensornet_ops as T
+    c = lambda s: [leaf(N, 1, F, seed=s), leaf(N, 3, F, seed=s + 1), leaf(N, 5, F, seed=s + 2)]
+    qf = (torch.rand(N, generator=torch.Generator().manual_seed(5)) + 0.5).to(dev)
+
+    def chain(p1, p2, p3):
+        def fn(I, A, S):
+            Y = p1(I, A, S)
+            M = p1(Y[0] * 1.5, Y[1] - 0.3 * A, Y[2] + S)          # M depends on Y (stand-in for the message passing)
+            C = p2(Y[0], Y[1], Y[2], M[0], M[1], M[2], qf, True)
+            D = (0.7 * C[0] + Y[0], C[1] * 1.1, C[2] - Y[2])       # dX depends on X = Y
+            return p3(Y[0], Y[1], Y[2], D[0], D[1], D[2], qf)
+        return fn
+
+    compare(chain(T.interaction_normalize, T.interaction_product, T.interaction_update), chain(T._t_p1, T._t_p2, T._t_p3), lambda: c(90),
+            tol=5e-4)
+
+
 def test_message_passing_double_backward():
     """interaction and embedding message passing on a real neighbour graph: the interaction op re-enters its own kernels
     (tmd_mp_fwd / tmd_mp_bwd) in the double backward"""

@@ -50,20 +50,48 @@ def _triple(N, F, ref):
 # models/model.py:618-628 of the reference, whose ops chain fwd -> bwd -> bwd_bwd primitives).  Every Function below therefore
 # has two backward branches: grad mode off (inference, the hand-written backward kernel) and grad mode on (create_graph): the
 # gradient is produced by DIFFERENTIABLE operations -- either the same kernels re-entered through autograd Functions when the op is
-# (bi)linear (compose / decompose / 3x3 products / message passing: `_MPBwd`), or a torch restatement of the per-(atom, channel)
-# formula whose derivatives torch builds itself -- so it can be differentiated again to any order.
+# (bi)linear (compose / decompose / 3x3 products / message passing: `_MPBwd`; any order), or a torch restatement of the
+# per-(atom, channel) formula whose second derivatives torch builds itself (`_DDFn`: second order, what a force loss needs).
 def _needs_graph(*tensors) -> bool:
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
+class _DDFn(torch.autograd.Function):
+    """H(inputs, grads) = d<ref_fn(inputs), grads>/d inputs as ONE autograd node.
+
+    The torch restatement is evaluated on detached leaf copies, so H holds the PARTIAL derivatives w.r.t. each input: several
+    stages receive inputs that depend on one another (P2 gets (Y, M) with M = message_passing(Y); P3 gets (X, dX) with dX a function
+    of X), and differentiating the restatement directly on the original tensors would let autograd walk from one input into the
+    history of the other and add that path a second time.  The backward of this node is the vector-Jacobian product of H w.r.t.
+    (inputs, grads) taken through the graph built in the forward (second order; a third derivative raises)."""
+
+    @staticmethod
+    def forward(ctx, ref_fn, n_in, *args):
+        ins = [a.detach().requires_grad_(True) for a in args[:n_in]]
+        gs = [a.detach().requires_grad_(True) for a in args[n_in:]]
+        with torch.enable_grad():
+            outs = ref_fn(*ins)
+            outs = list(outs) if isinstance(outs, (tuple, list)) else [outs]
+            g = torch.autograd.grad(outs, ins, gs, create_graph=True, allow_unused=True)
+        ctx.leaves, ctx.g = ins + gs, g
+        ctx.set_materialize_grads(False)
+        return tuple(torch.zeros_like(t) if x is None else x.detach() for x, t in zip(g, ins))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *gg):
+        pairs = [(x, y) for x, y in zip(ctx.g, gg) if x is not None and y is not None and x.requires_grad]
+        if not pairs:
+            return (None, None) + (None,) * len(ctx.leaves)
+        with torch.enable_grad():
+            res = torch.autograd.grad([x for x, _ in pairs], ctx.leaves, [y for _, y in pairs], allow_unused=True, retain_graph=True)
+        return (None, None) + tuple(res)
+
+
 def _dd(ref_fn, inputs, grads):
-    """create_graph branch: d<ref_fn(*inputs), grads>/d inputs through autograd on the torch restatement `ref_fn`; `inputs` are the
-    Function's ORIGINAL input tensors (they carry their history), the result is differentiable w.r.t. them and w.r.t. `grads`."""
-    with torch.enable_grad():
-        ins = [t if t.requires_grad else t.detach().requires_grad_(True) for t in inputs]
-        outs = ref_fn(*ins)
-        outs = list(outs) if isinstance(outs, (tuple, list)) else [outs]
-        g = torch.autograd.grad(outs, ins, list(grads), create_graph=True, allow_unused=True)
+    """create_graph branch of the per-(atom, channel) stages: the first-order gradient as a differentiable function of the
+    Function's original inputs and of the incoming gradients (see _DDFn); None for inputs that need no gradient."""
+    g = _DDFn.apply(ref_fn, len(inputs), *inputs, *grads)
     return tuple(gi if t.requires_grad else None for gi, t in zip(g, inputs))
 
 
