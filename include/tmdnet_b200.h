@@ -231,6 +231,22 @@ int tmd_embed_bwd(const float* vec, const float* dist, const float* dp, const fl
                   const int* nbr_j, const int* indptr, const float* U, const float* V, const int64_t* zidx, double lo, double hi,
                   int n, int F, const float* dI, const float* dA, const float* dS, float* g_dist, float* g_vec, void* stream);
 
+/* ---- a5 by radial moments (csrc/embed_moments.cu) ---------------------------------------------------------------------------
+ * The embedding's edge weight C(r)(U[z_i]+V[z_j])(W_g rbf(r) + b_g) (models/tensornet.py:554-585) is linear in the radial basis,
+ * so the neighbour sum is taken before the linear map: per atom and neighbour element v the moments
+ * m[v][k][c] = sum_e C phi_c(rhat) rbf_k(r) (c = 1 + 3 + 5 angular factors, k = R is the bias) and then
+ * X[c][h] = sum_v (U+V_v)[h] sum_k W~[h][k] m[v][k][c].  No per-pair radial rows are read or written.
+ * zslot[n]: slot (0..Z-1) of every atom's element; Uz, Vz [Z, F]: element-table rows of the Z species; Wk [3, R+1, F] (k-major,
+ * row R = bias), Wh [3, F, R]; means/betas [R], alpha, lo, hi: ExpNormalSmearing / CosineCutoff parameters
+ * (models/utils.py:356-407, 500-528).  bwd returns dE/d dist[e] and dE/d vec[e,3] (buffers zero-initialised by the caller). */
+int tmd_embed_moments_fwd(const float* vec, const float* dist, const int* nbr_j, const int* indptr, const int* zslot, const float* Uz,
+                          const float* Vz, const float* Wk, const float* means, const float* betas, double alpha, double lo, double hi,
+                          int R, int n, int F, int Z, float* oI, float* oA, float* oS, void* stream);
+int tmd_embed_moments_bwd(const float* vec, const float* dist, const int* nbr_j, const int* indptr, const int* zslot, const float* Uz,
+                          const float* Vz, const float* Wk, const float* Wh, const float* means, const float* betas, double alpha,
+                          double lo, double hi, int R, int n, int F, int Z, const float* dI, const float* dA, const float* dS,
+                          float* g_dist, float* g_vec, void* stream);
+
 /* ---- a10 + a11: TensorNet tail + Scalar head + per-molecule reduction (csrc/head.cu) -------------------------------------
  * Replaces tensor_norm3 -> LayerNorm(3F) -> Linear(3F->F) -> SiLU (models/tensornet.py:394-402), Scalar.pre_reduce = MLP
  * Linear(F->H) -> SiLU -> Linear(H->1) (models/output_modules.py:79-117, models/utils.py:531-580), * std, + atomref[z]

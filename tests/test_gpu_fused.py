@@ -162,6 +162,46 @@ def test_fused_embedding():
     assert (g1 - g2).abs().max() < 2e-4 * (1 + g2.abs().max()), (g1 - g2).abs().max()
 
 
+@pytest.mark.parametrize("R,F,nz,lo", [(32, 128, 2, 0.0), (32, 64, 7, 0.0), (50, 96, 16, 0.5), (64, 256, 3, 0.0)])
+def test_embedding_by_moments(R, F, nz, lo):
+    """csrc/embed_moments.cu (neighbour sums of C phi(rhat) rbf_k first, the radial projections per atom after) vs the composed
+    reference formula (models/tensornet.py:554-585) in torch: outputs and position gradients"""
+    from torchmdnet_b200.extensions import fused
+    from torchmdnet_b200.extensions import tensornet_ops as ops
+    from torchmdnet_b200.models.utils import ExpNormalSmearing, CosineCutoff
+    torch.manual_seed(5)
+    z, pos, g = graph_for(n=150, seed=8)
+    n = z.numel()
+    E = int(g.num_pairs)
+    rbf = ExpNormalSmearing(lo, 5.0, R, trainable=False).to(dev)
+    lins = [torch.nn.Linear(R, F).to(dev) for _ in range(3)]
+    for l in lins:
+        for t in (l.weight, l.bias):
+            t.requires_grad_(False)
+    elements = torch.randperm(40, device=dev)[:nz].sort().values
+    zz = elements[torch.randint(0, nz, (n,), device=dev)]
+    TU, TV = torch.randn(41, F, device=dev), torch.randn(41, F, device=dev)
+    dist, vec = g.dist[:E], g.vec[:E]
+    slots = fused.SpeciesSlots().get(zz)
+    assert slots is not None and slots[1].numel() <= nz
+    mom = fused.EmbedMomentWeights(lins)
+    assert mom.supported(rbf)
+    Wk, Wh = mom.tensors()
+    Uz, Vz = mom.species_rows(TU, TV, slots[1])
+    out = fused.embedding_moments(dist, vec, slots[0], Uz, Vz, Wk, Wh, rbf, lo, 5.0, g)
+    i, j = g.nbr_i[:E].long(), g.nbr_j[:E].long()
+    rhat = vec / dist.masked_fill(dist == 0, 1).unsqueeze(1)
+    x = rbf(dist)
+    w = (CosineCutoff(lo, 5.0)(dist).unsqueeze(-1) * (TU[zz[i]] + TV[zz[j]])).unsqueeze(1) * torch.stack([l(x) for l in lins], 1)
+    ref = ops._t_radial_mp(rhat, w, None, g.indptr)
+    for a, b in zip(out, ref):
+        assert (a - b).abs().max() < 2e-5 * (1 + b.abs().max()), float((a - b).abs().max() / (1 + b.abs().max()))
+    ws = [torch.randn_like(m) for m in out]
+    (g1,) = torch.autograd.grad(sum((a * w_).sum() for a, w_ in zip(out, ws)), [pos], retain_graph=True)
+    (g2,) = torch.autograd.grad(sum((a * w_).sum() for a, w_ in zip(ref, ws)), [pos], retain_graph=True)
+    assert (g1 - g2).abs().max() < 1e-4 * (1 + g2.abs().max()), float((g1 - g2).abs().max() / (1 + g2.abs().max()))
+
+
 @pytest.mark.parametrize("vcut", [True, False])
 def test_et_attention_message(vcut):
     """fused ET message kernel (tmd_et_msg_fwd/bwd) vs the reference formulas (models/torchmd_et.py:355-426) in torch."""

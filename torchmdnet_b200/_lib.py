@@ -75,6 +75,8 @@ SIGNATURES = {
     "tmd_head_bwd": ([P, P, P, I, I, I, P, D] + [P] * 6 + [I] + [P] * 6 + [P], 1),
     "tmd_embed_fwd": ([P] * 9 + [D, D, I, I] + [P] * 3 + [P], 1),
     "tmd_embed_bwd": ([P] * 10 + [D, D, I, I] + [P] * 5 + [P], 1),
+    "tmd_embed_moments_fwd": ([P] * 10 + [D, D, D, I, I, I, I] + [P] * 3 + [P], 1),
+    "tmd_embed_moments_bwd": ([P] * 11 + [D, D, D, I, I, I, I] + [P] * 5 + [P], 1),
 }
 
 

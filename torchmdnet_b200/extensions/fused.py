@@ -493,6 +493,104 @@ def embedding_message_passing(dist, vec, U, V, pair_r, chain, rbf_mod, lo, hi, g
     return _EmbeddingMP.apply(dist, vec, U, V, zidx, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op)
 
 
+# embedding by radial moments (csrc/embed_moments.cu): no per-pair radial rows at all; TMD_EMBED_MOMENTS=0 -> chain + embed kernels
+USE_EMBED_MOMENTS = os.environ.get("TMD_EMBED_MOMENTS", "1") != "0"
+MAX_SPECIES = 16
+
+
+class SpeciesSlots:
+    """zslot[N] (int32 slot of every atom's element among the Z elements present) for the LAST atomic-number tensor seen.  Finding
+    the distinct elements needs one host read (torch.unique), so the result is cached against the identity of `z` (the tensor is
+    kept alive, so its storage cannot be recycled under the key); inside a CUDA-graph capture only a cached entry can be used."""
+
+    def __init__(self):
+        self._z, self._ver, self._val = None, None, None
+
+    def get(self, z: Tensor):
+        c = self._z
+        if c is not None and c.data_ptr() == z.data_ptr() and c.shape == z.shape and self._ver == z._version and c.device == z.device:
+            return self._val
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        species = torch.unique(z)                         # host sync: output size
+        if species.numel() == 0 or species.numel() > MAX_SPECIES:
+            val = None
+        else:
+            zslot = torch.searchsorted(species, z).to(torch.int32).contiguous()
+            val = (zslot, species)
+        self._z, self._ver, self._val = z, z._version, val
+        return val
+
+
+class EmbedMomentWeights:
+    """Radial projections of the embedding as Wk [3, R+1, F] (k-major, row R = bias) and Wh [3, F, R]; Uz / Vz rows of the element
+    tables for the species present.  Cached per weight version / species set."""
+
+    def __init__(self, projs: Sequence[torch.nn.Linear]):
+        self.projs = list(projs)
+        self._key, self._uvkey = None, None
+
+    def frozen(self) -> bool:
+        return not any(t.requires_grad for m in self.projs for t in (m.weight, m.bias))
+
+    def supported(self, rbf_mod) -> bool:
+        from ..models.utils import ExpNormalSmearing
+        R, F = self.projs[0].in_features, self.projs[0].out_features
+        return (isinstance(rbf_mod, ExpNormalSmearing) and len(self.projs) == 3 and R <= 64 and F % 4 == 0 and
+                all(m.in_features == R and m.out_features == F and m.bias is not None and m.weight.dtype == torch.float32 for m in self.projs))
+
+    def tensors(self):
+        key = tuple((t.data_ptr(), t._version) for m in self.projs for t in (m.weight, m.bias))
+        if key != self._key:
+            W = torch.stack([m.weight.detach() for m in self.projs], 0)                    # [3, F, R]
+            b = torch.stack([m.bias.detach() for m in self.projs], 0)                      # [3, F]
+            self._Wk = torch.cat([W.transpose(1, 2), b.unsqueeze(1)], 1).contiguous()      # [3, R+1, F]
+            self._Wh = W.contiguous()
+            self._key = key
+        return self._Wk, self._Wh
+
+    def species_rows(self, U: Tensor, V: Tensor, species: Tensor):
+        key = (U.data_ptr(), V.data_ptr(), species.data_ptr())
+        if key != self._uvkey:
+            self._uv = (U.index_select(0, species).contiguous(), V.index_select(0, species).contiguous(), U, V, species)
+            self._uvkey = key
+        return self._uv[0], self._uv[1]
+
+
+class _EmbeddingMoments(torch.autograd.Function):
+    """I/A/S of the TensorNet embedding (row a5) from per-atom radial moments: see csrc/embed_moments.cu."""
+
+    @staticmethod
+    def forward(ctx, dist, vec, zslot, Uz, Vz, Wk, Wh, rbf_mod, lo, hi, g):
+        dist_c, vec_c = dist.detach().contiguous(), vec.detach().contiguous()
+        means, betas = rbf_mod.means.detach().contiguous(), rbf_mod.betas.detach().contiguous()
+        N, F, R, Z = g.indptr.shape[0] - 1, Uz.shape[-1], Wh.shape[-1], Uz.shape[0]
+        out = _triple(N, F, Uz.device)
+        _lib.call("tmd_embed_moments_fwd", p(vec_c), p(dist_c), p(g.nbr_j), p(g.indptr), p(zslot), p(Uz), p(Vz), p(Wk), p(means), p(betas),
+                  float(rbf_mod.alpha), float(lo), float(hi), R, N, F, Z, p(out[0]), p(out[1]), p(out[2]), device=Uz.device)
+        ctx.save_for_backward(dist_c, vec_c, zslot, Uz, Vz, Wk, Wh, means, betas, g.nbr_j, g.indptr)
+        ctx.cfg = (float(rbf_mod.alpha), float(lo), float(hi), N, dist.requires_grad or vec.requires_grad)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dI, dA, dS):
+        dist, vec, zslot, Uz, Vz, Wk, Wh, means, betas, nbr_j, indptr = ctx.saved_tensors
+        alpha, lo, hi, N, need = ctx.cfg
+        if not need:
+            return (None,) * 11
+        F, R, Z = Uz.shape[-1], Wh.shape[-1], Uz.shape[0]
+        g_dist, g_vec = torch.zeros_like(dist), torch.zeros_like(vec)
+        dI, dA, dS = dI.contiguous(), dA.contiguous(), dS.contiguous()
+        _lib.call("tmd_embed_moments_bwd", p(vec), p(dist), p(nbr_j), p(indptr), p(zslot), p(Uz), p(Vz), p(Wk), p(Wh), p(means), p(betas),
+                  alpha, lo, hi, R, N, F, Z, p(dI), p(dA), p(dS), p(g_dist), p(g_vec), device=Uz.device)
+        return (g_dist, g_vec) + (None,) * 9
+
+
+def embedding_moments(dist, vec, zslot, Uz, Vz, Wk, Wh, rbf_mod, lo, hi, g):
+    return _EmbeddingMoments.apply(dist, vec, zslot, Uz, Vz, Wk, Wh, rbf_mod, lo, hi, g)
+
+
 class _ETMessage(torch.autograd.Function):
     """Fused ET attention message + aggregation (row a14): see csrc/et_attention.cu."""
 

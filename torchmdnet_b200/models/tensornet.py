@@ -76,6 +76,21 @@ class TensorEmbedding(nn.Module):
             self._nl = fused.IrrepsLinearWeights(self.linears_tensor)
         return self._nl
 
+    def moment_weights(self) -> "fused.EmbedMomentWeights":
+        if getattr(self, "_mom", None) is None:
+            self._mom = fused.EmbedMomentWeights([self.distance_proj1, self.distance_proj2, self.distance_proj3])
+        return self._mom
+
+    def species_slots(self, z, rbf_mod):
+        """(zslot, species) when the moment form of the embedding applies to this input (frozen expnorm projections, at most
+        fused.MAX_SPECIES elements present), else None -> radial chain / table + embed kernels"""
+        mom = self.moment_weights()
+        if not (fused.USE_EMBED_MOMENTS and mom.supported(rbf_mod) and (mom.frozen() or not torch.is_grad_enabled())):
+            return None
+        if getattr(self, "_species", None) is None:
+            self._species = fused.SpeciesSlots()
+        return self._species.get(z)
+
     def element_tables(self):
         """(U, V) [max_z, F]: emb2([Z_i ; Z_j]) = U[z_i] + V[z_j] with U = emb W_u^T, V = emb W_v^T + b.  The pair embedding depends
         on the two ELEMENTS only, so for frozen weights it is two small tables built once per weight version -- what the reference's
@@ -96,8 +111,19 @@ class TensorEmbedding(nn.Module):
             # fused path: U/V per atom, radial projections per pair (with d/dr), w assembled inside the kernel
             dist, pair_r, pidx, rbf_mod, rbf_op, _plan = fast
             UT, VT = self.element_tables()
-            I, A, S = fused.embedding_message_passing(dist, g.vec[: dist.shape[0]], UT, VT, pair_r, self.radial_chain(), rbf_mod,
-                                                      self.cutoff.cutoff_lower, self.cutoff.cutoff_upper, g, pidx, rbf_op, zidx=z)
+            mom = self.moment_weights()
+            slots = self.species_slots(z, rbf_mod)
+            if slots is not None:
+                # the radial projections are linear in rbf(r): neighbour sums of C phi(rhat) rbf_k first, the linear map per atom after
+                # (csrc/embed_moments.cu) -- no per-pair radial rows, no chain / table call for the embedding
+                zslot, species = slots
+                Wk, Wh = mom.tensors()
+                Uz, Vz = mom.species_rows(UT, VT, species)
+                I, A, S = fused.embedding_moments(dist, g.vec[: dist.shape[0]], zslot, Uz, Vz, Wk, Wh, rbf_mod,
+                                                  self.cutoff.cutoff_lower, self.cutoff.cutoff_upper, g)
+            else:
+                I, A, S = fused.embedding_message_passing(dist, g.vec[: dist.shape[0]], UT, VT, pair_r, self.radial_chain(), rbf_mod,
+                                                          self.cutoff.cutoff_lower, self.cutoff.cutoff_upper, g, pidx, rbf_op, zidx=z)
         else:
             w = self.pair_weights(z, nbr_i, nbr_j, cut, rbf)
             I, A, S = ops.fn_radial_message_passing(rhat, w, None, g.indptr)
@@ -273,7 +299,9 @@ class TensorNet(nn.Module):
         if use_fused:
             pair_r = pidx.pair_r[:P]   # per-pair distances (no autograd: every fused op differentiates w.r.t. the per-slot dist)
             # rbf(r) and d rbf/dr once per frame: the layer-0 tensor-core operand of every radial chain
-            chains = [self.tensor_embedding.radial_chain()] + [l.radial_chain() for l in self.layers]
+            chains = [l.radial_chain() for l in self.layers]
+            if self.tensor_embedding.species_slots(z, self.distance_expansion) is None:   # else: embedding by moments, no chain
+                chains = [self.tensor_embedding.radial_chain()] + chains
             rbf_op = fused.shared_rbf_operand(chains, pair_r, pidx.num_unique, self.distance_expansion,
                                               self.cutoff_lower, self.cutoff_upper, dist.requires_grad)
             # one plan per frame for the message passing of all layers (row groups + their neighbour unions, csrc/mp_coop.cu)
