@@ -199,25 +199,26 @@ int tmd_mp_edge_bwd(const float* YI, const float* YA, const float* YS, const flo
                     const float* dMS, const float* f, const float* fp, const int* pid, const int* nbr_j,
                     const int* indptr, int n, int F, float* dYI, float* dYA, float* dYS, float* g_dist, void* stream);
 /* ---- a7, cooperative form (csrc/mp_coop.cu): the same message passing (tensornet_mp.py:42-131) with the neighbour rows of a
- * GROUP of tmd_mp_group_size() (15) spatially adjacent atoms staged once per group in shared memory (bulk async copies into an mbarrier ring) and the
+ * GROUP of up to tmd_mp_group_size() (15) spatially adjacent atoms staged once per group in shared memory (bulk async copies into an mbarrier ring) and the
  * per-pair radial rows streamed through per-warp async rings.  Bit-identical to tmd_mp_fwd / tmd_mp_edge_bwd.
- * tmd_mp_plan builds the per-frame plan shared by all launches of a frame: rows[n] (atom of slot r; group g = rows[G g .. G g + G),
- * G = tmd_mp_group_size():
+ * tmd_mp_plan builds the per-frame plan shared by all launches of a frame: rows[n] (atom of slot r; group g = rows[gs g .. gs g + gs),
+ * gs = rows per group, 1 .. tmd_mp_group_size(); tmd_mp_pick_group(n) returns the size that fills the 148 one-CTA-per-SM slots best:
  * `order` when given and *order_flag != 0, else 0..n-1), union_j / ucount [max_pairs] (sorted distinct neighbours of each group
  * and the number of its rows containing them, at goff[g] .. goff[g] + gcnt[g]), upos[max_pairs] (position of nbr_j[k] in its
- * group's union, bit 15 = self loop), gcnt[g] = -1 for a group over the staged capacity (it is gathered directly).
- * cursor: one int of scratch.  F % 4 == 0, F <= 128. */
+ * group's union, bit 15 = self loop), goff / gcnt [ceil(n / gs)], gcnt[g] = -1 for a group over the staged capacity (it is gathered
+ * directly).  cursor: one int of scratch.  F % 4 == 0, F <= 128.  The same gs goes to the plan and to the two kernels. */
 int tmd_mp_group_size(void);
-int tmd_mp_plan(const int* indptr, const int* nbr_j, const int* num_pairs, int max_pairs, int n, const int* order,
+int tmd_mp_pick_group(int n);
+int tmd_mp_plan(const int* indptr, const int* nbr_j, const int* num_pairs, int max_pairs, int n, int gs, const int* order,
                 const int* order_flag, int* rows, int* cursor, int* union_j, unsigned char* ucount, unsigned short* upos,
                 int* goff, int* gcnt, void* stream);
 int tmd_mp_coop_fwd(const float* YI, const float* YA, const float* YS, const float* f, const int* pid, const int* nbr_j,
-                    const int* indptr, const int* num_pairs, int max_pairs, int n, int F, const int* rows, const int* union_j,
+                    const int* indptr, const int* num_pairs, int max_pairs, int n, int F, int gs, const int* rows, const int* union_j,
                     const unsigned char* ucount, const unsigned short* upos, const int* goff, const int* gcnt, float* MI,
                     float* MA, float* MS, void* stream);
 int tmd_mp_coop_bwd(const float* YI, const float* YA, const float* YS, const float* dMI, const float* dMA, const float* dMS,
                     const float* f, const float* fp, const int* pid, const int* nbr_j, const int* indptr, const int* num_pairs,
-                    int max_pairs, int n, int F, const int* rows, const int* union_j, const unsigned char* ucount,
+                    int max_pairs, int n, int F, int gs, const int* rows, const int* union_j, const unsigned char* ucount,
                     const unsigned short* upos, const int* goff, const int* gcnt, float* dYI, float* dYA, float* dYS,
                     float* g_dist, void* stream);
 /* embedding message passing on pair-indexed radial projections dp[P_u,3F] (and their d/dr dpp): the unit vector is formed in the
@@ -237,7 +238,7 @@ int tmd_embed_bwd(const float* vec, const float* dist, const float* dp, const fl
  * m[v][k][c] = sum_e C phi_c(rhat) rbf_k(r) (c = 1 + 3 + 5 angular factors, k = R is the bias) and then
  * X[c][h] = sum_v (U+V_v)[h] sum_k W~[h][k] m[v][k][c].  No per-pair radial rows are read or written.
  * zslot[n]: slot (0..Z-1) of every atom's element; Uz, Vz [Z, F]: element-table rows of the Z species; Wk [3, R+1, F] (k-major,
- * row R = bias), Wh [3, F, R]; means/betas [R], alpha, lo, hi: ExpNormalSmearing / CosineCutoff parameters
+ * row R = bias), Wh [3, F/4, R, 4] (Wh[g][h/4][k][h%4] = W_g[h][k]); means/betas [R], alpha, lo, hi: ExpNormalSmearing / CosineCutoff parameters
  * (models/utils.py:356-407, 500-528).  bwd returns dE/d dist[e] and dE/d vec[e,3] (buffers zero-initialised by the caller). */
 int tmd_embed_moments_fwd(const float* vec, const float* dist, const int* nbr_j, const int* indptr, const int* zslot, const float* Uz,
                           const float* Vz, const float* Wk, const float* means, const float* betas, double alpha, double lo, double hi,

@@ -359,7 +359,7 @@ def test_cooperative_message_passing_overflow_fallback():
         M0 = ref.forward(Y, f); dY0, gd0 = ref.backward(Y, dM, f, fp)
         fused.USE_MP_COOP = True
         plan = fused.MessagePassingPlan(g, pidx, F)
-        assert (plan.gcnt == -1).all()
+        assert (plan.gcnt[:-1] == -1).all()      # (the partial last group may fit the staged path: 4 rows x 1000 edges)
         M1 = plan.forward(Y, f); dY1, gd1 = plan.backward(Y, dM, f, fp)
     finally:
         fused.USE_MP_COOP = fused_coop

@@ -67,9 +67,10 @@ SIGNATURES = {
     "tmd_nbr_embed_bwd": ([P] * 6 + [I, I, P, P, P], 1),
     "tmd_mp_edge_bwd": ([P] * 11 + [I, I] + [P] * 4 + [P], 1),
     "tmd_mp_group_size": ([], 0),
-    "tmd_mp_plan": ([P, P, P, I, I, P, P, P, P, P, P, P, P, P, P], 1),
-    "tmd_mp_coop_fwd": ([P] * 8 + [I, I, I] + [P] * 9 + [P], 1),
-    "tmd_mp_coop_bwd": ([P] * 12 + [I, I, I] + [P] * 10 + [P], 1),
+    "tmd_mp_pick_group": ([I], 0),
+    "tmd_mp_plan": ([P, P, P, I, I, I, P, P, P, P, P, P, P, P, P, P], 1),
+    "tmd_mp_coop_fwd": ([P] * 8 + [I, I, I, I] + [P] * 9 + [P], 1),
+    "tmd_mp_coop_bwd": ([P] * 12 + [I, I, I, I] + [P] * 10 + [P], 1),
     "tmd_head_fwd": ([P, P, P, I, I, I, P, P, D] + [P] * 9 + [I] + [P] * 4 + [P], 1),
     "tmd_segment_sum": ([P, P, I, I, P, P, P, P], 2),
     "tmd_head_bwd": ([P, P, P, I, I, I, P, D] + [P] * 6 + [I] + [P] * 6 + [P], 1),

@@ -48,7 +48,11 @@ struct In3 { const float* I; const float* A; const float* S; };
 
 // ------------------------------------------------------------------------------------------------------------ forward
 // Wk [3][R+1][F]: Wk[g][k][h] = W_g[h][k] (k < R), Wk[g][R][h] = b_g[h].  Uz, Vz [Z][F]: rows of the element tables for the Z
-// species present; zslot[n]: species slot of every atom.  dynamic smem: wpb x Z x (R+1) x 12 floats.
+// species present; zslot[n]: species slot of every atom.  dynamic smem per warp: Z x (R+1) x 12 floats (moments) + 32 x 12 floats
+// (per-edge factors of the current 32-edge chunk).
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+template <bool BIG>   // BIG: 32 < R <= 64 (two radial indices per lane)
 __global__ void __launch_bounds__(256) embed_moments_fwd_kernel(const float* __restrict__ vec, const float* __restrict__ dist,
                                                                 const int* __restrict__ nbr_j, const int* __restrict__ indptr,
                                                                 const int* __restrict__ zslot, const float* __restrict__ Uz,
@@ -58,52 +62,89 @@ __global__ void __launch_bounds__(256) embed_moments_fwd_kernel(const float* __r
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int RP = R + 1;
-  float* mw = smem + (size_t)wid * Z * RP * CP;
-  float mu[2], be[2];
+  const size_t per_warp = (size_t)Z * RP * CP + 32 * CP;
+  float* mw = smem + (size_t)wid * per_warp;
+  float* st = mw + (size_t)Z * RP * CP;          // [32 edges][12]: cut * phi_0..8, u, c0, -
+  constexpr int NQ = BIG ? 2 : 1;
+  float mu[NQ], be2[NQ];                          // be2 = -beta log2(e): exp(-beta t^2) = ex2(be2 t^2)
 #pragma unroll
-  for (int q = 0; q < 2; ++q) { const int k = lane + 32 * q; mu[q] = k < R ? means[k] : 0.f; be[q] = k < R ? betas[k] : 0.f; }
+  for (int q = 0; q < NQ; ++q) {
+    const int k = lane + 32 * q;
+    mu[q] = k < R ? means[k] : 0.f;
+    be2[q] = k < R ? -betas[k] * 1.4426950408889634f : 0.f;
+  }
   for (int b = blockIdx.x * wpb + wid; b < n; b += gridDim.x * wpb) {
     const int k0 = indptr[b], k1 = indptr[b + 1];
     unsigned present = 0u;
-    // ---- phase 1: moments (lane <-> radial index k; edges one after the other) ----
+    // ---- phase 1: moments.  Per 32-edge chunk the per-edge factors are prepared lane-parallel (lane <-> edge) and staged in
+    // shared memory; the accumulation runs lane <-> radial index with register accumulators, one species after the other,
+    // and touches the moment tile once per (chunk, species) ----
     for (int e0 = k0; e0 < k1; e0 += 32) {
-      const Geo ge = load_geo(vec, dist, nbr_j, zslot, e0 + lane, e0 + lane < k1, lo, hi, alpha);
-      const int m = min(32, k1 - e0);
-      for (int i = 0; i < m; ++i) {
-        const int v = __shfl_sync(0xffffffffu, ge.v, i);
-        const float cut = __shfl_sync(0xffffffffu, ge.cut, i), u = __shfl_sync(0xffffffffu, ge.u, i), c0 = __shfl_sync(0xffffffffu, ge.c0, i);
-        const float r[3] = {__shfl_sync(0xffffffffu, ge.r0, i), __shfl_sync(0xffffffffu, ge.r1, i), __shfl_sync(0xffffffffu, ge.r2, i)};
-        float* mv = mw + (size_t)v * RP * CP;
-        if (!((present >> v) & 1u)) {
-          for (int t = lane; t < RP * CP; t += 32) mv[t] = 0.f;
-          present |= 1u << v;
-          __syncwarp();
-        }
+      const bool valid = e0 + lane < k1;
+      const Geo ge = load_geo(vec, dist, nbr_j, zslot, e0 + lane, valid, lo, hi, alpha);
+      float c9[9];
+      {
+        const float r[3] = {ge.r0, ge.r1, ge.r2};
         float a[3], sb[5];
         tn::skew_compact(r, a); tn::sym_basis(r, sb);
+        c9[0] = ge.cut;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int k = lane + 32 * q;
-          if (k < R) {
-            const float t = u - mu[q];
-            const float val = cut * c0 * expf(-be[q] * t * t);
-            float4* mp = reinterpret_cast<float4*>(mv + (size_t)k * CP);
-            float4 x = mp[0], y = mp[1], z = mp[2];
-            x.x += val; x.y = fmaf(val, a[0], x.y); x.z = fmaf(val, a[1], x.z); x.w = fmaf(val, a[2], x.w);
-            y.x = fmaf(val, sb[0], y.x); y.y = fmaf(val, sb[1], y.y); y.z = fmaf(val, sb[2], y.z); y.w = fmaf(val, sb[3], y.w);
-            z.x = fmaf(val, sb[4], z.x);
-            mp[0] = x; mp[1] = y; mp[2] = z;
+        for (int c = 0; c < 3; ++c) c9[1 + c] = ge.cut * a[c];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) c9[4 + c] = ge.cut * sb[c];
+        float4* sp = reinterpret_cast<float4*>(st + (size_t)lane * CP);
+        sp[0] = make_float4(c9[0], c9[1], c9[2], c9[3]); sp[1] = make_float4(c9[4], c9[5], c9[6], c9[7]);
+        sp[2] = make_float4(c9[8], ge.u, ge.c0, 0.f);
+      }
+      __syncwarp();
+      unsigned todo = __ballot_sync(0xffffffffu, valid);
+      while (todo) {
+        const int v = __shfl_sync(0xffffffffu, ge.v, __ffs(todo) - 1);
+        const unsigned mask = __ballot_sync(0xffffffffu, valid && ge.v == v);
+        todo &= ~mask;
+        float acc[NQ][9];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+          for (int c = 0; c < 9; ++c) acc[q][c] = 0.f;
+        for (unsigned mm = mask; mm; mm &= mm - 1) {
+          const int i = __ffs(mm) - 1;
+          const float4 s0 = *reinterpret_cast<const float4*>(st + (size_t)i * CP), s1 = *reinterpret_cast<const float4*>(st + (size_t)i * CP + 4),
+                       s2 = *reinterpret_cast<const float4*>(st + (size_t)i * CP + 8);
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            const float t = s2.y - mu[q];
+            const float val = s2.z * ex2_approx(be2[q] * t * t);
+            acc[q][0] = fmaf(val, s0.x, acc[q][0]); acc[q][1] = fmaf(val, s0.y, acc[q][1]); acc[q][2] = fmaf(val, s0.z, acc[q][2]);
+            acc[q][3] = fmaf(val, s0.w, acc[q][3]); acc[q][4] = fmaf(val, s1.x, acc[q][4]); acc[q][5] = fmaf(val, s1.y, acc[q][5]);
+            acc[q][6] = fmaf(val, s1.z, acc[q][6]); acc[q][7] = fmaf(val, s1.w, acc[q][7]); acc[q][8] = fmaf(val, s2.x, acc[q][8]);
           }
         }
-        if (lane == 0) {   // bias row: rho_R = 1
-          float4* mp = reinterpret_cast<float4*>(mv + (size_t)R * CP);
-          float4 x = mp[0], y = mp[1], z = mp[2];
-          x.x += cut; x.y = fmaf(cut, a[0], x.y); x.z = fmaf(cut, a[1], x.z); x.w = fmaf(cut, a[2], x.w);
-          y.x = fmaf(cut, sb[0], y.x); y.y = fmaf(cut, sb[1], y.y); y.z = fmaf(cut, sb[2], y.z); y.w = fmaf(cut, sb[3], y.w);
-          z.x = fmaf(cut, sb[4], z.x);
-          mp[0] = x; mp[1] = y; mp[2] = z;
+        // bias row (rho_R = 1): totals of cut * phi over the species' edges; lane c < 9 ends up with component c
+        float bt[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) bt[c] = (c < 9 && ((mask >> lane) & 1u)) ? c9[c < 9 ? c : 0] : 0.f;
+        const float btot = warp_reduce_transpose<16>(bt, lane);
+        float* mv = mw + (size_t)v * RP * CP;
+        const bool first = !((present >> v) & 1u);
+        present |= 1u << v;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int k = lane + 32 * q;
+          if (k < R) {
+            float4* mp = reinterpret_cast<float4*>(mv + (size_t)k * CP);
+            float4 x = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]), y = make_float4(acc[q][4], acc[q][5], acc[q][6], acc[q][7]);
+            float z = acc[q][8];
+            if (!first) {
+              const float4 ox = mp[0], oy = mp[1];
+              x = add4v(x, ox); y = add4v(y, oy); z += mv[(size_t)k * CP + 8];
+            }
+            mp[0] = x; mp[1] = y; mp[2] = make_float4(z, 0.f, 0.f, 0.f);
+          }
         }
+        if (lane < 9) mv[(size_t)R * CP + lane] = (first ? 0.f : mv[(size_t)R * CP + lane]) + btot;
       }
+      __syncwarp();   // the staging rows are rewritten by the next chunk
     }
     __syncwarp();
     // ---- phase 2: contraction with the radial weights (lane <-> 4 channels) ----
@@ -153,7 +194,7 @@ __global__ void __launch_bounds__(256) embed_moments_fwd_kernel(const float* __r
 }
 
 // ------------------------------------------------------------------------------------------------------------ backward
-// Wh [3][F][R]: Wh[g][h][k] = W_g[h][k]; bias rows are read from Wk[g][R][:].  dynamic smem: 2 R floats (means, betas) then per
+// Wh [3][F/4][R][4]: Wh[g][h/4][k][h%4] = W_g[h][k] (one float4 per (4 channels, k)); bias rows are read from Wk[g][R][:].  dynamic smem: 2 R floats (means, betas) then per
 // warp Z x (R+1) x 12 floats (G) + 9 F floats (p = dX * (U + V)).
 __global__ void __launch_bounds__(256) embed_moments_bwd_kernel(const float* __restrict__ vec, const float* __restrict__ dist,
                                                                 const int* __restrict__ nbr_j, const int* __restrict__ indptr,
@@ -226,15 +267,16 @@ __global__ void __launch_bounds__(256) embed_moments_bwd_kernel(const float* __r
           const float pv[9][4] = {{p[0].x, p[0].y, p[0].z, p[0].w}, {p[1].x, p[1].y, p[1].z, p[1].w}, {p[2].x, p[2].y, p[2].z, p[2].w},
                                   {p[3].x, p[3].y, p[3].z, p[3].w}, {p[4].x, p[4].y, p[4].z, p[4].w}, {p[5].x, p[5].y, p[5].z, p[5].w},
                                   {p[6].x, p[6].y, p[6].z, p[6].w}, {p[7].x, p[7].y, p[7].z, p[7].w}, {p[8].x, p[8].y, p[8].z, p[8].w}};
+          const float4 w1 = ldg4(Wh + (((size_t)0 * F + h) / 4 * R + k) * 4), w2 = ldg4(Wh + (((size_t)1 * F + h) / 4 * R + k) * 4),
+                       w3 = ldg4(Wh + (((size_t)2 * F + h) / 4 * R + k) * 4);
+          const float wv[3][4] = {{w1.x, w1.y, w1.z, w1.w}, {w2.x, w2.y, w2.z, w2.w}, {w3.x, w3.y, w3.z, w3.w}};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float w1 = __ldg(Wh + ((size_t)0 * F + h + q) * R + k), w2 = __ldg(Wh + ((size_t)1 * F + h + q) * R + k),
-                        w3 = __ldg(Wh + ((size_t)2 * F + h + q) * R + k);
-            g[0] = fmaf(pv[0][q], w1, g[0]);
+            g[0] = fmaf(pv[0][q], wv[0][q], g[0]);
 #pragma unroll
-            for (int c = 1; c < 4; ++c) g[c] = fmaf(pv[c][q], w2, g[c]);
+            for (int c = 1; c < 4; ++c) g[c] = fmaf(pv[c][q], wv[1][q], g[c]);
 #pragma unroll
-            for (int c = 4; c < 9; ++c) g[c] = fmaf(pv[c][q], w3, g[c]);
+            for (int c = 4; c < 9; ++c) g[c] = fmaf(pv[c][q], wv[2][q], g[c]);
           }
         }
         float4* gp = reinterpret_cast<float4*>(Gv + (size_t)k * CP);
@@ -256,9 +298,12 @@ __global__ void __launch_bounds__(256) embed_moments_bwd_kernel(const float* __r
 #pragma unroll
           for (int c = 0; c < 9; ++c) Pd[c] = 0.f;
         }
+        const float two_alpha_u_c0 = 2.f * alpha * ge.u * ge.c0;
         for (int k = 0; k < R; ++k) {
-          float rho, drho;
-          tn::expnorm_rbf(ge.u, alpha, ge.c0, ge.dc0, s_mu[k], s_be[k], &rho, &drho);
+          // rbf_k = c0 e, d rbf_k/dr = dc0 e + 2 alpha beta u t c0 e  with e = exp(-beta t^2), t = u - mu_k  (tn::expnorm_rbf)
+          const float t = ge.u - s_mu[k], bk = s_be[k];
+          const float ee = ex2_approx(-1.4426950408889634f * bk * t * t);
+          const float rho = ge.c0 * ee, drho = ee * fmaf(two_alpha_u_c0 * bk, t, ge.dc0);
           const float4 x = *reinterpret_cast<const float4*>(Gv + (size_t)k * CP), y = *reinterpret_cast<const float4*>(Gv + (size_t)k * CP + 4);
           const float z = Gv[(size_t)k * CP + 8];
           const float gk[9] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w, z};
@@ -305,13 +350,20 @@ int tmd_embed_moments_fwd(const float* vec, const float* dist, const int* nbr_j,
   TMD_REQUIRE(Z > 0 && Z <= 32, "embed_moments_fwd: 1 <= number of species <= 32");
   TMD_REQUIRE(vec && dist && nbr_j && indptr && zslot && Uz && Vz && Wk && means && betas && oI && oA && oS, "embed_moments_fwd: null pointer");
   if (n == 0) return TMD_OK;
-  const size_t per_warp = (size_t)Z * (R + 1) * CP * sizeof(float);
+  const size_t per_warp = ((size_t)Z * (R + 1) * CP + 32 * CP) * sizeof(float);
   TMD_REQUIRE(per_warp <= 200 * 1024, "embed_moments_fwd: species x num_rbf tile exceeds shared memory");
   const int wpb = pick_warps(per_warp, 0);
   const size_t smem = (size_t)wpb * per_warp;
-  cudaFuncSetAttribute(embed_moments_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  embed_moments_fwd_kernel<<<tmd_blocks_for((long long)n * 32, wpb * 32), wpb * 32, smem, (cudaStream_t)stream>>>(
-      vec, dist, nbr_j, indptr, zslot, Uz, Vz, Wk, means, betas, (float)alpha, (float)lo, (float)hi, R, n, F, Z, Out3{oI, oA, oS});
+  const int blocks = tmd_blocks_for((long long)n * 32, wpb * 32);
+  if (R > 32) {
+    cudaFuncSetAttribute(embed_moments_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    embed_moments_fwd_kernel<true><<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(
+        vec, dist, nbr_j, indptr, zslot, Uz, Vz, Wk, means, betas, (float)alpha, (float)lo, (float)hi, R, n, F, Z, Out3{oI, oA, oS});
+  } else {
+    cudaFuncSetAttribute(embed_moments_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    embed_moments_fwd_kernel<false><<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(
+        vec, dist, nbr_j, indptr, zslot, Uz, Vz, Wk, means, betas, (float)alpha, (float)lo, (float)hi, R, n, F, Z, Out3{oI, oA, oS});
+  }
   return tmd_check_launch("embed_moments_fwd");
 }
 

@@ -15,9 +15,9 @@
 
 namespace {
 
-constexpr int TA = 32;     // atoms per CTA
-constexpr int HT = 256;    // threads per CTA: warp w owns atoms 4w .. 4w+3 in the GEMM stages
-constexpr int MAXC = 8;    // output columns per lane and pass: widths up to 256
+constexpr int HT_MAX = 320;  // threads per CTA: nw = 8..10 warps, warp w owns atoms 4w .. 4w+3 in the GEMM stages (TA = 4 nw atoms per CTA;
+                             // the host picks nw so that the grid fits the resident CTA slots in as few rounds as possible)
+constexpr int MAXC = 8;      // output columns per lane and pass: widths up to 256
 
 struct CI { const float* I; const float* A; const float* S; };
 struct MI { float* I; float* A; float* S; };
@@ -34,13 +34,13 @@ __device__ __forceinline__ void ld_c(const CI& t, long long n, int F, int h, flo
 // W is streamed through shared memory in chunks of KC rows with cp.async double buffering: every CTA reads each weight row
 // once, coalesced, KC rows ahead of its use.  (Reading W straight from global in the inner loop made all ~300 CTAs hit the same
 // 512-byte row of L2 at the same time with the full L2 latency exposed per k-step: 220 us instead of ~20 us for the forward.)
-constexpr int KC = 16;
+constexpr int KC = 8;
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void stage_w(float* wb, const float* __restrict__ W, int ldw, int k0, int nc4, int tid) {
   // KC rows x nc4 float4 columns of W -> wb [KC][4 nc4]
-  for (int i = tid; i < KC * nc4; i += HT) {
+  for (int i = tid; i < KC * nc4; i += blockDim.x) {
     const int r = i / nc4, c = i - r * nc4;
     cp_async16(wb + (size_t)r * 4 * nc4 + 4 * c, W + (size_t)(k0 + r) * ldw + 4 * c);
   }
@@ -95,12 +95,13 @@ struct HeadW {
   float eps;
 };
 
-// shared memory: xs [TA][3F+4] | h1s [TA][F+4] | h2s [TA][H+4] | wbuf [2][KC][256] (weight staging)
-__global__ void __launch_bounds__(HT) head_fwd_kernel(CI X, int N, int F, int H, HeadW P, const int64_t* __restrict__ z,
+// shared memory (TA = 4 x warps): xs [TA][3F+4] | h1s [TA][F+4] | h2s [TA][H+4] | wbuf [2][KC][256] (weight staging)
+__global__ void __launch_bounds__(HT_MAX) head_fwd_kernel(CI X, int N, int F, int H, HeadW P, const int64_t* __restrict__ z,
                                                       const float* __restrict__ atomref, int n_ref, float* __restrict__ e_out,
                                                       float* __restrict__ mu_rstd, float* __restrict__ z1, float* __restrict__ z2) {
   extern __shared__ __align__(16) float sm[];
   const int ldx = 3 * F + 4, ld1 = F + 4, ld2 = H + 4;
+  const int HT = blockDim.x, TA = HT >> 3;
   float* xs = sm; float* h1s = xs + TA * ldx; float* h2s = h1s + TA * ld1; float* wbuf = h2s + TA * ld2;
   const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
   const long long a0 = (long long)blockIdx.x * TA;
@@ -184,22 +185,19 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(CI X, int N, int F, int H,
   }
 }
 
-// shared memory: x0 [TA][3F+4] (pre-LN norms) | dxs [TA][3F+4] | d1s [TA][F+4] | d2s [TA][H+4] | wbuf [2][KC][256]
-__global__ void __launch_bounds__(HT) head_bwd_kernel(CI X, int N, int F, int H, HeadW P, const float* __restrict__ gy,
+// shared memory (TA = 4 x warps): dxs [TA][3F+4] | d1s [TA][F+4] | d2s [TA][H+4] | wbuf [2][KC][256].  The pre-LayerNorm norms
+// (xhat of the LayerNorm backward) are recomputed from the node tensors instead of being kept in a second [TA][3F] tile: the
+// smaller footprint lets two CTAs share an SM.
+__global__ void __launch_bounds__(HT_MAX) head_bwd_kernel(CI X, int N, int F, int H, HeadW P, const float* __restrict__ gy,
                                                       const int64_t* __restrict__ batch, int M, const float* __restrict__ mu_rstd,
                                                       const float* __restrict__ z1, const float* __restrict__ z2, MI dX) {
   extern __shared__ __align__(16) float sm[];
   const int ldx = 3 * F + 4, ld1 = F + 4, ld2 = H + 4;
-  float* x0 = sm; float* dxs = x0 + TA * ldx; float* d1s = dxs + TA * ldx; float* d2s = d1s + TA * ld1; float* wbuf = d2s + TA * ld2;
+  const int HT = blockDim.x, TA = HT >> 3;
+  float* dxs = sm; float* d1s = dxs + TA * ldx; float* d2s = d1s + TA * ld1; float* wbuf = d2s + TA * ld2;
   const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
   const long long a0 = (long long)blockIdx.x * TA;
-  // pre-LN norms (LayerNorm backward needs xhat) and dz2 = de * w3 * SiLU'(z2)
-  for (int idx = tid; idx < TA * F; idx += HT) {
-    const int a = idx / F, h = idx - a * F;
-    float o[3] = {0.f, 0.f, 0.f};
-    if (a0 + a < N) { float c[9]; ld_c(X, a0 + a, F, h, c); tn::norm3_compact(c, o); }
-    x0[a * ldx + h] = o[0]; x0[a * ldx + F + h] = o[1]; x0[a * ldx + 2 * F + h] = o[2];
-  }
+  // dz2 = de * w3 * SiLU'(z2)
   const float stdv = __ldg(P.std_);
   for (int idx = tid; idx < TA * H; idx += HT) {
     const int a = idx / H, c = idx - a * H;
@@ -251,32 +249,37 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(CI X, int N, int F, int H,
         }
   }
   __syncthreads();
-  // LayerNorm backward per atom: dx = rstd (g - mean(g) - xhat mean(g xhat))
+  // LayerNorm backward per atom, dx = rstd (g - mean(g) - xhat mean(g xhat)), fused with the norm3 backward -> dI, dA, dS.
+  // The node row is read twice (sums, then gradients); the second read hits L1.
   for (int q = 0; q < 4; ++q) {
     const int a = 4 * wy + q;
     if (a0 + a >= N) continue;   // warp-uniform
-    const float mu = mu_rstd[2 * (a0 + a)], rstd = mu_rstd[2 * (a0 + a) + 1];
-    float* g = dxs + a * ldx; const float* x = x0 + a * ldx;
-    float s1 = 0.f, s2 = 0.f;
-    for (int k = lane; k < 3 * F; k += 32) { const float xh = (x[k] - mu) * rstd; s1 += g[k]; s2 = fmaf(g[k], xh, s2); }
-    s1 = warp_sum(s1) / (float)(3 * F); s2 = warp_sum(s2) / (float)(3 * F);
-    for (int k = lane; k < 3 * F; k += 32) { const float xh = (x[k] - mu) * rstd; g[k] = rstd * (g[k] - s1 - xh * s2); }
-  }
-  __syncthreads();
-  // norm3 backward -> dI, dA, dS
-  for (int idx = tid; idx < TA * F; idx += HT) {
-    const int a = idx / F, h = idx - a * F;
-    if (a0 + a >= N) continue;
-    float c[9], dc[9];
-    ld_c(X, a0 + a, F, h, c);
-    const float dn[3] = {dxs[a * ldx + h], dxs[a * ldx + F + h], dxs[a * ldx + 2 * F + h]};
-    tn::norm3_compact_bwd(c, dn, dc);
     const long long n = a0 + a;
-    dX.I[n * F + h] = dc[0];
+    const float mu = mu_rstd[2 * n], rstd = mu_rstd[2 * n + 1];
+    const float* g = dxs + a * ldx;
+    float s1 = 0.f, s2 = 0.f;
+    for (int h = lane; h < F; h += 32) {
+      float c[9], o[3];
+      ld_c(X, n, F, h, c); tn::norm3_compact(c, o);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) dX.A[(n * 3 + k) * F + h] = dc[1 + k];
+      for (int t = 0; t < 3; ++t) {
+        const float gv = g[t * F + h];
+        s1 += gv; s2 = fmaf(gv, (o[t] - mu) * rstd, s2);
+      }
+    }
+    s1 = warp_sum(s1) / (float)(3 * F); s2 = warp_sum(s2) / (float)(3 * F);
+    for (int h = lane; h < F; h += 32) {     // second pass: the row comes from L1 this time
+      float c[9], o[3], dn[3], dc[9];
+      ld_c(X, n, F, h, c); tn::norm3_compact(c, o);
 #pragma unroll
-    for (int k = 0; k < 5; ++k) dX.S[(n * 5 + k) * F + h] = dc[4 + k];
+      for (int t = 0; t < 3; ++t) dn[t] = rstd * (g[t * F + h] - s1 - (o[t] - mu) * rstd * s2);
+      tn::norm3_compact_bwd(c, dn, dc);
+      dX.I[n * F + h] = dc[0];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) dX.A[(n * 3 + k) * F + h] = dc[1 + k];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) dX.S[(n * 5 + k) * F + h] = dc[4 + k];
+    }
   }
 }
 
@@ -316,6 +319,24 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const float* __restric
   }
 }
 
+// warps per CTA (8..10; 4 atoms per warp): the tile size that covers the N atoms in the fewest rounds of resident CTAs
+// (148 SMs x CTAs that fit the shared memory), ties -> fewer atom-slots of work, i.e. the smaller rounds x tile product
+int pick_tile_warps(int N, size_t per_atom_bytes, size_t fixed_bytes) {
+  int best = 8; long long best_cost = -1;
+  for (int nw = 8; nw <= HT_MAX / 32; ++nw) {
+    const size_t smem = (size_t)4 * nw * per_atom_bytes + fixed_bytes;
+    if (smem > 227 * 1024) break;
+    int per_sm = (int)((size_t)(228 * 1024) / (smem + 1024));
+    const int by_threads = 2048 / (32 * nw);
+    if (per_sm > by_threads) per_sm = by_threads;
+    if (per_sm < 1) per_sm = 1;
+    const long long tiles = (N + 4 * nw - 1) / (4 * nw), slots = 148LL * per_sm;
+    const long long cost = ((tiles + slots - 1) / slots) * (4 * nw) * (per_sm > 1 ? 3 : 4);   // co-resident CTAs hide each other's barriers
+    if (best_cost < 0 || cost < best_cost) { best = nw; best_cost = cost; }
+  }
+  return best;
+}
+
 }  // namespace
 
 extern "C" {
@@ -331,9 +352,11 @@ int tmd_head_fwd(const float* I, const float* A, const float* S, int N, int F, i
   TMD_REQUIRE(!atomref || z, "head_fwd: atomref without z");
   if (N == 0) return TMD_OK;
   HeadW P{ln_w, ln_b, W1T, b1, W2T, b2, w3, b3, nullptr, nullptr, std_, (float)eps};
-  const size_t smem = ((size_t)TA * ((3 * F + 4) + (F + 4) + (H + 4)) + 2 * KC * 256) * sizeof(float);
+  const size_t per_atom = (size_t)((3 * F + 4) + (F + 4) + (H + 4)) * sizeof(float), fixed = (size_t)2 * KC * 256 * sizeof(float);
+  const int nw = pick_tile_warps(N, per_atom, fixed);
+  const size_t smem = (size_t)4 * nw * per_atom + fixed;
   cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  head_fwd_kernel<<<(N + TA - 1) / TA, HT, smem, (cudaStream_t)stream>>>(CI{I, A, S}, N, F, H, P, z, atomref, n_ref, e, mu_rstd, z1, z2);
+  head_fwd_kernel<<<(N + 4 * nw - 1) / (4 * nw), 32 * nw, smem, (cudaStream_t)stream>>>(CI{I, A, S}, N, F, H, P, z, atomref, n_ref, e, mu_rstd, z1, z2);
   return tmd_check_launch("head_fwd");
 }
 
@@ -356,10 +379,12 @@ int tmd_head_bwd(const float* I, const float* A, const float* S, int N, int F, i
   TMD_REQUIRE(I && A && S && ln_w && W1 && W2 && w3 && std_ && gy && batch && mu_rstd && z1 && z2 && dI && dA && dS, "head_bwd: null pointer");
   if (N == 0) return TMD_OK;
   HeadW P{ln_w, nullptr, nullptr, nullptr, nullptr, nullptr, w3, nullptr, W1, W2, std_, (float)eps};
-  const size_t smem = ((size_t)TA * (2 * (3 * F + 4) + (F + 4) + (H + 4)) + 2 * KC * 256) * sizeof(float);
+  const size_t per_atom = (size_t)((3 * F + 4) + (F + 4) + (H + 4)) * sizeof(float), fixed = (size_t)2 * KC * 256 * sizeof(float);
+  const int nw = pick_tile_warps(N, per_atom, fixed);
+  const size_t smem = (size_t)4 * nw * per_atom + fixed;
   TMD_REQUIRE(smem <= 227 * 1024, "head_bwd: F too large for the tile buffers");
   cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  head_bwd_kernel<<<(N + TA - 1) / TA, HT, smem, (cudaStream_t)stream>>>(CI{I, A, S}, N, F, H, P, gy, batch, M, mu_rstd, z1, z2, MI{dI, dA, dS});
+  head_bwd_kernel<<<(N + 4 * nw - 1) / (4 * nw), 32 * nw, smem, (cudaStream_t)stream>>>(CI{I, A, S}, N, F, H, P, gy, batch, M, mu_rstd, z1, z2, MI{dI, dA, dS});
   return tmd_check_launch("head_bwd");
 }
 

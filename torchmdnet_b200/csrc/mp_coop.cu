@@ -116,7 +116,7 @@ __device__ __forceinline__ void st9(const MIrr& T, long long n, int F, int h, co
 // group exceeds the staged path's capacity (the MP kernels then gather directly for it).  Space is allocated from `cursor`
 // (one int, zeroed by the caller's memset): sum of gcnt <= number of edges.
 __global__ void __launch_bounds__(PLAN_THREADS) mp_plan_kernel(const int* __restrict__ indptr, const int* __restrict__ nbr_j,
-                                                               const int* __restrict__ num_pairs, int max_pairs, int n,
+                                                               const int* __restrict__ num_pairs, int max_pairs, int n, int gs,
                                                                const int* __restrict__ order, const int* __restrict__ order_flag,
                                                                int* __restrict__ rows_out, int* __restrict__ cursor,
                                                                int* __restrict__ union_j, unsigned char* __restrict__ ucount,
@@ -131,15 +131,15 @@ __global__ void __launch_bounds__(PLAN_THREADS) mp_plan_kernel(const int* __rest
   const int E = min(*num_pairs, max_pairs);
   const bool use_order = order && (!order_flag || *order_flag != 0);
   if (tid < G) {
-    const int r = g * G + tid;
+    const int r = g * gs + tid;
     int b = -1, k0 = 0, len = 0;
-    if (r < n) {
+    if (tid < gs && r < n) {
       b = use_order ? order[r] : r;
       k0 = min(indptr[b], E);
       len = min(indptr[b + 1], E) - k0;
     }
     s_row[tid] = b; s_k0[tid] = k0; s_len[tid] = len;
-    if (r < n) rows_out[r] = b;
+    if (tid < gs && r < n) rows_out[r] = b;
   }
   __syncthreads();
   if (tid == 0) {
@@ -292,7 +292,7 @@ __device__ __forceinline__ void producer_loop(uint64_t* full, uint64_t* empty, v
 template <int S, int D, bool POLL>
 __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_fwd_kernel(CIrr Y, const float* __restrict__ f, const int* __restrict__ pid,
                                                                      const int* __restrict__ nbr_j, const int* __restrict__ indptr,
-                                                                     const int* __restrict__ num_pairs, int max_pairs, int n, int F,
+                                                                     const int* __restrict__ num_pairs, int max_pairs, int n, int F, int gs,
                                                                      const int* __restrict__ rows, const int* __restrict__ union_j,
                                                                      const unsigned char* __restrict__ ucount,
                                                                      const unsigned short* __restrict__ upos,
@@ -320,8 +320,8 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_fwd_kernel(CIrr Y, co
     return;
   }
   // ------------------------------------------------------------------------------------ consumer warp = one row
-  const int r = g * G + wid;
-  if (r >= n) return;
+  const int r = g * gs + wid;
+  if (wid >= gs || r >= n) return;
 #ifdef TMD_COOP_PROF
   long long p_f = 0, p_iss = 0, p_full = 0, p_tail = 0;
   const long long p_start = clock64();
@@ -416,7 +416,7 @@ template <int S, int D, bool POLL>
 __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_bwd_kernel(CIrr Y, CIrr dM, const float* __restrict__ f,
                                                                      const float* __restrict__ fp, const int* __restrict__ pid,
                                                                      const int* __restrict__ nbr_j, const int* __restrict__ indptr,
-                                                                     const int* __restrict__ num_pairs, int max_pairs, int n, int F,
+                                                                     const int* __restrict__ num_pairs, int max_pairs, int n, int F, int gs,
                                                                      const int* __restrict__ rows, const int* __restrict__ union_j,
                                                                      const unsigned char* __restrict__ ucount,
                                                                      const unsigned short* __restrict__ upos,
@@ -443,8 +443,8 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_bwd_kernel(CIrr Y, CI
     if (U > 0) producer_loop<S>(full, empty, issued, ring, dM, F, union_j, ucount, off, U, lane);
     return;
   }
-  const int r = g * G + wid;
-  if (r >= n) return;
+  const int r = g * gs + wid;
+  if (wid >= gs || r >= n) return;
   const int b = rows[r];
   const int k0 = min(indptr[b], E), nE = min(indptr[b + 1], E) - k0;
   const int h = lane * 4;
@@ -562,28 +562,44 @@ extern "C" {
 int tmd_mp_coop_set_profile(long long* buf) { cudaMemcpyToSymbol(g_prof, &buf, sizeof(buf)); return 0; }
 #endif
 
-// rows per cooperative group (the plan arrays goff / gcnt have ceil(n / this) entries)
+// largest number of rows per cooperative group (= consumer warps per CTA)
 int tmd_mp_group_size(void) { return G; }
+
+// rows per group for n rows: every launch is one CTA per group on 148 SMs with one resident CTA each, and a group's time is
+// proportional to its rows, so the frame cost is rounds x rows; among G-3 .. G pick the size with the smallest product (a
+// 10 125-atom frame: 15 rows -> 675 groups = 5 rounds (4.56 filled), 14 rows -> 724 groups = 5 rounds (4.89 filled): 7 % less).
+// The plan arrays goff / gcnt have ceil(n / rows) entries.
+int tmd_mp_pick_group(int n) {
+  int best = G; long long best_cost = -1;
+  for (int gs = G; gs >= G - 3 && gs >= 1; --gs) {
+    const long long groups = (n + gs - 1) / gs, rounds = (groups + 147) / 148;
+    const long long cost = rounds * gs;
+    if (best_cost < 0 || cost < best_cost) { best = gs; best_cost = cost; }
+  }
+  return best;
+}
 
 // workspace sizes (elements): rows[n] int, union_j[max_pairs] int, ucount[max_pairs] u8, upos[max_pairs] u16,
 // goff / gcnt [ceil(n / tmd_mp_group_size())] int, cursor[1] int (zeroed by this call)
-int tmd_mp_plan(const int* indptr, const int* nbr_j, const int* num_pairs, int max_pairs, int n, const int* order,
+int tmd_mp_plan(const int* indptr, const int* nbr_j, const int* num_pairs, int max_pairs, int n, int gs, const int* order,
                 const int* order_flag, int* rows, int* cursor, int* union_j, unsigned char* ucount, unsigned short* upos,
                 int* goff, int* gcnt, void* stream) {
   TMD_REQUIRE(indptr && nbr_j && num_pairs && rows && cursor && union_j && ucount && upos && goff && gcnt, "mp_plan: null pointer");
+  TMD_REQUIRE(gs >= 1 && gs <= G, "mp_plan: rows per group must be 1 .. tmd_mp_group_size()");
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(cursor, 0, sizeof(int), st);
   if (n == 0) return tmd_check_launch("mp_plan(empty)");
-  mp_plan_kernel<<<(n + G - 1) / G, PLAN_THREADS, 0, st>>>(indptr, nbr_j, num_pairs, max_pairs, n, order, order_flag, rows, cursor,
+  mp_plan_kernel<<<(n + gs - 1) / gs, PLAN_THREADS, 0, st>>>(indptr, nbr_j, num_pairs, max_pairs, n, gs, order, order_flag, rows, cursor,
                                                           union_j, ucount, upos, goff, gcnt);
   return tmd_check_launch("mp_plan");
 }
 
 int tmd_mp_coop_fwd(const float* YI, const float* YA, const float* YS, const float* f, const int* pid, const int* nbr_j,
-                    const int* indptr, const int* num_pairs, int max_pairs, int n, int F, const int* rows, const int* union_j,
+                    const int* indptr, const int* num_pairs, int max_pairs, int n, int F, int gs, const int* rows, const int* union_j,
                     const unsigned char* ucount, const unsigned short* upos, const int* goff, const int* gcnt, float* MI,
                     float* MA, float* MS, void* stream) {
   TMD_REQUIRE(F > 0 && F % 4 == 0 && F <= 128, "mp_coop_fwd: F must be a multiple of 4, <= 128");
+  TMD_REQUIRE(gs >= 1 && gs <= G, "mp_coop_fwd: rows per group must be 1 .. tmd_mp_group_size()");
   TMD_REQUIRE(YI && YA && YS && f && pid && nbr_j && indptr && num_pairs && rows && union_j && ucount && upos && goff && gcnt && MI && MA && MS,
               "mp_coop_fwd: null pointer");
   if (n == 0) return TMD_OK;
@@ -592,8 +608,8 @@ int tmd_mp_coop_fwd(const float* YI, const float* YA, const float* YS, const flo
   do {                                                                                                                              \
     const size_t smem = CoopSmem<S_, D_, false>::total(F);                                                                          \
     cudaFuncSetAttribute(mp_coop_fwd_kernel<S_, D_, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                    \
-    mp_coop_fwd_kernel<S_, D_, P_><<<(n + G - 1) / G, COOP_THREADS, smem, (cudaStream_t)stream>>>(                                       \
-        CIrr{YI, YA, YS}, f, pid, nbr_j, indptr, num_pairs, max_pairs, n, F, rows, union_j, ucount, upos, goff, gcnt, MIrr{MI, MA, MS}); \
+    mp_coop_fwd_kernel<S_, D_, P_><<<(n + gs - 1) / gs, COOP_THREADS, smem, (cudaStream_t)stream>>>(                                     \
+        CIrr{YI, YA, YS}, f, pid, nbr_j, indptr, num_pairs, max_pairs, n, F, gs, rows, union_j, ucount, upos, goff, gcnt, MIrr{MI, MA, MS}); \
   } while (0)
   if (cfg == 1) TMD_COOP_FWD_LAUNCH(32, 2, false);
   else if (cfg == 2) TMD_COOP_FWD_LAUNCH(32, 3, false);
@@ -605,10 +621,11 @@ int tmd_mp_coop_fwd(const float* YI, const float* YA, const float* YS, const flo
 
 int tmd_mp_coop_bwd(const float* YI, const float* YA, const float* YS, const float* dMI, const float* dMA, const float* dMS,
                     const float* f, const float* fp, const int* pid, const int* nbr_j, const int* indptr, const int* num_pairs,
-                    int max_pairs, int n, int F, const int* rows, const int* union_j, const unsigned char* ucount,
+                    int max_pairs, int n, int F, int gs, const int* rows, const int* union_j, const unsigned char* ucount,
                     const unsigned short* upos, const int* goff, const int* gcnt, float* dYI, float* dYA, float* dYS,
                     float* g_dist, void* stream) {
   TMD_REQUIRE(F > 0 && F % 4 == 0 && F <= 128, "mp_coop_bwd: F must be a multiple of 4, <= 128");
+  TMD_REQUIRE(gs >= 1 && gs <= G, "mp_coop_bwd: rows per group must be 1 .. tmd_mp_group_size()");
   TMD_REQUIRE(YI && YA && YS && dMI && dMA && dMS && f && pid && nbr_j && indptr && num_pairs && rows && union_j && ucount && upos && goff && gcnt && dYI && dYA && dYS,
               "mp_coop_bwd: null pointer");
   TMD_REQUIRE(!fp || g_dist, "mp_coop_bwd: fp given without g_dist");
@@ -618,8 +635,8 @@ int tmd_mp_coop_bwd(const float* YI, const float* YA, const float* YS, const flo
   do {                                                                                                                              \
     const size_t smem = CoopSmem<S_, D_, true>::total(F);                                                                           \
     cudaFuncSetAttribute(mp_coop_bwd_kernel<S_, D_, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                    \
-    mp_coop_bwd_kernel<S_, D_, P_><<<(n + G - 1) / G, COOP_THREADS, smem, (cudaStream_t)stream>>>(                                       \
-        CIrr{YI, YA, YS}, CIrr{dMI, dMA, dMS}, f, fp, pid, nbr_j, indptr, num_pairs, max_pairs, n, F, rows, union_j, ucount, upos,      \
+    mp_coop_bwd_kernel<S_, D_, P_><<<(n + gs - 1) / gs, COOP_THREADS, smem, (cudaStream_t)stream>>>(                                     \
+        CIrr{YI, YA, YS}, CIrr{dMI, dMA, dMS}, f, fp, pid, nbr_j, indptr, num_pairs, max_pairs, n, F, gs, rows, union_j, ucount, upos,      \
         goff, gcnt, MIrr{dYI, dYA, dYS}, g_dist);                                                                                   \
   } while (0)
   if (cfg == 1) TMD_COOP_BWD_LAUNCH(28, 2, false);

@@ -353,7 +353,7 @@ class MessagePassingPlan:
     through `pid`): `forward(Y, f) -> M`, `backward(Y, dM, f, fp) -> (dY, g_dist)`.  bench.py times these two entry points for
     the `roofline` / `roofline_secondary` keys, so the benchmark and the model share one launch path.
 
-    Cooperative path (F <= 128): one `tmd_mp_plan` launch per frame groups the rows 15 by 15 in the neighbour search's cell order
+    Cooperative path (F <= 128): one `tmd_mp_plan` launch per frame groups the rows (12-15 per group, the size that fills the 148 SMs best) in the neighbour search's cell order
     (spatially adjacent atoms share most neighbours) and lists each group's distinct neighbours; the forward / backward kernels
     stage every distinct neighbour row once per group in shared memory.  Results are bit-identical to the warp-per-atom kernels."""
 
@@ -363,7 +363,8 @@ class MessagePassingPlan:
         self.coop = bool(USE_MP_COOP and self.N > 0 and (F is None or (F % 4 == 0 and F <= 128)))
         if self.coop:
             dev, cap, n = g.dist.device, g.dist.shape[0], self.N
-            self.group = int(_lib.library().tmd_mp_group_size())
+            forced = int(os.environ.get("TMD_MP_GROUP", "0"))       # rows per group; default: the size that fills the SM slots best
+            self.group = forced if forced > 0 else int(_lib.library().tmd_mp_pick_group(n))
             ng = -(-n // self.group)
             i32 = dict(device=dev, dtype=torch.int32)
             self.rows = torch.empty(n, **i32)
@@ -373,7 +374,7 @@ class MessagePassingPlan:
             self.goff, self.gcnt = torch.empty(ng, **i32), torch.empty(ng, **i32)
             self.cursor = torch.empty(1, **i32)
             has_order = g.order is not None and g.order.numel() == n
-            _lib.call("tmd_mp_plan", p(g.indptr), p(g.nbr_j), p(g.num_pairs), cap, n, p(g.order) if has_order else None,
+            _lib.call("tmd_mp_plan", p(g.indptr), p(g.nbr_j), p(g.num_pairs), cap, n, self.group, p(g.order) if has_order else None,
                       p(g.order_flag) if has_order else None, p(self.rows), p(self.cursor), p(self.union_j), p(self.ucount),
                       p(self.upos), p(self.goff), p(self.gcnt), device=dev)
 
@@ -400,7 +401,7 @@ class MessagePassingPlan:
         g, x = self.g, self.pidx
         if self._ok(F):
             _lib.call("tmd_mp_coop_fwd", p(YI), p(YA), p(YS), p(f), p(x.pid), p(g.nbr_j), p(g.indptr), p(g.num_pairs), g.dist.shape[0],
-                      N, F, p(self.rows), p(self.union_j), p(self.ucount), p(self.upos), p(self.goff), p(self.gcnt), p(M[0]), p(M[1]),
+                      N, F, self.group, p(self.rows), p(self.union_j), p(self.ucount), p(self.upos), p(self.goff), p(self.gcnt), p(M[0]), p(M[1]),
                       p(M[2]), device=YI.device)
         else:
             _lib.call("tmd_mp_fwd", p(YI), p(YA), p(YS), p(f), p(x.pid), p(g.nbr_j), p(g.indptr), N, F, p(M[0]), p(M[1]), p(M[2]),
@@ -416,7 +417,7 @@ class MessagePassingPlan:
             # every valid slot is written by the kernel; padded slots (static shapes) are never read by the position gradient
             g_dist = torch.empty(g.dist.shape[0], device=YI.device, dtype=torch.float32) if fp is not None else None
             _lib.call("tmd_mp_coop_bwd", p(YI), p(YA), p(YS), p(dM[0]), p(dM[1]), p(dM[2]), p(f), p(fp), p(x.pid), p(g.nbr_j),
-                      p(g.indptr), p(g.num_pairs), g.dist.shape[0], N, F, p(self.rows), p(self.union_j), p(self.ucount), p(self.upos),
+                      p(g.indptr), p(g.num_pairs), g.dist.shape[0], N, F, self.group, p(self.rows), p(self.union_j), p(self.ucount), p(self.upos),
                       p(self.goff), p(self.gcnt), p(dY[0]), p(dY[1]), p(dY[2]), p(g_dist), device=YI.device)
         else:
             g_dist = torch.zeros(g.dist.shape[0], device=YI.device, dtype=torch.float32) if fp is not None else None
@@ -523,7 +524,7 @@ class SpeciesSlots:
 
 
 class EmbedMomentWeights:
-    """Radial projections of the embedding as Wk [3, R+1, F] (k-major, row R = bias) and Wh [3, F, R]; Uz / Vz rows of the element
+    """Radial projections of the embedding as Wk [3, R+1, F] (k-major, row R = bias) and Wh [3, F/4, R, 4]; Uz / Vz rows of the element
     tables for the species present.  Cached per weight version / species set."""
 
     def __init__(self, projs: Sequence[torch.nn.Linear]):
@@ -545,7 +546,8 @@ class EmbedMomentWeights:
             W = torch.stack([m.weight.detach() for m in self.projs], 0)                    # [3, F, R]
             b = torch.stack([m.bias.detach() for m in self.projs], 0)                      # [3, F]
             self._Wk = torch.cat([W.transpose(1, 2), b.unsqueeze(1)], 1).contiguous()      # [3, R+1, F]
-            self._Wh = W.contiguous()
+            F_, R_ = W.shape[1], W.shape[2]
+            self._Wh = W.view(3, F_ // 4, 4, R_).permute(0, 1, 3, 2).contiguous()             # [3, F/4, R, 4]: one float4 per (4 channels, k)
             self._key = key
         return self._Wk, self._Wh
 
@@ -564,7 +566,7 @@ class _EmbeddingMoments(torch.autograd.Function):
     def forward(ctx, dist, vec, zslot, Uz, Vz, Wk, Wh, rbf_mod, lo, hi, g):
         dist_c, vec_c = dist.detach().contiguous(), vec.detach().contiguous()
         means, betas = rbf_mod.means.detach().contiguous(), rbf_mod.betas.detach().contiguous()
-        N, F, R, Z = g.indptr.shape[0] - 1, Uz.shape[-1], Wh.shape[-1], Uz.shape[0]
+        N, F, R, Z = g.indptr.shape[0] - 1, Uz.shape[-1], Wh.shape[2], Uz.shape[0]
         out = _triple(N, F, Uz.device)
         _lib.call("tmd_embed_moments_fwd", p(vec_c), p(dist_c), p(g.nbr_j), p(g.indptr), p(zslot), p(Uz), p(Vz), p(Wk), p(means), p(betas),
                   float(rbf_mod.alpha), float(lo), float(hi), R, N, F, Z, p(out[0]), p(out[1]), p(out[2]), device=Uz.device)
@@ -579,7 +581,7 @@ class _EmbeddingMoments(torch.autograd.Function):
         alpha, lo, hi, N, need = ctx.cfg
         if not need:
             return (None,) * 11
-        F, R, Z = Uz.shape[-1], Wh.shape[-1], Uz.shape[0]
+        F, R, Z = Uz.shape[-1], Wh.shape[2], Uz.shape[0]
         g_dist, g_vec = torch.zeros_like(dist), torch.zeros_like(vec)
         dI, dA, dS = dI.contiguous(), dA.contiguous(), dS.contiguous()
         _lib.call("tmd_embed_moments_bwd", p(vec), p(dist), p(nbr_j), p(indptr), p(zslot), p(Uz), p(Vz), p(Wk), p(Wh), p(means), p(betas),
@@ -743,7 +745,7 @@ class HeadWeights:
     def supported(self) -> bool:
         out_norm, linear, lin_a, lin_b = self.mods
         F, H = linear.out_features, lin_a.out_features
-        smem_bwd = (32 * (2 * (3 * F + 4) + (F + 4) + (H + 4)) + 2 * 16 * 256) * 4      # tile + weight-staging buffers of head_bwd_kernel (csrc/head.cu)
+        smem_bwd = (32 * ((3 * F + 4) + (F + 4) + (H + 4)) + 2 * 8 * 256) * 4      # smallest tile + weight-staging buffers of the head kernels (csrc/head.cu)
         return (linear.in_features == 3 * F and lin_a.in_features == F and lin_b.in_features == H and lin_b.out_features == 1 and
                 F % 32 == 0 and H % 32 == 0 and F <= 256 and H <= 256 and smem_bwd <= 227 * 1024 and out_norm.elementwise_affine and
                 tuple(out_norm.normalized_shape) == (3 * F,) and all(t.dtype == torch.float32 for t in self.params()))
