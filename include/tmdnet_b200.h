@@ -219,8 +219,10 @@ int tmd_mp_coop_fwd(const float* YI, const float* YA, const float* YS, const flo
 int tmd_mp_coop_bwd(const float* YI, const float* YA, const float* YS, const float* dMI, const float* dMA, const float* dMS,
                     const float* f, const float* fp, const int* pid, const int* nbr_j, const int* indptr, const int* num_pairs,
                     int max_pairs, int n, int F, int gs, const int* rows, const int* union_j, const unsigned char* ucount,
-                    const unsigned short* upos, const int* goff, const int* gcnt, float* dYI, float* dYA, float* dYS,
-                    float* g_dist, void* stream);
+                    const unsigned short* upos, const int* goff, const int* gcnt, const float* addI, const float* addA,
+                    const float* addS, float* dYI, float* dYA, float* dYS, float* g_dist, void* stream);
+/* (addI, addA, addS): optional (all NULL or all given) gradient that reached Y along another path (the P2 stage); the kernel stores
+ * dY + add, which replaces the separate accumulation launches of an autograd chain. */
 /* embedding message passing on pair-indexed radial projections dp[P_u,3F] (and their d/dr dpp): the unit vector is formed in the
  * kernel from (vec, dist) of the neighbour list (0 for the self loop, tensornet.py:363-366); U, V are per-atom rows [n,F] when
  * zidx == NULL, else per-element tables [max_z,F] indexed through the atomic numbers zidx[n] (U_i = U[z_i], V_j = V[z_j]).
@@ -247,6 +249,30 @@ int tmd_embed_moments_bwd(const float* vec, const float* dist, const int* nbr_j,
                           const float* Vz, const float* Wk, const float* Wh, const float* means, const float* betas, double alpha,
                           double lo, double hi, int R, int n, int F, int Z, const float* dI, const float* dA, const float* dS,
                           float* g_dist, float* g_vec, void* stream);
+
+/* ---- a5, per-atom part of TensorEmbedding (csrc/atom_mlp.cu; models/tensornet.py:588-619) ------------------------------------
+ * tmd_embed_mlp_fwd: (oI, oA, oS) = (cI, cA, cS) * g[type] with g = SiLU(W2 SiLU(W1 LayerNorm_F(|X|^2) + b1) + b2) in R^{3F},
+ * X = (I, A, S) the un-normalised embedding, c = the node-linear output (tmd_irreps_linear_tc).  W1T [F,2F], W2T [2F,3F]
+ * transposed nn.Linear weights; saves (mu, rstd) [N,2] and the pre-activations z1 [N,2F], z2 [N,3F].
+ * tmd_gate_bwd_preact (tensor_ops.cu): gate backward with the gate given as its pre-activation z = z2: g = SiLU(z); returns the
+ * gradient of c (gI, gA, gS) and of the gates dg [N,3F].
+ * tmd_embed_mlp_bwd: gX = add + d/dX of the gate path for the gate gradient dg; W1 [2F,F], W2 [3F,2F] untransposed; the add triple
+ * (all NULL or all given) is the gradient that reached X through the node linears.  F % 32 == 0, F <= 256. */
+int tmd_embed_mlp_fwd(const float* I, const float* A, const float* S, const float* cI, const float* cA, const float* cS, int N, int F,
+                      const float* ln_w, const float* ln_b, double eps, const float* W1T, const float* b1, const float* W2T,
+                      const float* b2, float* oI, float* oA, float* oS, float* mu_rstd, float* z1, float* z2, void* stream);
+int tmd_gate_bwd_preact(const float* I, const float* A, const float* S, const float* z, const float* dI, const float* dA, const float* dS,
+                        float* gI, float* gA, float* gS, float* dg, int N, int F, void* stream);
+int tmd_embed_mlp_bwd(const float* I, const float* A, const float* S, int N, int F, const float* ln_w, double eps, const float* W1,
+                      const float* W2, const float* dg, const float* mu_rstd, const float* z1, const float* z2, const float* addI,
+                      const float* addA, const float* addS, float* gI, float* gA, float* gS, void* stream);
+/* P1 backward with the incoming gradient given as two tensors (d1 + d2), and P3 backward for the dX branch only (the Xn branch of
+ * X' = Xn + dX + qf dX.dX is the identity): what the hand-sequenced backward of one interaction layer needs
+ * (extensions/fused.py::_InteractionLayer; models/tensornet.py:745, :812). */
+int tmd_p1_bwd2(const float* I, const float* A, const float* S, const float* d1I, const float* d1A, const float* d1S, const float* d2I,
+                const float* d2A, const float* d2S, float* gI, float* gA, float* gS, int N, int F, void* stream);
+int tmd_p3_bwd_dx(const float* DI, const float* DA, const float* DS, const float* qf, const float* dI, const float* dA, const float* dS,
+                  float* gDI, float* gDA, float* gDS, int N, int F, void* stream);
 
 /* ---- a10 + a11: TensorNet tail + Scalar head + per-molecule reduction (csrc/head.cu) -------------------------------------
  * Replaces tensor_norm3 -> LayerNorm(3F) -> Linear(3F->F) -> SiLU (models/tensornet.py:394-402), Scalar.pre_reduce = MLP

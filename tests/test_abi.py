@@ -35,6 +35,23 @@ def test_header_symbols_exported(lib):
     assert lib.tmd_abi_version() == 1
 
 
+def test_ctypes_signatures_match_header_prototypes():
+    """every entry of _lib.SIGNATURES declares exactly the argument kinds of its prototype in include/tmdnet_b200.h (pointer /
+    int / double / long long, the trailing stream included).  An entry that is one argument short still *works* through ctypes:
+    the extra value is converted with the default rule (a 32-bit int), which truncates a 64-bit stream handle -- harmless on the
+    default stream (0), a wild pointer inside cudaLaunchKernel on any other one."""
+    from torchmdnet_b200 import _lib
+    txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "tmdnet_b200.h")).read(), flags=re.S)
+    kind = {_lib.P: "P", _lib.I: "I", _lib.D: "D", _lib.LL: "L"}
+    for name, (argtypes, _) in _lib.SIGNATURES.items():
+        m = re.search(r"\bint\s+" + name + r"\s*\(([^;]*?)\)\s*;", txt, flags=re.S)
+        assert m, f"{name}: no prototype in the header"
+        params = [q.strip() for q in m.group(1).split(",") if q.strip() and q.strip() != "void"]
+        want = ["P" if "*" in q else "D" if q.startswith("double") else "L" if q.startswith("long long") else "I" for q in params]
+        got = [kind[a] for a in argtypes]
+        assert got == want, f"{name}: _lib.py declares {''.join(got)} ({len(got)}), the header {''.join(want)} ({len(want)})"
+
+
 def test_operator_surface_matches_reference():
     from torchmdnet_b200.extensions import ops, tensornet_ops
     sig = inspect.signature(ops.get_neighbor_pairs_kernel)

@@ -58,7 +58,7 @@ SIGNATURES = {
     "tmd_pair_chain": ([P, P, I, P, P, P, P, P, P, P, I, I, I, P, P, D, D, D, P, P, P], 1),
     "tmd_pair_chain_tc": ([P, P, I, P, P, P, P, I, I, I, P, P, D, D, D, P, P, P, P, P, P, P, P, I, P], 3),
     "tmd_irreps_linear_tc": ([P, P, P, I, I, P, P, P, P, P, P], 1),
-    "tmd_radial_table": ([P, P, I, P, I, D, I, P, P], 1),
+    "tmd_radial_table": ([P, P, I, P, I, D, I, P, P, P], 1),
     "tmd_pair_rbf_split": ([P, P, I, I, I, P, P, D, D, D, P, P, I, P], 1),
     "tmd_mp_pair_bwd": ([P] * 11 + [I, I] + [P] * 4 + [P], 1),
     "tmd_et_msg_fwd": ([P] * 10 + [D, D, I, I, I, I, P, P, P], 1),
@@ -70,12 +70,17 @@ SIGNATURES = {
     "tmd_mp_pick_group": ([I], 0),
     "tmd_mp_plan": ([P, P, P, I, I, I, P, P, P, P, P, P, P, P, P, P], 1),
     "tmd_mp_coop_fwd": ([P] * 8 + [I, I, I, I] + [P] * 9 + [P], 1),
-    "tmd_mp_coop_bwd": ([P] * 12 + [I, I, I, I] + [P] * 10 + [P], 1),
+    "tmd_mp_coop_bwd": ([P] * 12 + [I, I, I, I] + [P] * 13 + [P], 1),
     "tmd_head_fwd": ([P, P, P, I, I, I, P, P, D] + [P] * 9 + [I] + [P] * 4 + [P], 1),
     "tmd_segment_sum": ([P, P, I, I, P, P, P, P], 2),
     "tmd_head_bwd": ([P, P, P, I, I, I, P, D] + [P] * 6 + [I] + [P] * 6 + [P], 1),
     "tmd_embed_fwd": ([P] * 9 + [D, D, I, I] + [P] * 3 + [P], 1),
     "tmd_embed_bwd": ([P] * 10 + [D, D, I, I] + [P] * 5 + [P], 1),
+    "tmd_gate_bwd_preact": ([P] * 11 + [I, I, P], 1),
+    "tmd_p1_bwd2": ([P] * 12 + [I, I, P], 1),
+    "tmd_p3_bwd_dx": ([P] * 10 + [I, I, P], 1),
+    "tmd_embed_mlp_fwd": ([P] * 6 + [I, I, P, P, D] + [P] * 10 + [P], 1),
+    "tmd_embed_mlp_bwd": ([P, P, P, I, I, P, D] + [P] * 12 + [P], 1),
     "tmd_embed_moments_fwd": ([P] * 10 + [D, D, D, I, I, I, I] + [P] * 3 + [P], 1),
     "tmd_embed_moments_bwd": ([P] * 11 + [D, D, D, I, I, I, I] + [P] * 5 + [P], 1),
 }

@@ -6,18 +6,17 @@
 // (output_modules.py:43-73, models/utils.py:671-701) -> + mean (models/model.py:590-610); in round 1 this was one own kernel
 // (norm3c) + LayerNorm + 3 cuBLAS SIMT SGEMMs + SiLU/fill/add/scatter launches of torch and their autograd mirrors.
 //
-// Here: ONE forward kernel per 32-atom tile (norm3 -> LN -> two FFMA GEMM layers with the weights read k-major from L2 ->
-// per-atom energy), one deterministic segmented sum, ONE backward kernel (dE/de_i = gy[batch] * std seeded by the caller's
-// grad, back through the MLP with the saved pre-activations, LayerNorm backward, norm3 backward -> dI, dA, dS).  The work
-// is ~2.4 GFLOP per C4 frame: latency-, not throughput-bound, so plain fp32 FFMA (exact fp32 parity, no operand split).
+// Here: ONE forward kernel per 32-atom tile (norm3 -> LN -> two GEMM layers on the tile, weights streamed k-major through shared
+// memory, 3xTF32 warp-level tensor-core MMAs with fp32 parity: mlp_tile.cuh -> per-atom energy), one deterministic segmented sum,
+// ONE backward kernel (dE/de_i = gy[batch] * std seeded by the caller's grad, back through the MLP with the saved
+// pre-activations, LayerNorm backward, norm3 backward -> dI, dA, dS).  The work is ~2.4 GFLOP per C4 frame.
 // Weight gradients are not produced (inference / frozen weights); training keeps the autograd-composed torch path.
 #include "common.cuh"
+#include "mlp_tile.cuh"
 
 namespace {
 
-constexpr int HT_MAX = 320;  // threads per CTA: nw = 8..10 warps, warp w owns atoms 4w .. 4w+3 in the GEMM stages (TA = 4 nw atoms per CTA;
-                             // the host picks nw so that the grid fits the resident CTA slots in as few rounds as possible)
-constexpr int MAXC = 8;      // output columns per lane and pass: widths up to 256
+using mlp::TA; using mlp::HT; using mlp::MAXNT;
 
 struct CI { const float* I; const float* A; const float* S; };
 struct MI { float* I; float* A; float* S; };
@@ -30,61 +29,6 @@ __device__ __forceinline__ void ld_c(const CI& t, long long n, int F, int h, flo
   for (int k = 0; k < 5; ++k) c[4 + k] = t.S[(n * 5 + k) * F + h];
 }
 
-// acc[q][c] += sum_k in_s[(4 wy + q) * ld + k] * W[k * ldw + lane + 32 c]   for c < ncol  (K % KC == 0)
-// W is streamed through shared memory in chunks of KC rows with cp.async double buffering: every CTA reads each weight row
-// once, coalesced, KC rows ahead of its use.  (Reading W straight from global in the inner loop made all ~300 CTAs hit the same
-// 512-byte row of L2 at the same time with the full L2 latency exposed per k-step: 220 us instead of ~20 us for the forward.)
-constexpr int KC = 8;
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void stage_w(float* wb, const float* __restrict__ W, int ldw, int k0, int nc4, int tid) {
-  // KC rows x nc4 float4 columns of W -> wb [KC][4 nc4]
-  for (int i = tid; i < KC * nc4; i += blockDim.x) {
-    const int r = i / nc4, c = i - r * nc4;
-    cp_async16(wb + (size_t)r * 4 * nc4 + 4 * c, W + (size_t)(k0 + r) * ldw + 4 * c);
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void tile_gemm(const float* __restrict__ in_s, int ld, int K, const float* __restrict__ W, int ldw,
-                                          int ncol, float (&acc)[4][MAXC], float* wbuf, int wy, int lane, int tid) {
-  const int NC = 32 * ncol, nc4 = NC >> 2;
-  const float* a0 = in_s + (4 * wy) * ld;
-  stage_w(wbuf, W, ldw, 0, nc4, tid);
-  for (int k0 = 0, it = 0; k0 < K; k0 += KC, ++it) {
-    float* cur = wbuf + (size_t)(it & 1) * KC * NC;
-    if (k0 + KC < K) {
-      stage_w(wbuf + (size_t)((it + 1) & 1) * KC * NC, W, ldw, k0 + KC, nc4, tid);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < KC; k += 4) {
-      float4 a[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) a[q] = *reinterpret_cast<const float4*>(a0 + q * ld + k0 + k);
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const float* wrow = cur + (size_t)(k + kk) * NC + lane;
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c) {
-          if (c < ncol) {
-            const float b = wrow[32 * c];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float x = kk == 0 ? a[q].x : kk == 1 ? a[q].y : kk == 2 ? a[q].z : a[q].w;
-              acc[q][c] = fmaf(x, b, acc[q][c]);
-            }
-          }
-        }
-      }
-    }
-    __syncthreads();   // the buffer is refilled two chunks later
-  }
-}
-
 struct HeadW {
   const float* ln_w; const float* ln_b;   // [3F]   representation_model.out_norm
   const float* W1T; const float* b1;      // [3F][F], [F]    representation_model.linear (transposed)
@@ -95,13 +39,12 @@ struct HeadW {
   float eps;
 };
 
-// shared memory (TA = 4 x warps): xs [TA][3F+4] | h1s [TA][F+4] | h2s [TA][H+4] | wbuf [2][KC][256] (weight staging)
-__global__ void __launch_bounds__(HT_MAX) head_fwd_kernel(CI X, int N, int F, int H, HeadW P, const int64_t* __restrict__ z,
+// shared memory: xs [TA][3F+4] | h1s [TA][F+4] | h2s [TA][H+4] | wbuf [3][KC][max(F,H)+8] (weight staging, mlp_tile.cuh)
+__global__ void __launch_bounds__(HT, 2) head_fwd_kernel(CI X, int N, int F, int H, HeadW P, const int64_t* __restrict__ z,
                                                       const float* __restrict__ atomref, int n_ref, float* __restrict__ e_out,
                                                       float* __restrict__ mu_rstd, float* __restrict__ z1, float* __restrict__ z2) {
   extern __shared__ __align__(16) float sm[];
   const int ldx = 3 * F + 4, ld1 = F + 4, ld2 = H + 4;
-  const int HT = blockDim.x, TA = HT >> 3;
   float* xs = sm; float* h1s = xs + TA * ldx; float* h2s = h1s + TA * ld1; float* wbuf = h2s + TA * ld2;
   const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
   const long long a0 = (long long)blockIdx.x * TA;
@@ -113,7 +56,7 @@ __global__ void __launch_bounds__(HT_MAX) head_fwd_kernel(CI X, int N, int F, in
     xs[a * ldx + h] = o[0]; xs[a * ldx + F + h] = o[1]; xs[a * ldx + 2 * F + h] = o[2];
   }
   __syncthreads();
-  // 2. LayerNorm over 3F (two-pass, biased variance), in place
+  // 2. LayerNorm over 3F (two-pass, biased variance), in place; warp w owns atoms 4w .. 4w+3
   for (int q = 0; q < 4; ++q) {
     const int a = 4 * wy + q;
     float* row = xs + a * ldx;
@@ -127,49 +70,24 @@ __global__ void __launch_bounds__(HT_MAX) head_fwd_kernel(CI X, int N, int F, in
     if (lane == 0 && a0 + a < N) { mu_rstd[2 * (a0 + a)] = mu; mu_rstd[2 * (a0 + a) + 1] = rstd; }
   }
   __syncthreads();
+  float acc[2][MAXNT][4];
   // 3. h1 = SiLU(W1 xn + b1)
-  {
-    const int ncol = F >> 5;
-    float acc[4][MAXC];
-#pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
-      const float b = c < ncol ? __ldg(P.b1 + lane + 32 * c) : 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q][c] = b;
-    }
-    tile_gemm(xs, ldx, 3 * F, P.W1T, F, ncol, acc, wbuf, wy, lane, tid);
-#pragma unroll
-    for (int c = 0; c < MAXC; ++c)
-      if (c < ncol)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int a = 4 * wy + q, col = lane + 32 * c;
-          if (a0 + a < N) z1[(a0 + a) * F + col] = acc[q][c];
-          h1s[a * ld1 + col] = tn::silu(acc[q][c]);
-        }
-  }
+  mlp::zero_acc(acc);
+  mlp::tile_gemm_tc(xs, ldx, 3 * F, P.W1T, F, F, acc, wbuf, wy, lane, tid);
+  mlp::for_each_acc(acc, F, wy, lane, [&](int row, int col, float& v) {
+    const float zz = v + __ldg(P.b1 + col);
+    if (a0 + row < N) z1[(a0 + row) * F + col] = zz;
+    h1s[row * ld1 + col] = tn::silu(zz);
+  });
   __syncthreads();
   // 4. h2 = SiLU(W2 h1 + b2)
-  {
-    const int ncol = H >> 5;
-    float acc[4][MAXC];
-#pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
-      const float b = c < ncol ? __ldg(P.b2 + lane + 32 * c) : 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q][c] = b;
-    }
-    tile_gemm(h1s, ld1, F, P.W2T, H, ncol, acc, wbuf, wy, lane, tid);
-#pragma unroll
-    for (int c = 0; c < MAXC; ++c)
-      if (c < ncol)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int a = 4 * wy + q, col = lane + 32 * c;
-          if (a0 + a < N) z2[(a0 + a) * H + col] = acc[q][c];
-          h2s[a * ld2 + col] = tn::silu(acc[q][c]);
-        }
-  }
+  mlp::zero_acc(acc);
+  mlp::tile_gemm_tc(h1s, ld1, F, P.W2T, H, H, acc, wbuf, wy, lane, tid);
+  mlp::for_each_acc(acc, H, wy, lane, [&](int row, int col, float& v) {
+    const float zz = v + __ldg(P.b2 + col);
+    if (a0 + row < N) z2[(a0 + row) * H + col] = zz;
+    h2s[row * ld2 + col] = tn::silu(zz);
+  });
   __syncthreads();
   // 5. e_i = (w3 . h2 + b3) * std + atomref[z_i]
   for (int q = 0; q < 4; ++q) {
@@ -185,15 +103,13 @@ __global__ void __launch_bounds__(HT_MAX) head_fwd_kernel(CI X, int N, int F, in
   }
 }
 
-// shared memory (TA = 4 x warps): dxs [TA][3F+4] | d1s [TA][F+4] | d2s [TA][H+4] | wbuf [2][KC][256].  The pre-LayerNorm norms
-// (xhat of the LayerNorm backward) are recomputed from the node tensors instead of being kept in a second [TA][3F] tile: the
-// smaller footprint lets two CTAs share an SM.
-__global__ void __launch_bounds__(HT_MAX) head_bwd_kernel(CI X, int N, int F, int H, HeadW P, const float* __restrict__ gy,
+// shared memory: dxs [TA][3F+4] | d1s [TA][F+4] | d2s [TA][H+4] | wbuf.  The pre-LayerNorm norms (xhat of the LayerNorm backward)
+// are recomputed from the node tensors instead of being kept in a second [TA][3F] tile: two CTAs share an SM.
+__global__ void __launch_bounds__(HT, 2) head_bwd_kernel(CI X, int N, int F, int H, HeadW P, const float* __restrict__ gy,
                                                       const int64_t* __restrict__ batch, int M, const float* __restrict__ mu_rstd,
                                                       const float* __restrict__ z1, const float* __restrict__ z2, MI dX) {
   extern __shared__ __align__(16) float sm[];
   const int ldx = 3 * F + 4, ld1 = F + 4, ld2 = H + 4;
-  const int HT = blockDim.x, TA = HT >> 3;
   float* dxs = sm; float* d1s = dxs + TA * ldx; float* d2s = d1s + TA * ld1; float* wbuf = d2s + TA * ld2;
   const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
   const long long a0 = (long long)blockIdx.x * TA;
@@ -210,43 +126,22 @@ __global__ void __launch_bounds__(HT_MAX) head_bwd_kernel(CI X, int N, int F, in
     d2s[a * ld2 + c] = v;
   }
   __syncthreads();
+  float acc[2][MAXNT][4];
   // dz1 = (dz2 . W2) * SiLU'(z1)
-  {
-    const int ncol = F >> 5;
-    float acc[4][MAXC];
-#pragma unroll
-    for (int c = 0; c < MAXC; ++c)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q][c] = 0.f;
-    tile_gemm(d2s, ld2, H, P.W2, F, ncol, acc, wbuf, wy, lane, tid);
-#pragma unroll
-    for (int c = 0; c < MAXC; ++c)
-      if (c < ncol)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int a = 4 * wy + q, col = lane + 32 * c;
-          const float zz = (a0 + a < N) ? z1[(a0 + a) * F + col] : 0.f;
-          d1s[a * ld1 + col] = acc[q][c] * tn::silu_grad(zz);
-        }
-  }
+  mlp::zero_acc(acc);
+  mlp::tile_gemm_tc(d2s, ld2, H, P.W2, F, F, acc, wbuf, wy, lane, tid);
+  mlp::for_each_acc(acc, F, wy, lane, [&](int row, int col, float& v) {
+    const float zz = (a0 + row < N) ? z1[(a0 + row) * F + col] : 0.f;
+    d1s[row * ld1 + col] = v * tn::silu_grad(zz);
+  });
   __syncthreads();
   // dxn = dz1 . W1, in three column blocks of F; g = dxn * gamma
   for (int blk = 0; blk < 3; ++blk) {
-    const int ncol = F >> 5;
-    float acc[4][MAXC];
-#pragma unroll
-    for (int c = 0; c < MAXC; ++c)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q][c] = 0.f;
-    tile_gemm(d1s, ld1, F, P.W1 + blk * F, 3 * F, ncol, acc, wbuf, wy, lane, tid);
-#pragma unroll
-    for (int c = 0; c < MAXC; ++c)
-      if (c < ncol)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int col = blk * F + lane + 32 * c;
-          dxs[(4 * wy + q) * ldx + col] = acc[q][c] * __ldg(P.ln_w + col);
-        }
+    mlp::zero_acc(acc);
+    mlp::tile_gemm_tc(d1s, ld1, F, P.W1 + blk * F, 3 * F, F, acc, wbuf, wy, lane, tid);
+    mlp::for_each_acc(acc, F, wy, lane, [&](int row, int col, float& v) {
+      dxs[row * ldx + blk * F + col] = v * __ldg(P.ln_w + blk * F + col);
+    });
   }
   __syncthreads();
   // LayerNorm backward per atom, dx = rstd (g - mean(g) - xhat mean(g xhat)), fused with the norm3 backward -> dI, dA, dS.
@@ -268,7 +163,7 @@ __global__ void __launch_bounds__(HT_MAX) head_bwd_kernel(CI X, int N, int F, in
       }
     }
     s1 = warp_sum(s1) / (float)(3 * F); s2 = warp_sum(s2) / (float)(3 * F);
-    for (int h = lane; h < F; h += 32) {     // second pass: the row comes from L1 this time
+    for (int h = lane; h < F; h += 32) {
       float c[9], o[3], dn[3], dc[9];
       ld_c(X, n, F, h, c); tn::norm3_compact(c, o);
 #pragma unroll
@@ -319,24 +214,6 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const float* __restric
   }
 }
 
-// warps per CTA (8..10; 4 atoms per warp): the tile size that covers the N atoms in the fewest rounds of resident CTAs
-// (148 SMs x CTAs that fit the shared memory), ties -> fewer atom-slots of work, i.e. the smaller rounds x tile product
-int pick_tile_warps(int N, size_t per_atom_bytes, size_t fixed_bytes) {
-  int best = 8; long long best_cost = -1;
-  for (int nw = 8; nw <= HT_MAX / 32; ++nw) {
-    const size_t smem = (size_t)4 * nw * per_atom_bytes + fixed_bytes;
-    if (smem > 227 * 1024) break;
-    int per_sm = (int)((size_t)(228 * 1024) / (smem + 1024));
-    const int by_threads = 2048 / (32 * nw);
-    if (per_sm > by_threads) per_sm = by_threads;
-    if (per_sm < 1) per_sm = 1;
-    const long long tiles = (N + 4 * nw - 1) / (4 * nw), slots = 148LL * per_sm;
-    const long long cost = ((tiles + slots - 1) / slots) * (4 * nw) * (per_sm > 1 ? 3 : 4);   // co-resident CTAs hide each other's barriers
-    if (best_cost < 0 || cost < best_cost) { best = nw; best_cost = cost; }
-  }
-  return best;
-}
-
 }  // namespace
 
 extern "C" {
@@ -347,16 +224,14 @@ int tmd_head_fwd(const float* I, const float* A, const float* S, int N, int F, i
                  double eps, const float* W1T, const float* b1, const float* W2T, const float* b2, const float* w3,
                  const float* b3, const float* std_, const int64_t* z, const float* atomref, int n_ref, float* e,
                  float* mu_rstd, float* z1, float* z2, void* stream) {
-  TMD_REQUIRE(F > 0 && F % 32 == 0 && F <= 256 && H > 0 && H % 32 == 0 && H <= 256 && H % KC == 0, "head_fwd: F, H must be multiples of 32, <= 256");
+  TMD_REQUIRE(F > 0 && F % 32 == 0 && F <= 256 && H > 0 && H % 32 == 0 && H <= 256, "head_fwd: F, H must be multiples of 32, <= 256");
   TMD_REQUIRE(I && A && S && ln_w && ln_b && W1T && b1 && W2T && b2 && w3 && b3 && std_ && e && mu_rstd && z1 && z2, "head_fwd: null pointer");
   TMD_REQUIRE(!atomref || z, "head_fwd: atomref without z");
   if (N == 0) return TMD_OK;
   HeadW P{ln_w, ln_b, W1T, b1, W2T, b2, w3, b3, nullptr, nullptr, std_, (float)eps};
-  const size_t per_atom = (size_t)((3 * F + 4) + (F + 4) + (H + 4)) * sizeof(float), fixed = (size_t)2 * KC * 256 * sizeof(float);
-  const int nw = pick_tile_warps(N, per_atom, fixed);
-  const size_t smem = (size_t)4 * nw * per_atom + fixed;
+  const size_t smem = ((size_t)TA * ((3 * F + 4) + (F + 4) + (H + 4)) + mlp::wbuf_floats(F > H ? F : H)) * sizeof(float);
   cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  head_fwd_kernel<<<(N + 4 * nw - 1) / (4 * nw), 32 * nw, smem, (cudaStream_t)stream>>>(CI{I, A, S}, N, F, H, P, z, atomref, n_ref, e, mu_rstd, z1, z2);
+  head_fwd_kernel<<<(N + TA - 1) / TA, HT, smem, (cudaStream_t)stream>>>(CI{I, A, S}, N, F, H, P, z, atomref, n_ref, e, mu_rstd, z1, z2);
   return tmd_check_launch("head_fwd");
 }
 
@@ -379,12 +254,10 @@ int tmd_head_bwd(const float* I, const float* A, const float* S, int N, int F, i
   TMD_REQUIRE(I && A && S && ln_w && W1 && W2 && w3 && std_ && gy && batch && mu_rstd && z1 && z2 && dI && dA && dS, "head_bwd: null pointer");
   if (N == 0) return TMD_OK;
   HeadW P{ln_w, nullptr, nullptr, nullptr, nullptr, nullptr, w3, nullptr, W1, W2, std_, (float)eps};
-  const size_t per_atom = (size_t)((3 * F + 4) + (F + 4) + (H + 4)) * sizeof(float), fixed = (size_t)2 * KC * 256 * sizeof(float);
-  const int nw = pick_tile_warps(N, per_atom, fixed);
-  const size_t smem = (size_t)4 * nw * per_atom + fixed;
+  const size_t smem = ((size_t)TA * ((3 * F + 4) + (F + 4) + (H + 4)) + mlp::wbuf_floats(F > H ? F : H)) * sizeof(float);
   TMD_REQUIRE(smem <= 227 * 1024, "head_bwd: F too large for the tile buffers");
   cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  head_bwd_kernel<<<(N + 4 * nw - 1) / (4 * nw), 32 * nw, smem, (cudaStream_t)stream>>>(CI{I, A, S}, N, F, H, P, gy, batch, M, mu_rstd, z1, z2, MI{dI, dA, dS});
+  head_bwd_kernel<<<(N + TA - 1) / TA, HT, smem, (cudaStream_t)stream>>>(CI{I, A, S}, N, F, H, P, gy, batch, M, mu_rstd, z1, z2, MI{dI, dA, dS});
   return tmd_check_launch("head_bwd");
 }
 

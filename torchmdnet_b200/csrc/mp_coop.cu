@@ -83,6 +83,7 @@ __device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c) {
 __device__ __forceinline__ float4 mul4(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 struct CIrr { const float* I; const float* A; const float* S; };
 struct MIrr { float* I; float* A; float* S; };
@@ -421,7 +422,7 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_bwd_kernel(CIrr Y, CI
                                                                      const unsigned char* __restrict__ ucount,
                                                                      const unsigned short* __restrict__ upos,
                                                                      const int* __restrict__ goff, const int* __restrict__ gcnt,
-                                                                     MIrr dY, float* __restrict__ g_dist) {
+                                                                     CIrr add, MIrr dY, float* __restrict__ g_dist) {
   extern __shared__ __align__(128) unsigned char smem[];
   using L = CoopSmem<S, D, true>;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -478,7 +479,7 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_bwd_kernel(CIrr Y, CI
         if (lane == 0) g_dist[k] = (j == b) ? 0.f : t;
       }
     }
-    if (on) st9(dY, b, F, h, acc);
+    if (on) { if (add.I) { float4 ad[9]; ld9(add, b, F, h, ad); for (int c = 0; c < 9; ++c) acc[c] = add4(acc[c], ad[c]); } st9(dY, b, F, h, acc); }
     return;
   }
   float* myf = fring + (size_t)wid * D * 6 * F;
@@ -551,7 +552,15 @@ __global__ void __launch_bounds__(COOP_THREADS, 1) mp_coop_bwd_kernel(CIrr Y, CI
     pid_n = e0 + 64 + lane < nE ? pid[k0 + e0 + 64 + lane] : 0;
     up_n = e0 + 64 + lane < nE ? (int)upos[k0 + e0 + 64 + lane] : 0;
   }
-  if (on) st9(dY, b, F, h, acc);
+  if (on) {
+    if (add.I) {   // gradient that reached Y_b along another path (P2): summed here instead of by a separate launch
+      float4 ad[9];
+      ld9(add, b, F, h, ad);
+#pragma unroll
+      for (int c = 0; c < 9; ++c) acc[c] = add4(acc[c], ad[c]);
+    }
+    st9(dY, b, F, h, acc);
+  }
 }
 
 }  // namespace
@@ -622,13 +631,14 @@ int tmd_mp_coop_fwd(const float* YI, const float* YA, const float* YS, const flo
 int tmd_mp_coop_bwd(const float* YI, const float* YA, const float* YS, const float* dMI, const float* dMA, const float* dMS,
                     const float* f, const float* fp, const int* pid, const int* nbr_j, const int* indptr, const int* num_pairs,
                     int max_pairs, int n, int F, int gs, const int* rows, const int* union_j, const unsigned char* ucount,
-                    const unsigned short* upos, const int* goff, const int* gcnt, float* dYI, float* dYA, float* dYS,
-                    float* g_dist, void* stream) {
+                    const unsigned short* upos, const int* goff, const int* gcnt, const float* addI, const float* addA,
+                    const float* addS, float* dYI, float* dYA, float* dYS, float* g_dist, void* stream) {
   TMD_REQUIRE(F > 0 && F % 4 == 0 && F <= 128, "mp_coop_bwd: F must be a multiple of 4, <= 128");
   TMD_REQUIRE(gs >= 1 && gs <= G, "mp_coop_bwd: rows per group must be 1 .. tmd_mp_group_size()");
   TMD_REQUIRE(YI && YA && YS && dMI && dMA && dMS && f && pid && nbr_j && indptr && num_pairs && rows && union_j && ucount && upos && goff && gcnt && dYI && dYA && dYS,
               "mp_coop_bwd: null pointer");
   TMD_REQUIRE(!fp || g_dist, "mp_coop_bwd: fp given without g_dist");
+  TMD_REQUIRE((addI && addA && addS) || (!addI && !addA && !addS), "mp_coop_bwd: the add triple is all-or-nothing");
   if (n == 0) return TMD_OK;
   static const int cfg = getenv("TMD_COOP_BWD") ? atoi(getenv("TMD_COOP_BWD")) : 0;
 #define TMD_COOP_BWD_LAUNCH(S_, D_, P_)                                                                                                  \
@@ -637,7 +647,7 @@ int tmd_mp_coop_bwd(const float* YI, const float* YA, const float* YS, const flo
     cudaFuncSetAttribute(mp_coop_bwd_kernel<S_, D_, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                    \
     mp_coop_bwd_kernel<S_, D_, P_><<<(n + gs - 1) / gs, COOP_THREADS, smem, (cudaStream_t)stream>>>(                                     \
         CIrr{YI, YA, YS}, CIrr{dMI, dMA, dMS}, f, fp, pid, nbr_j, indptr, num_pairs, max_pairs, n, F, gs, rows, union_j, ucount, upos,      \
-        goff, gcnt, MIrr{dYI, dYA, dYS}, g_dist);                                                                                   \
+        goff, gcnt, CIrr{addI, addA, addS}, MIrr{dYI, dYA, dYS}, g_dist);                                                                                 \
   } while (0)
   if (cfg == 1) TMD_COOP_BWD_LAUNCH(28, 2, false);
   else if (cfg == 2) TMD_COOP_BWD_LAUNCH(20, 2, false);

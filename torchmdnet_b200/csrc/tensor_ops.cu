@@ -144,11 +144,39 @@ __global__ void gate_bwd_k(CI c, const float* g, CI dout, MI dc, float* dg, int 
     st_c(dc, n, F, h, d);
   }
 }
+// gate backward with the gate given as its pre-activation: g = SiLU(z) (z = z2 of the embedding MLP, csrc/atom_mlp.cu)
+__global__ void gate_bwd_preact_k(CI c, const float* z, CI dout, MI dc, float* dg, int N, int F) {
+  TMD_FOR_NH(n, h) {
+    float cc[9], d[9]; ld_c(c, n, F, h, cc); ld_c(dout, n, F, h, d);
+    const float g0 = tn::silu(z[n * 3 * F + h]), g1 = tn::silu(z[n * 3 * F + F + h]), g2 = tn::silu(z[n * 3 * F + 2 * F + h]);
+    float s0 = d[0] * cc[0], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) s1 += d[k] * cc[k];
+#pragma unroll
+    for (int k = 4; k < 9; ++k) s2 += d[k] * cc[k];
+    dg[n * 3 * F + h] = s0; dg[n * 3 * F + F + h] = s1; dg[n * 3 * F + 2 * F + h] = s2;
+    d[0] *= g0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) d[k] *= g1;
+#pragma unroll
+    for (int k = 4; k < 9; ++k) d[k] *= g2;
+    st_c(dc, n, F, h, d);
+  }
+}
 __global__ void p1_fwd_k(CI c, MI out, int N, int F) {
   TMD_FOR_NH(n, h) { float cc[9], o[9]; ld_c(c, n, F, h, cc); tn::p1_fwd(cc, o); st_c(out, n, F, h, o); }
 }
 __global__ void p1_bwd_k(CI c, CI dout, MI dc, int N, int F) {
   TMD_FOR_NH(n, h) { float cc[9], d[9], g[9]; ld_c(c, n, F, h, cc); ld_c(dout, n, F, h, d); tn::p1_bwd(cc, d, g); st_c(dc, n, F, h, g); }
+}
+// the same with the incoming gradient given as the sum of two tensors (the layer's own residual path + the node-linear path)
+__global__ void p1_bwd2_k(CI c, CI d1, CI d2, MI dc, int N, int F) {
+  TMD_FOR_NH(n, h) {
+    float cc[9], a[9], b[9], g[9]; ld_c(c, n, F, h, cc); ld_c(d1, n, F, h, a); ld_c(d2, n, F, h, b);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a[k] += b[k];
+    tn::p1_bwd(cc, a, g); st_c(dc, n, F, h, g);
+  }
 }
 __global__ void p2_fwd_k(CI Y, CI M, const float* qf, int o3, MI out, int N, int F) {
   TMD_FOR_NH(n, h) {
@@ -172,6 +200,14 @@ __global__ void p3_bwd_k(CI dX, const float* qf, CI dout, MI gXn, MI gdX, int N,
   TMD_FOR_NH(n, h) {
     float b[9], d[9], g1[9], g2[9]; ld_c(dX, n, F, h, b); ld_c(dout, n, F, h, d);
     tn::p3_bwd(b, qf[n], d, g1, g2); st_c(gXn, n, F, h, g1); st_c(gdX, n, F, h, g2);
+  }
+}
+
+// P3 backward, dX branch only (the Xn branch of X' = Xn + dX + qf dX.dX is the identity: the caller passes dout on)
+__global__ void p3_bwd_dx_k(CI dX, const float* qf, CI dout, MI gdX, int N, int F) {
+  TMD_FOR_NH(n, h) {
+    float b[9], d[9], g1[9], g2[9]; ld_c(dX, n, F, h, b); ld_c(dout, n, F, h, d);
+    tn::p3_bwd(b, qf[n], d, g1, g2); st_c(gdX, n, F, h, g2);
   }
 }
 
@@ -223,6 +259,18 @@ int tmd_gate_bwd(const float* I, const float* A, const float* S, const float* g,
                  float* gI, float* gA, float* gS, float* dg, int N, int F, void* stream) {
   TMD_REQUIRE(I && A && S && g && dI && dA && dS && gI && gA && gS && dg, "gate_bwd: null pointer");
   TMD_LAUNCH_NF(gate_bwd_k, CI{I, A, S}, g, CI{dI, dA, dS}, MI{gI, gA, gS}, dg); }
+int tmd_gate_bwd_preact(const float* I, const float* A, const float* S, const float* z, const float* dI, const float* dA, const float* dS,
+                        float* gI, float* gA, float* gS, float* dg, int N, int F, void* stream) {
+  TMD_REQUIRE(I && A && S && z && dI && dA && dS && gI && gA && gS && dg, "gate_bwd_preact: null pointer");
+  TMD_LAUNCH_NF(gate_bwd_preact_k, CI{I, A, S}, z, CI{dI, dA, dS}, MI{gI, gA, gS}, dg); }
+int tmd_p1_bwd2(const float* I, const float* A, const float* S, const float* d1I, const float* d1A, const float* d1S, const float* d2I,
+                const float* d2A, const float* d2S, float* gI, float* gA, float* gS, int N, int F, void* stream) {
+  TMD_REQUIRE(I && A && S && d1I && d1A && d1S && d2I && d2A && d2S && gI && gA && gS, "p1_bwd2: null pointer");
+  TMD_LAUNCH_NF(p1_bwd2_k, CI{I, A, S}, CI{d1I, d1A, d1S}, CI{d2I, d2A, d2S}, MI{gI, gA, gS}); }
+int tmd_p3_bwd_dx(const float* DI, const float* DA, const float* DS, const float* qf, const float* dI, const float* dA, const float* dS,
+                  float* gDI, float* gDA, float* gDS, int N, int F, void* stream) {
+  TMD_REQUIRE(DI && DA && DS && qf && dI && dA && dS && gDI && gDA && gDS, "p3_bwd_dx: null pointer");
+  TMD_LAUNCH_NF(p3_bwd_dx_k, CI{DI, DA, DS}, qf, CI{dI, dA, dS}, MI{gDI, gDA, gDS}); }
 int tmd_p1_fwd(const float* I, const float* A, const float* S, float* oI, float* oA, float* oS, int N, int F, void* stream) {
   TMD_REQUIRE(I && A && S && oI && oA && oS, "p1_fwd: null pointer"); TMD_LAUNCH_NF(p1_fwd_k, CI{I, A, S}, MI{oI, oA, oS}); }
 int tmd_p1_bwd(const float* I, const float* A, const float* S, const float* dI, const float* dA, const float* dS,

@@ -408,21 +408,25 @@ class MessagePassingPlan:
                       device=YI.device)
         return M
 
-    def backward(self, Y, dM, f, fp):
+    def backward(self, Y, dM, f, fp, add=None):
+        """-> (dY, g_dist); `add` (optional triple): a gradient that reached Y along another path, summed into dY by the kernel"""
         YI, YA, YS = Y
         N, F = self.N, YI.shape[-1]
         dY = _triple(N, F, YI.device)
         g, x = self.g, self.pidx
+        ad = (None, None, None) if add is None else add
         if self._ok(F):
             # every valid slot is written by the kernel; padded slots (static shapes) are never read by the position gradient
             g_dist = torch.empty(g.dist.shape[0], device=YI.device, dtype=torch.float32) if fp is not None else None
             _lib.call("tmd_mp_coop_bwd", p(YI), p(YA), p(YS), p(dM[0]), p(dM[1]), p(dM[2]), p(f), p(fp), p(x.pid), p(g.nbr_j),
                       p(g.indptr), p(g.num_pairs), g.dist.shape[0], N, F, self.group, p(self.rows), p(self.union_j), p(self.ucount), p(self.upos),
-                      p(self.goff), p(self.gcnt), p(dY[0]), p(dY[1]), p(dY[2]), p(g_dist), device=YI.device)
+                      p(self.goff), p(self.gcnt), p(ad[0]), p(ad[1]), p(ad[2]), p(dY[0]), p(dY[1]), p(dY[2]), p(g_dist), device=YI.device)
         else:
             g_dist = torch.zeros(g.dist.shape[0], device=YI.device, dtype=torch.float32) if fp is not None else None
             _lib.call("tmd_mp_edge_bwd", p(YI), p(YA), p(YS), p(dM[0]), p(dM[1]), p(dM[2]), p(f), p(fp), p(x.pid), p(g.nbr_j),
                       p(g.indptr), N, F, p(dY[0]), p(dY[1]), p(dY[2]), p(g_dist), device=YI.device)
+            if add is not None:
+                dY = tuple(a + b for a, b in zip(dY, add))
         return dY, g_dist
 
 
@@ -494,6 +498,9 @@ def embedding_message_passing(dist, vec, U, V, pair_r, chain, rbf_mod, lo, hi, g
     return _EmbeddingMP.apply(dist, vec, U, V, zidx, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op)
 
 
+# whole-stage autograd nodes (hand-sequenced backward, fused gradient sums): TMD_FUSED_LAYER=0 / TMD_EMBED_TAIL=0 -> one node per kernel
+USE_FUSED_LAYER = os.environ.get("TMD_FUSED_LAYER", "1") != "0"
+USE_EMBED_TAIL = os.environ.get("TMD_EMBED_TAIL", "0") != "0"   # off: the per-tile weight streaming of csrc/atom_mlp.cu is latency-bound (334 + 306 us vs ~250 us through cuBLAS at C4)
 # embedding by radial moments (csrc/embed_moments.cu): no per-pair radial rows at all; TMD_EMBED_MOMENTS=0 -> chain + embed kernels
 USE_EMBED_MOMENTS = os.environ.get("TMD_EMBED_MOMENTS", "1") != "0"
 MAX_SPECIES = 16
@@ -727,6 +734,138 @@ def irreps_linear(X, weights: IrrepsLinearWeights):
     return _IrrepsLinear.apply(X[0], X[1], X[2], weights)
 
 
+# ------------------------------------------------------------------------------------------ whole stages as ONE autograd node
+# The frozen-weights frame differentiates w.r.t. geometry only, so a stage's backward is a fixed kernel sequence.  Written out by
+# hand (instead of chaining one autograd Function per kernel) the sums that autograd would perform with separate `add` launches
+# -- a tensor consumed by two kernels receives two gradients -- become part of a consumer kernel: the message-passing backward
+# adds the gradient Y received from P2, the P1 backward takes its two incoming gradients as separate operands, the embedding's MLP
+# backward adds what came back through the node linears, and P3's identity branch is not materialised at all.
+class _InteractionLayer(torch.autograd.Function):
+    """One TensorNet interaction (reference tensornet.py:723-814): P1 -> node linears -> radial chain / table -> message passing ->
+    P2 -> node linears -> P3.  Inputs X = (I, A, S) [N,{1,3,5},F] and the per-slot distances; output X'."""
+
+    @staticmethod
+    def forward(ctx, XI, XA, XS, dist, qf, o3, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op, plan, nl0, nl1):
+        XI, XA, XS, qf = XI.contiguous(), XA.contiguous(), XS.contiguous(), qf.contiguous()
+        N, F, dev = XI.shape[0], XI.shape[-1], XI.device
+        (w0, _), (w1, _) = nl0.tensors(), nl1.tensors()
+        Xn = _triple(N, F, dev)
+        _lib.call("tmd_p1_fwd", p(XI), p(XA), p(XS), p(Xn[0]), p(Xn[1]), p(Xn[2]), N, F, device=dev)
+        Y = _irreps_gemm(Xn[0], Xn[1], Xn[2], w0[0], w0[1])
+        f, fp = run_chain(chain, pair_r.detach(), pidx.num_unique, rbf_mod, lo, hi, dist.requires_grad, rbf_op)
+        if plan is None:
+            plan = MessagePassingPlan(g, pidx, F)
+        M = plan.forward(Y, f)
+        Cn = _triple(N, F, dev)
+        _lib.call("tmd_p2_fwd", p(Y[0]), p(Y[1]), p(Y[2]), p(M[0]), p(M[1]), p(M[2]), p(qf), int(o3), p(Cn[0]), p(Cn[1]), p(Cn[2]), N, F, device=dev)
+        dX = _irreps_gemm(Cn[0], Cn[1], Cn[2], w1[0], w1[1])
+        out = _triple(N, F, dev)
+        _lib.call("tmd_p3_fwd", p(Xn[0]), p(Xn[1]), p(Xn[2]), p(dX[0]), p(dX[1]), p(dX[2]), p(qf), p(out[0]), p(out[1]), p(out[2]), N, F, device=dev)
+        ctx.save_for_backward(XI, XA, XS, *Y, *M, *dX, f, fp if fp is not None else f, qf)
+        ctx.cfg = (int(o3), plan, fp is not None, dist.shape[0], nl0, nl1)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dI, dA, dS):
+        XI, XA, XS, YI, YA, YS, MI, MA, MS, DI, DA, DS, f, fp, qf = ctx.saved_tensors
+        o3, plan, has_fp, E, nl0, nl1 = ctx.cfg
+        N, F, dev = XI.shape[0], XI.shape[-1], XI.device
+        dO = (dI.contiguous(), dA.contiguous(), dS.contiguous())
+        (_, b0), (_, b1) = nl0.tensors(), nl1.tensors()
+        gD = _triple(N, F, dev)
+        _lib.call("tmd_p3_bwd_dx", p(DI), p(DA), p(DS), p(qf), p(dO[0]), p(dO[1]), p(dO[2]), p(gD[0]), p(gD[1]), p(gD[2]), N, F, device=dev)
+        gC = _irreps_gemm(gD[0], gD[1], gD[2], b1[0], b1[1])
+        gYa, gM = _triple(N, F, dev), _triple(N, F, dev)
+        _lib.call("tmd_p2_bwd", p(YI), p(YA), p(YS), p(MI), p(MA), p(MS), p(qf), o3, p(gC[0]), p(gC[1]), p(gC[2]), p(gYa[0]), p(gYa[1]), p(gYa[2]),
+                  p(gM[0]), p(gM[1]), p(gM[2]), N, F, device=dev)
+        gY, g_dist = plan.backward((YI, YA, YS), gM, f, fp if has_fp else None, add=gYa)
+        if g_dist is not None and g_dist.shape[0] != E:     # dynamic shapes: `dist` is the exact-size prefix of the capacity buffer
+            g_dist = g_dist[:E]
+        gXn = _irreps_gemm(gY[0], gY[1], gY[2], b0[0], b0[1])
+        gX = _triple(N, F, dev)
+        _lib.call("tmd_p1_bwd2", p(XI), p(XA), p(XS), p(dO[0]), p(dO[1]), p(dO[2]), p(gXn[0]), p(gXn[1]), p(gXn[2]), p(gX[0]), p(gX[1]), p(gX[2]),
+                  N, F, device=dev)
+        return (gX[0], gX[1], gX[2], g_dist) + (None,) * 13
+
+
+def interaction_layer(X, dist, qf, o3, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op, plan, nl0, nl1):
+    return _InteractionLayer.apply(X[0], X[1], X[2], dist, qf, bool(o3), pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op, plan, nl0, nl1)
+
+
+class EmbedMlpWeights:
+    """init_norm + linears_scalar[0..1] of TensorEmbedding in the layouts of csrc/atom_mlp.cu, cached per weight version."""
+
+    def __init__(self, init_norm: torch.nn.LayerNorm, lin0: torch.nn.Linear, lin1: torch.nn.Linear):
+        self.mods = (init_norm, lin0, lin1)
+        self._key = None
+
+    def params(self):
+        return [t for m in self.mods for t in (m.weight, m.bias)]
+
+    def frozen(self) -> bool:
+        return not any(t.requires_grad for t in self.params())
+
+    def supported(self) -> bool:
+        ln, l0, l1 = self.mods
+        F = l0.in_features
+        return (F % 32 == 0 and F <= 256 and l0.out_features == 2 * F and l1.in_features == 2 * F and l1.out_features == 3 * F and
+                ln.elementwise_affine and tuple(ln.normalized_shape) == (F,) and l0.bias is not None and l1.bias is not None and
+                (32 * (5 * F + 8) + 3 * 16 * (F + 8)) * 4 <= 227 * 1024 and all(t.dtype == torch.float32 for t in self.params()))   # bwd tile + weight staging (csrc/atom_mlp.cu)
+
+    def tensors(self):
+        key = tuple((t.data_ptr(), t._version) for t in self.params())
+        if key != self._key:
+            ln, l0, l1 = self.mods
+            d = lambda t: t.detach().contiguous()
+            self._t = dict(ln_w=d(ln.weight), ln_b=d(ln.bias), eps=float(ln.eps), W1T=d(l0.weight.detach().t()), b1=d(l0.bias),
+                           W2T=d(l1.weight.detach().t()), b2=d(l1.bias), W1=d(l0.weight), W2=d(l1.weight))
+            self._key = key
+        return self._t
+
+
+class _EmbeddingTail(torch.autograd.Function):
+    """Per-atom part of TensorEmbedding (tensornet.py:588-619): X' = (W_t X) * SiLU(MLP(LayerNorm(|X|^2)))  (csrc/atom_mlp.cu)."""
+
+    @staticmethod
+    def forward(ctx, I, A, S, nl, mw):
+        I, A, S = I.contiguous(), A.contiguous(), S.contiguous()
+        N, F, dev = I.shape[0], I.shape[-1], I.device
+        (wf, _), t = nl.tensors(), mw.tensors()
+        C = _irreps_gemm(I, A, S, wf[0], wf[1])
+        out = _triple(N, F, dev)
+        mu_rstd = torch.empty(N, 2, device=dev, dtype=torch.float32)
+        z1 = torch.empty(N, 2 * F, device=dev, dtype=torch.float32)
+        z2 = torch.empty(N, 3 * F, device=dev, dtype=torch.float32)
+        _lib.call("tmd_embed_mlp_fwd", p(I), p(A), p(S), p(C[0]), p(C[1]), p(C[2]), N, F, p(t["ln_w"]), p(t["ln_b"]), t["eps"], p(t["W1T"]),
+                  p(t["b1"]), p(t["W2T"]), p(t["b2"]), p(out[0]), p(out[1]), p(out[2]), p(mu_rstd), p(z1), p(z2), device=dev)
+        ctx.save_for_backward(I, A, S, *C, mu_rstd, z1, z2)
+        ctx.w = (nl, t)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dI, dA, dS):
+        I, A, S, CI, CA, CS, mu_rstd, z1, z2 = ctx.saved_tensors
+        nl, t = ctx.w
+        N, F, dev = I.shape[0], I.shape[-1], I.device
+        dO = (dI.contiguous(), dA.contiguous(), dS.contiguous())
+        (_, wb) = nl.tensors()
+        dC = _triple(N, F, dev)
+        dg = torch.empty(N, 3 * F, device=dev, dtype=torch.float32)
+        _lib.call("tmd_gate_bwd_preact", p(CI), p(CA), p(CS), p(z2), p(dO[0]), p(dO[1]), p(dO[2]), p(dC[0]), p(dC[1]), p(dC[2]), p(dg), N, F,
+                  device=dev)
+        gXa = _irreps_gemm(dC[0], dC[1], dC[2], wb[0], wb[1])
+        gX = _triple(N, F, dev)
+        _lib.call("tmd_embed_mlp_bwd", p(I), p(A), p(S), N, F, p(t["ln_w"]), t["eps"], p(t["W1"]), p(t["W2"]), p(dg), p(mu_rstd), p(z1), p(z2),
+                  p(gXa[0]), p(gXa[1]), p(gXa[2]), p(gX[0]), p(gX[1]), p(gX[2]), device=dev)
+        return gX[0], gX[1], gX[2], None, None
+
+
+def embedding_tail(X, nl: IrrepsLinearWeights, mw: EmbedMlpWeights):
+    return _EmbeddingTail.apply(X[0], X[1], X[2], nl, mw)
+
+
 # ------------------------------------------------------------------------------------------ tail + head + reduce (rows a10, a11)
 class HeadWeights:
     """Contiguous (and transposed) copies of the weights behind norm3 -> LayerNorm -> Linear -> SiLU -> MLP(F -> F/2 -> 1), cached
@@ -745,7 +884,7 @@ class HeadWeights:
     def supported(self) -> bool:
         out_norm, linear, lin_a, lin_b = self.mods
         F, H = linear.out_features, lin_a.out_features
-        smem_bwd = (32 * ((3 * F + 4) + (F + 4) + (H + 4)) + 2 * 8 * 256) * 4      # smallest tile + weight-staging buffers of the head kernels (csrc/head.cu)
+        smem_bwd = (32 * ((3 * F + 4) + (F + 4) + (H + 4)) + 3 * 16 * (max(F, H) + 8)) * 4      # tile + weight-staging buffers of the head kernels (csrc/head.cu, mlp_tile.cuh)
         return (linear.in_features == 3 * F and lin_a.in_features == F and lin_b.in_features == H and lin_b.out_features == 1 and
                 F % 32 == 0 and H % 32 == 0 and F <= 256 and H <= 256 and smem_bwd <= 227 * 1024 and out_norm.elementwise_affine and
                 tuple(out_norm.normalized_shape) == (3 * F,) and all(t.dtype == torch.float32 for t in self.params()))

@@ -76,6 +76,11 @@ class TensorEmbedding(nn.Module):
             self._nl = fused.IrrepsLinearWeights(self.linears_tensor)
         return self._nl
 
+    def mlp_weights(self) -> "fused.EmbedMlpWeights":
+        if getattr(self, "_mlpw", None) is None:
+            self._mlpw = fused.EmbedMlpWeights(self.init_norm, self.linears_scalar[0], self.linears_scalar[1])
+        return self._mlpw
+
     def moment_weights(self) -> "fused.EmbedMomentWeights":
         if getattr(self, "_mom", None) is None:
             self._mom = fused.EmbedMomentWeights([self.distance_proj1, self.distance_proj2, self.distance_proj3])
@@ -127,6 +132,11 @@ class TensorEmbedding(nn.Module):
         else:
             w = self.pair_weights(z, nbr_i, nbr_j, cut, rbf)
             I, A, S = ops.fn_radial_message_passing(rhat, w, None, g.indptr)
+        if fast is not None and self.node_linear().supported() and self.node_linear().frozen():
+            mw = self.mlp_weights()
+            if fused.USE_EMBED_TAIL and mw.supported() and mw.frozen() and isinstance(self.act, nn.SiLU):
+                # node linears + LayerNorm(|X|^2) -> MLP -> gate as one autograd node (csrc/atom_mlp.cu)
+                return fused.embedding_tail((I, A, S), self.node_linear(), mw)
         norm = self.init_norm(ops.norm2_compact(I, A, S))
         for lin in self.linears_scalar:
             norm = self.act(lin(norm))
@@ -180,6 +190,12 @@ class Interaction(nn.Module):
     def forward(self, X, g, rbf, cut, qf, fast=None):
         lt = self.linears_tensor
         tc_lin = fast is not None and all(self.node_linear(k).supported() and self.node_linear(k).frozen() for k in (0, 1))
+        if tc_lin and fused.USE_FUSED_LAYER:
+            # the whole layer as one autograd node with a hand-sequenced backward (extensions/fused.py::_InteractionLayer)
+            dist, pair_r, pidx, rbf_mod, rbf_op, plan = fast
+            return fused.interaction_layer(X, dist, qf, self.equivariance_invariance_group == "O(3)", pair_r, self.radial_chain(), rbf_mod,
+                                           self.cutoff.cutoff_lower, self.cutoff.cutoff_upper, g, pidx, rbf_op, plan,
+                                           self.node_linear(0), self.node_linear(1))
         Xn = ops.interaction_normalize(*X)
         Y = fused.irreps_linear(Xn, self.node_linear(0)) if tc_lin else (lt[0](Xn[0]), lt[1](Xn[1]), lt[2](Xn[2]))
         if fast is not None:
