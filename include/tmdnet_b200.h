@@ -250,22 +250,32 @@ int tmd_embed_moments_bwd(const float* vec, const float* dist, const int* nbr_j,
                           double lo, double hi, int R, int n, int F, int Z, const float* dI, const float* dA, const float* dS,
                           float* g_dist, float* g_vec, void* stream);
 
-/* ---- a5, per-atom part of TensorEmbedding (csrc/atom_mlp.cu; models/tensornet.py:588-619) ------------------------------------
- * tmd_embed_mlp_fwd: (oI, oA, oS) = (cI, cA, cS) * g[type] with g = SiLU(W2 SiLU(W1 LayerNorm_F(|X|^2) + b1) + b2) in R^{3F},
- * X = (I, A, S) the un-normalised embedding, c = the node-linear output (tmd_irreps_linear_tc).  W1T [F,2F], W2T [2F,3F]
- * transposed nn.Linear weights; saves (mu, rstd) [N,2] and the pre-activations z1 [N,2F], z2 [N,3F].
- * tmd_gate_bwd_preact (tensor_ops.cu): gate backward with the gate given as its pre-activation z = z2: g = SiLU(z); returns the
- * gradient of c (gI, gA, gS) and of the gates dg [N,3F].
- * tmd_embed_mlp_bwd: gX = add + d/dX of the gate path for the gate gradient dg; W1 [2F,F], W2 [3F,2F] untransposed; the add triple
- * (all NULL or all given) is the gradient that reached X through the node linears.  F % 32 == 0, F <= 256. */
-int tmd_embed_mlp_fwd(const float* I, const float* A, const float* S, const float* cI, const float* cA, const float* cS, int N, int F,
-                      const float* ln_w, const float* ln_b, double eps, const float* W1T, const float* b1, const float* W2T,
-                      const float* b2, float* oI, float* oA, float* oS, float* mu_rstd, float* z1, float* z2, void* stream);
+/* ---- per-atom dense layers as weight-tiled GEMMs and the row-wise stages around them (csrc/rows_gemm.cu) ---------------------
+ * Rows a10 / a11 (TensorNet tail + Scalar head, models/tensornet.py:394-402, models/output_modules.py:79-117) and the scalar gate of
+ * the embedding (row a5, models/tensornet.py:588-619) are chains  norm -> LayerNorm -> Linear -> SiLU -> Linear -> SiLU.
+ * tmd_rows_gemm: out[M,N] = epilogue(A[M,K] . W[K,N]), fp32 operands, 3xTF32 warp-level tensor-core MMAs with fp32 parity; W is the
+ * TRANSPOSED nn.Linear weight in the forward and the nn.Linear weight itself in the backward.  lda/ldw/ldo/ldaux: row strides (floats).
+ *   epi 0: z = acc + vec[col]; zout (may be NULL) = z; out = SiLU(z)        (forward layer, saves the pre-activation)
+ *   epi 1: out = acc * SiLU'(aux[row,col])                                  (backward through an activation)
+ *   epi 2: out = acc * vec[col]                                             (backward into a LayerNorm: x gamma)
+ * K % 16 == 0, N % 32 == 0.
+ * tmd_norm_ln_fwd: xn = LayerNorm(norm(X)), mode 3: norm = (3 I^2, |A|^2, |S|^2) in R^{3F} (tensor_norm3), mode 2: |X|^2 per channel
+ * in R^F; saves (mu, rstd) [N,2].  tmd_norm_ln_bwd: g [N,K] = d xn * gamma -> gX = add + d/dX (add: all NULL or all given).
+ * tmd_head_energy: e = (w3 . h2 + b3) * std + atomref[z];  tmd_head_seed: dz2 = gy[batch] * std * w3 * SiLU'(z2).
+ * tmd_gate_bwd_preact (tensor_ops.cu): gate backward with the gate given as its pre-activation z: g = SiLU(z); returns the gradient of
+ * the gated tensors (gI, gA, gS) and dg [N,3F] = gradient of the gates (chain == 0) or of z (chain != 0). */
+int tmd_rows_gemm(const float* A, int lda, const float* W, int ldw, int M, int K, int N, int epi, const float* vec, const float* aux,
+                  int ldaux, float* zout, float* out, int ldo, void* stream);
+int tmd_norm_ln_fwd(const float* I, const float* A, const float* S, int N, int F, int mode, const float* ln_w, const float* ln_b, double eps,
+                    float* xn, float* mu_rstd, void* stream);
+int tmd_norm_ln_bwd(const float* I, const float* A, const float* S, int N, int F, int mode, const float* g, const float* mu_rstd,
+                    const float* addI, const float* addA, const float* addS, float* gI, float* gA, float* gS, void* stream);
+int tmd_head_energy(const float* h2, int N, int H, const float* w3, const float* b3, const float* std_, const int64_t* z, const float* atomref,
+                    int n_ref, float* e, void* stream);
+int tmd_head_seed(const float* gy, const int64_t* batch, int M, const float* std_, const float* w3, const float* z2, int N, int H, float* dz2,
+                  void* stream);
 int tmd_gate_bwd_preact(const float* I, const float* A, const float* S, const float* z, const float* dI, const float* dA, const float* dS,
-                        float* gI, float* gA, float* gS, float* dg, int N, int F, void* stream);
-int tmd_embed_mlp_bwd(const float* I, const float* A, const float* S, int N, int F, const float* ln_w, double eps, const float* W1,
-                      const float* W2, const float* dg, const float* mu_rstd, const float* z1, const float* z2, const float* addI,
-                      const float* addA, const float* addS, float* gI, float* gA, float* gS, void* stream);
+                        float* gI, float* gA, float* gS, float* dg, int chain, int N, int F, void* stream);
 /* P1 backward with the incoming gradient given as two tensors (d1 + d2), and P3 backward for the dX branch only (the Xn branch of
  * X' = Xn + dX + qf dX.dX is the identity): what the hand-sequenced backward of one interaction layer needs
  * (extensions/fused.py::_InteractionLayer; models/tensornet.py:745, :812). */

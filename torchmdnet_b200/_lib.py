@@ -76,11 +76,14 @@ SIGNATURES = {
     "tmd_head_bwd": ([P, P, P, I, I, I, P, D] + [P] * 6 + [I] + [P] * 6 + [P], 1),
     "tmd_embed_fwd": ([P] * 9 + [D, D, I, I] + [P] * 3 + [P], 1),
     "tmd_embed_bwd": ([P] * 10 + [D, D, I, I] + [P] * 5 + [P], 1),
-    "tmd_gate_bwd_preact": ([P] * 11 + [I, I, P], 1),
+    "tmd_gate_bwd_preact": ([P] * 11 + [I, I, I, P], 1),
+    "tmd_rows_gemm": ([P, I, P, I, I, I, I, I, P, P, I, P, P, I, P], 1),
+    "tmd_norm_ln_fwd": ([P, P, P, I, I, I, P, P, D, P, P, P], 1),
+    "tmd_norm_ln_bwd": ([P, P, P, I, I, I] + [P] * 8 + [P], 1),
+    "tmd_head_energy": ([P, I, I, P, P, P, P, P, I, P, P], 1),
+    "tmd_head_seed": ([P, P, I, P, P, P, I, I, P, P], 1),
     "tmd_p1_bwd2": ([P] * 12 + [I, I, P], 1),
     "tmd_p3_bwd_dx": ([P] * 10 + [I, I, P], 1),
-    "tmd_embed_mlp_fwd": ([P] * 6 + [I, I, P, P, D] + [P] * 10 + [P], 1),
-    "tmd_embed_mlp_bwd": ([P, P, P, I, I, P, D] + [P] * 12 + [P], 1),
     "tmd_embed_moments_fwd": ([P] * 10 + [D, D, D, I, I, I, I] + [P] * 3 + [P], 1),
     "tmd_embed_moments_bwd": ([P] * 11 + [D, D, D, I, I, I, I] + [P] * 5 + [P], 1),
 }

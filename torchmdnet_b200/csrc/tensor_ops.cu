@@ -144,16 +144,19 @@ __global__ void gate_bwd_k(CI c, const float* g, CI dout, MI dc, float* dg, int 
     st_c(dc, n, F, h, d);
   }
 }
-// gate backward with the gate given as its pre-activation: g = SiLU(z) (z = z2 of the embedding MLP, csrc/atom_mlp.cu)
-__global__ void gate_bwd_preact_k(CI c, const float* z, CI dout, MI dc, float* dg, int N, int F) {
+// gate backward with the gate given as its pre-activation: g = SiLU(z) (z = z2 of the embedding's scalar MLP); chain != 0: dg is the
+// gradient w.r.t. z (x SiLU'(z)), ready to be the A operand of the MLP's backward GEMM (csrc/rows_gemm.cu)
+__global__ void gate_bwd_preact_k(CI c, const float* z, CI dout, MI dc, float* dg, int chain, int N, int F) {
   TMD_FOR_NH(n, h) {
     float cc[9], d[9]; ld_c(c, n, F, h, cc); ld_c(dout, n, F, h, d);
-    const float g0 = tn::silu(z[n * 3 * F + h]), g1 = tn::silu(z[n * 3 * F + F + h]), g2 = tn::silu(z[n * 3 * F + 2 * F + h]);
+    const float z0 = z[n * 3 * F + h], z1 = z[n * 3 * F + F + h], z2 = z[n * 3 * F + 2 * F + h];
+    const float g0 = tn::silu(z0), g1 = tn::silu(z1), g2 = tn::silu(z2);
     float s0 = d[0] * cc[0], s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 1; k < 4; ++k) s1 += d[k] * cc[k];
 #pragma unroll
     for (int k = 4; k < 9; ++k) s2 += d[k] * cc[k];
+    if (chain) { s0 *= tn::silu_grad(z0); s1 *= tn::silu_grad(z1); s2 *= tn::silu_grad(z2); }   // gradient w.r.t. z instead of g
     dg[n * 3 * F + h] = s0; dg[n * 3 * F + F + h] = s1; dg[n * 3 * F + 2 * F + h] = s2;
     d[0] *= g0;
 #pragma unroll
@@ -260,9 +263,9 @@ int tmd_gate_bwd(const float* I, const float* A, const float* S, const float* g,
   TMD_REQUIRE(I && A && S && g && dI && dA && dS && gI && gA && gS && dg, "gate_bwd: null pointer");
   TMD_LAUNCH_NF(gate_bwd_k, CI{I, A, S}, g, CI{dI, dA, dS}, MI{gI, gA, gS}, dg); }
 int tmd_gate_bwd_preact(const float* I, const float* A, const float* S, const float* z, const float* dI, const float* dA, const float* dS,
-                        float* gI, float* gA, float* gS, float* dg, int N, int F, void* stream) {
+                        float* gI, float* gA, float* gS, float* dg, int chain, int N, int F, void* stream) {
   TMD_REQUIRE(I && A && S && z && dI && dA && dS && gI && gA && gS && dg, "gate_bwd_preact: null pointer");
-  TMD_LAUNCH_NF(gate_bwd_preact_k, CI{I, A, S}, z, CI{dI, dA, dS}, MI{gI, gA, gS}, dg); }
+  TMD_LAUNCH_NF(gate_bwd_preact_k, CI{I, A, S}, z, CI{dI, dA, dS}, MI{gI, gA, gS}, dg, chain); }
 int tmd_p1_bwd2(const float* I, const float* A, const float* S, const float* d1I, const float* d1A, const float* d1S, const float* d2I,
                 const float* d2A, const float* d2S, float* gI, float* gA, float* gS, int N, int F, void* stream) {
   TMD_REQUIRE(I && A && S && d1I && d1A && d1S && d2I && d2A && d2S && gI && gA && gS, "p1_bwd2: null pointer");

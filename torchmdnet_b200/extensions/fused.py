@@ -500,7 +500,10 @@ def embedding_message_passing(dist, vec, U, V, pair_r, chain, rbf_mod, lo, hi, g
 
 # whole-stage autograd nodes (hand-sequenced backward, fused gradient sums): TMD_FUSED_LAYER=0 / TMD_EMBED_TAIL=0 -> one node per kernel
 USE_FUSED_LAYER = os.environ.get("TMD_FUSED_LAYER", "1") != "0"
-USE_EMBED_TAIL = os.environ.get("TMD_EMBED_TAIL", "0") != "0"   # off: the per-tile weight streaming of csrc/atom_mlp.cu is latency-bound (334 + 306 us vs ~250 us through cuBLAS at C4)
+USE_EMBED_TAIL = os.environ.get("TMD_EMBED_TAIL", "1") != "0"
+# per-atom dense layers (head, embedding gate MLP) as weight-tiled GEMM launches (csrc/rows_gemm.cu); TMD_ROWS_GEMM=0 -> the head runs
+# the per-32-atom-tile kernels of csrc/head.cu (whole chain in one launch, but every tile re-streams the weights: latency-bound)
+USE_ROWS_GEMM = os.environ.get("TMD_ROWS_GEMM", "1") != "0"
 # embedding by radial moments (csrc/embed_moments.cu): no per-pair radial rows at all; TMD_EMBED_MOMENTS=0 -> chain + embed kernels
 USE_EMBED_MOMENTS = os.environ.get("TMD_EMBED_MOMENTS", "1") != "0"
 MAX_SPECIES = 16
@@ -740,6 +743,18 @@ def irreps_linear(X, weights: IrrepsLinearWeights):
 # -- a tensor consumed by two kernels receives two gradients -- become part of a consumer kernel: the message-passing backward
 # adds the gradient Y received from P2, the P1 backward takes its two incoming gradients as separate operands, the embedding's MLP
 # backward adds what came back through the node linears, and P3's identity branch is not materialised at all.
+def rows_gemm(A: Tensor, W: Tensor, epi: int, vec: Optional[Tensor] = None, aux: Optional[Tensor] = None, save_z: bool = False):
+    """out [M,N] = epilogue(A [M,K] . W [K,N]) (csrc/rows_gemm.cu); epi 0: SiLU(acc + vec) (+ pre-activation if save_z),
+    1: acc * SiLU'(aux), 2: acc * vec.  -> out, or (z, out) when save_z."""
+    M, K = A.shape
+    N = W.shape[1]
+    out = torch.empty(M, N, device=A.device, dtype=torch.float32)
+    z = torch.empty_like(out) if save_z else None
+    _lib.call("tmd_rows_gemm", p(A), A.stride(0), p(W), W.stride(0), M, K, N, int(epi), p(vec), p(aux), 0 if aux is None else aux.stride(0),
+              p(z), p(out), N, device=A.device)
+    return (z, out) if save_z else out
+
+
 class _InteractionLayer(torch.autograd.Function):
     """One TensorNet interaction (reference tensornet.py:723-814): P1 -> node linears -> radial chain / table -> message passing ->
     P2 -> node linears -> P3.  Inputs X = (I, A, S) [N,{1,3,5},F] and the per-slot distances; output X'."""
@@ -794,7 +809,7 @@ def interaction_layer(X, dist, qf, o3, pair_r, chain, rbf_mod, lo, hi, g, pidx, 
 
 
 class EmbedMlpWeights:
-    """init_norm + linears_scalar[0..1] of TensorEmbedding in the layouts of csrc/atom_mlp.cu, cached per weight version."""
+    """init_norm + linears_scalar[0..1] of TensorEmbedding in the layouts of csrc/rows_gemm.cu, cached per weight version."""
 
     def __init__(self, init_norm: torch.nn.LayerNorm, lin0: torch.nn.Linear, lin1: torch.nn.Linear):
         self.mods = (init_norm, lin0, lin1)
@@ -811,7 +826,7 @@ class EmbedMlpWeights:
         F = l0.in_features
         return (F % 32 == 0 and F <= 256 and l0.out_features == 2 * F and l1.in_features == 2 * F and l1.out_features == 3 * F and
                 ln.elementwise_affine and tuple(ln.normalized_shape) == (F,) and l0.bias is not None and l1.bias is not None and
-                (32 * (5 * F + 8) + 3 * 16 * (F + 8)) * 4 <= 227 * 1024 and all(t.dtype == torch.float32 for t in self.params()))   # bwd tile + weight staging (csrc/atom_mlp.cu)
+                all(t.dtype == torch.float32 for t in self.params()))
 
     def tensors(self):
         key = tuple((t.data_ptr(), t._version) for t in self.params())
@@ -825,7 +840,9 @@ class EmbedMlpWeights:
 
 
 class _EmbeddingTail(torch.autograd.Function):
-    """Per-atom part of TensorEmbedding (tensornet.py:588-619): X' = (W_t X) * SiLU(MLP(LayerNorm(|X|^2)))  (csrc/atom_mlp.cu)."""
+    """Per-atom part of TensorEmbedding (tensornet.py:588-619): X' = (W_t X) * SiLU(MLP(LayerNorm(|X|^2))) as one autograd node:
+    node linears (tcgen05), norm + LayerNorm, two GEMM launches with fused bias / SiLU, gate; the backward adds the gradient that
+    came back through the node linears inside the norm backward (csrc/rows_gemm.cu, tensor_ops.cu)."""
 
     @staticmethod
     def forward(ctx, I, A, S, nl, mw):
@@ -833,12 +850,13 @@ class _EmbeddingTail(torch.autograd.Function):
         N, F, dev = I.shape[0], I.shape[-1], I.device
         (wf, _), t = nl.tensors(), mw.tensors()
         C = _irreps_gemm(I, A, S, wf[0], wf[1])
-        out = _triple(N, F, dev)
+        xn = torch.empty(N, F, device=dev, dtype=torch.float32)
         mu_rstd = torch.empty(N, 2, device=dev, dtype=torch.float32)
-        z1 = torch.empty(N, 2 * F, device=dev, dtype=torch.float32)
-        z2 = torch.empty(N, 3 * F, device=dev, dtype=torch.float32)
-        _lib.call("tmd_embed_mlp_fwd", p(I), p(A), p(S), p(C[0]), p(C[1]), p(C[2]), N, F, p(t["ln_w"]), p(t["ln_b"]), t["eps"], p(t["W1T"]),
-                  p(t["b1"]), p(t["W2T"]), p(t["b2"]), p(out[0]), p(out[1]), p(out[2]), p(mu_rstd), p(z1), p(z2), device=dev)
+        _lib.call("tmd_norm_ln_fwd", p(I), p(A), p(S), N, F, 2, p(t["ln_w"]), p(t["ln_b"]), t["eps"], p(xn), p(mu_rstd), device=dev)
+        z1, h1 = rows_gemm(xn, t["W1T"], 0, vec=t["b1"], save_z=True)
+        z2, gact = rows_gemm(h1, t["W2T"], 0, vec=t["b2"], save_z=True)
+        out = _triple(N, F, dev)
+        _lib.call("tmd_gate_fwd", p(C[0]), p(C[1]), p(C[2]), p(gact), p(out[0]), p(out[1]), p(out[2]), N, F, device=dev)
         ctx.save_for_backward(I, A, S, *C, mu_rstd, z1, z2)
         ctx.w = (nl, t)
         return out
@@ -852,13 +870,15 @@ class _EmbeddingTail(torch.autograd.Function):
         dO = (dI.contiguous(), dA.contiguous(), dS.contiguous())
         (_, wb) = nl.tensors()
         dC = _triple(N, F, dev)
-        dg = torch.empty(N, 3 * F, device=dev, dtype=torch.float32)
-        _lib.call("tmd_gate_bwd_preact", p(CI), p(CA), p(CS), p(z2), p(dO[0]), p(dO[1]), p(dO[2]), p(dC[0]), p(dC[1]), p(dC[2]), p(dg), N, F,
+        dz2 = torch.empty(N, 3 * F, device=dev, dtype=torch.float32)
+        _lib.call("tmd_gate_bwd_preact", p(CI), p(CA), p(CS), p(z2), p(dO[0]), p(dO[1]), p(dO[2]), p(dC[0]), p(dC[1]), p(dC[2]), p(dz2), 1, N, F,
                   device=dev)
         gXa = _irreps_gemm(dC[0], dC[1], dC[2], wb[0], wb[1])
+        dz1 = rows_gemm(dz2, t["W2"], 1, aux=z1)
+        g = rows_gemm(dz1, t["W1"], 2, vec=t["ln_w"])
         gX = _triple(N, F, dev)
-        _lib.call("tmd_embed_mlp_bwd", p(I), p(A), p(S), N, F, p(t["ln_w"]), t["eps"], p(t["W1"]), p(t["W2"]), p(dg), p(mu_rstd), p(z1), p(z2),
-                  p(gXa[0]), p(gXa[1]), p(gXa[2]), p(gX[0]), p(gX[1]), p(gX[2]), device=dev)
+        _lib.call("tmd_norm_ln_bwd", p(I), p(A), p(S), N, F, 2, p(g), p(mu_rstd), p(gXa[0]), p(gXa[1]), p(gXa[2]), p(gX[0]), p(gX[1]), p(gX[2]),
+                  device=dev)
         return gX[0], gX[1], gX[2], None, None
 
 
@@ -920,9 +940,17 @@ class _TailHead(torch.autograd.Function):
         batch_c, z_c = batch.contiguous(), z.contiguous()
         std_c, mean_c = std.detach().reshape(1).contiguous(), mean.detach().reshape(1).contiguous()
         aref = None if atomref is None else atomref.detach().contiguous()
-        _lib.call("tmd_head_fwd", p(I), p(A), p(S), N, F, H, p(t["ln_w"]), p(t["ln_b"]), t["eps"], p(t["W1T"]), p(t["b1"]), p(t["W2T"]),
-                  p(t["b2"]), p(t["w3"]), p(t["b3"]), p(std_c), p(z_c), p(aref), 0 if aref is None else aref.shape[0], p(e), p(mu_rstd),
-                  p(z1), p(z2), device=dev)
+        if USE_ROWS_GEMM:   # norm3 + LayerNorm, two GEMM launches (bias + SiLU fused, pre-activations saved), energy per atom
+            xn = torch.empty(N, 3 * F, device=dev, dtype=torch.float32)
+            _lib.call("tmd_norm_ln_fwd", p(I), p(A), p(S), N, F, 3, p(t["ln_w"]), p(t["ln_b"]), t["eps"], p(xn), p(mu_rstd), device=dev)
+            z1, h1 = rows_gemm(xn, t["W1T"], 0, vec=t["b1"], save_z=True)
+            z2, h2 = rows_gemm(h1, t["W2T"], 0, vec=t["b2"], save_z=True)
+            _lib.call("tmd_head_energy", p(h2), N, H, p(t["w3"]), p(t["b3"]), p(std_c), p(z_c), p(aref), 0 if aref is None else aref.shape[0],
+                      p(e), device=dev)
+        else:
+            _lib.call("tmd_head_fwd", p(I), p(A), p(S), N, F, H, p(t["ln_w"]), p(t["ln_b"]), t["eps"], p(t["W1T"]), p(t["b1"]), p(t["W2T"]),
+                      p(t["b2"]), p(t["w3"]), p(t["b3"]), p(std_c), p(z_c), p(aref), 0 if aref is None else aref.shape[0], p(e), p(mu_rstd),
+                      p(z1), p(z2), device=dev)
         _lib.call("tmd_segment_sum", p(e), p(batch_c), N, M, p(mean_c), p(flag), p(y), device=dev)
         ctx.save_for_backward(I, A, S, batch_c, mu_rstd, z1, z2, std_c)
         ctx.hw, ctx.M = t, M
@@ -936,8 +964,16 @@ class _TailHead(torch.autograd.Function):
         N, F, H = I.shape[0], t["F"], t["H"]
         gy = gy.contiguous()
         dX = _triple(N, F, I.device)
-        _lib.call("tmd_head_bwd", p(I), p(A), p(S), N, F, H, p(t["ln_w"]), t["eps"], p(t["W1"]), p(t["W2"]), p(t["w3"]), p(std_c), p(gy),
-                  p(batch), ctx.M, p(mu_rstd), p(z1), p(z2), p(dX[0]), p(dX[1]), p(dX[2]), device=I.device)
+        if USE_ROWS_GEMM:
+            dz2 = torch.empty(N, H, device=I.device, dtype=torch.float32)
+            _lib.call("tmd_head_seed", p(gy), p(batch), ctx.M, p(std_c), p(t["w3"]), p(z2), N, H, p(dz2), device=I.device)
+            dz1 = rows_gemm(dz2, t["W2"], 1, aux=z1)
+            g = rows_gemm(dz1, t["W1"], 2, vec=t["ln_w"])
+            _lib.call("tmd_norm_ln_bwd", p(I), p(A), p(S), N, F, 3, p(g), p(mu_rstd), None, None, None, p(dX[0]), p(dX[1]), p(dX[2]),
+                      device=I.device)
+        else:
+            _lib.call("tmd_head_bwd", p(I), p(A), p(S), N, F, H, p(t["ln_w"]), t["eps"], p(t["W1"]), p(t["W2"]), p(t["w3"]), p(std_c), p(gy),
+                      p(batch), ctx.M, p(mu_rstd), p(z1), p(z2), p(dX[0]), p(dX[1]), p(dX[2]), device=I.device)
         return dX[0], dX[1], dX[2], None, None, None, None, None, None, None
 
 
