@@ -387,9 +387,9 @@ class MessagePassingPlan:
         return "mp_coop_bwd_kernel" if self.coop else "mp_edge_bwd_kernel"
 
     # dram bytes per launch on the C4 graph from the committed ncu captures (bench.py `roofline.traffic`)
-    fwd_traffic_bytes = 0.627e9
-    bwd_traffic_bytes = 1.53e9
-    traffic_source = "ncu --set full, dram read + write per launch on the C4 graph (profiles/r01_mp_ncu.md)"
+    fwd_traffic_bytes = 0.605e9
+    bwd_traffic_bytes = 1.455e9
+    traffic_source = "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch on the C4 graph (profiles/r02_mp_coop_notes.md)"
 
     def _ok(self, F):
         return self.coop and F % 4 == 0 and F <= 128
