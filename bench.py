@@ -44,7 +44,7 @@ import systems  # noqa: E402  (synthetic inputs; shared with tests and the golde
 METRIC = "frames_per_sec_energy_forces_tensornet_10k_atom_box"
 UNIT = "frames/s"
 PARITY_TOL = 1e-4   # BASELINE.json north_star: energies/forces within 1e-4 relative fp32
-GOLDEN_FULL = {"c4": "c4_water10125_tensornet_L3", "c3": "c3_et_spice_256mol", "c5": "c5_8x5000_tensornet_L2"}
+GOLDEN_FULL = {"c4": "c4_water10125_tensornet_L3", "c3": "c3_et_spice_256mol", "c5": "c5_8x5000_tensornet_L2", "tn2": "tn2_256mol_charged"}
 
 
 def workload(name, seed=0, n_boxes=8):
@@ -64,9 +64,20 @@ def workload(name, seed=0, n_boxes=8):
         hp = systems.tensornet_hparams(num_layers=2, F=128, R=32, cutoff=5.0, max_nb=128)
         z, pos, batch, box = systems.random_box(5000, seed=seed, n_boxes=n_boxes)
         desc = f"C5: TensorNet-ANI2X config (2 layers, F=128), ONE batch of {n_boxes} x 5000-atom periodic boxes sharded over the ranks (8 per GPU), energy+forces"
+    elif name == "tn2":
+        # the architecture of the released AceFF-2.0 checkpoints -- TensorNet2 (charge-conditioned edge MLP,
+        # per-molecule charge equilibration) + ScalarPlusWeightedCoulomb, all-pairs Coulomb inside each molecule, total charges given
+        hp = systems.tensornet_hparams(num_layers=2, F=128, R=32, cutoff=5.0, max_nb=128)
+        hp.update(model="tensornet2", output_model="ScalarPlusWeightedCoulomb", q_dim=16, q_weights=[1.0, 0.5, 2.0], coulomb_cutoff=None,
+                  coulomb_max_num_neighbors=256, reduce_op="sum", static_shapes=False)
+        z, pos, batch, box = systems.molecule_batch(n_mol=256, seed=seed)
+        g = torch.Generator().manual_seed(100 + seed)
+        q = torch.randint(-1, 2, (256,), generator=g).float()
+        desc = "TN2: TensorNet2 (2 layers, F=128, q_dim=16) + ScalarPlusWeightedCoulomb, 256 molecules x 20-40 atoms with total charges -1/0/+1, energy+forces"
+        return hp, z, pos, batch, box, desc, q
     else:
         raise ValueError(name)
-    return hp, z, pos, batch, box, desc
+    return hp, z, pos, batch, box, desc, None
 
 
 def seeded_model(hp, seed=1):
@@ -190,7 +201,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    hp, z, pos, batch, box, desc = workload(args.workload)
+    hp, z, pos, batch, box, desc, _q = workload(args.workload)
     if hp["model"] != "tensornet":
         print(json.dumps({"impl": "reference", "unavailable": "the CPU arm is defined for the TensorNet workloads (c4, c2, c5)"}), flush=True)
         return
@@ -264,7 +275,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3", "c5"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3", "c5", "tn2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch the kernels of a frame from Python instead of replaying a CUDA graph")
@@ -296,12 +307,16 @@ def main():
     shard_info = None
     if args.workload == "c5":
         # ONE batch of 8*world boxes, sharded over the ranks (BASELINE configs[4]: 64 x 5000 atoms on 8 GPUs)
-        hp, gz, gpos, gbatch, gbox, desc = workload("c5", seed=0, n_boxes=8 * world)
+        hp, gz, gpos, gbatch, gbox, desc, _ = workload("c5", seed=0, n_boxes=8 * world)
         z, pos, batch, box, _, sys_rng, atom_sl = parallel.shard_batch(gz, gpos, gbatch, gbox, None, rank, world)
         shard_info = (gz, gpos, gbatch, gbox, sys_rng)
         args.eager = True  # 40k atoms at max_num_neighbors=128: exact-size (dynamic) buffers instead of 2.4x capacity ones
     else:
-        hp, z, pos, batch, box, desc = workload(args.workload, seed=rank)
+        hp, z, pos, batch, box, desc, q_sys = workload(args.workload, seed=rank)
+    if args.workload == "c5":
+        q_sys = None
+    if args.workload == "tn2":
+        args.eager = True   # all-pairs Coulomb + per-molecule equilibration: dynamic shapes
     is_tn = hp["model"] == "tensornet"
     hp["static_shapes"] = (not args.eager) and is_tn   # capacity-sized buffers + device counters: the frame is CUDA-graph capturable
     model = seeded_model(hp).to(dev)
@@ -310,6 +325,7 @@ def main():
     zd, bd, boxd = z.to(dev), batch.to(dev), (None if box is None else box.to(dev))
     n_sys = int(batch.max()) + 1
     pos_d = pos.to(dev)
+    qd = None if q_sys is None else q_sys.to(dev)
 
     def barrier():
         if dist_on:
@@ -318,7 +334,7 @@ def main():
 
     # radial tables etc. are built by the first evaluation (weights only; reported as table_build_s)
     torch.cuda.synchronize(); t_b = time.perf_counter()
-    y_first, f_first = model(zd, pos_d.clone(), bd, box=boxd, num_systems=n_sys)
+    y_first, f_first = model(zd, pos_d.clone(), bd, box=boxd, q=qd, num_systems=n_sys)
     torch.cuda.synchronize(); table_build_s = time.perf_counter() - t_b
     y_first, f_first = y_first.detach().clone(), f_first.detach().clone()
 
@@ -326,10 +342,10 @@ def main():
     graph_allreduce = False
     if not args.eager and is_tn:  # (the ET module reads the pair counter on the host: eager only)
         graph_allreduce = dist_on and os.environ.get("TMD_GRAPH_ALLREDUCE", "1") != "0"
-        ff = CUDAGraphForceField(model, zd, bd, box=boxd, num_systems=n_sys, allreduce_total=graph_allreduce).capture(pos_d)
+        ff = CUDAGraphForceField(model, zd, bd, box=boxd, q=qd, num_systems=n_sys, allreduce_total=graph_allreduce).capture(pos_d)
 
     def frame(p):
-        y, f = ff(p) if ff is not None else model(zd, p, bd, box=boxd, num_systems=n_sys)
+        y, f = ff(p) if ff is not None else model(zd, p, bd, box=boxd, q=qd, num_systems=n_sys)
         if dist_on and not graph_allreduce:  # the single collective of the path: total energy over all boxes
             tot = y.sum()
             dist.all_reduce(tot)
@@ -340,7 +356,7 @@ def main():
     barrier()
     launches_per_frame = None
     if ff is not None:  # count this library's launches in one frame with an eager evaluation (the graph replays the same nodes)
-        l_a = _lib.launches(); model(zd, pos_d.clone(), bd, box=boxd, num_systems=n_sys); launches_per_frame = _lib.launches() - l_a
+        l_a = _lib.launches(); model(zd, pos_d.clone(), bd, box=boxd, q=qd, num_systems=n_sys); launches_per_frame = _lib.launches() - l_a
         barrier()
     l0 = _lib.launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -375,7 +391,7 @@ def main():
         def frame_e2e():
             zz, pp, bb = h_z.to(dev, non_blocking=True), h_pos.to(dev, non_blocking=True), h_batch.to(dev, non_blocking=True)
             xx = h_box.to(dev, non_blocking=True) if box is not None else None
-            e, f = model(zz, pp, bb, box=xx, num_systems=n_sys)
+            e, f = model(zz, pp, bb, box=xx, q=qd, num_systems=n_sys)
             if dist_on:
                 tot = e.sum(); dist.all_reduce(tot)
             h_e.copy_(e, non_blocking=True); h_f.copy_(f, non_blocking=True)
@@ -395,8 +411,8 @@ def main():
         try:
             ff2 = None
             if ff is not None:
-                ff2 = CUDAGraphForceField(model, zd, bd, box=boxd, num_systems=n_sys, allreduce_total=graph_allreduce).capture(pos_d)
-            frame2 = (lambda: ff2(pos_d)) if ff2 is not None else (lambda: model(zd, pos_d.clone(), bd, box=boxd, num_systems=n_sys))
+                ff2 = CUDAGraphForceField(model, zd, bd, box=boxd, q=qd, num_systems=n_sys, allreduce_total=graph_allreduce).capture(pos_d)
+            frame2 = (lambda: ff2(pos_d)) if ff2 is not None else (lambda: model(zd, pos_d.clone(), bd, box=boxd, q=qd, num_systems=n_sys))
             for _ in range(3):
                 frame2()
             ms3 = time_loop(frame2, args.steps, barrier, ev0, ev1, dist_on, dev)

@@ -70,8 +70,29 @@ def write(name, hp, z, pos, batch, box, gen, chunks, seed=1):
     print(f"[{name}] N={z.numel()} E={y.flatten()[:3].tolist()} max|F|={f.abs().max():.4f}  ({time.time() - t0:.0f} s)")
 
 
+def write_tn2():
+    """bench.py --workload tn2: TensorNet2 + ScalarPlusWeightedCoulomb on 256 charged molecules (the oracle functions of this row are
+    pinned to the unmodified reference by make_golden_tn2.py)"""
+    import bench
+    hp, z, pos, batch, box, desc, q = bench.workload("tn2", seed=0)
+    t0 = time.time()
+    sd = orc.cast_state_dict(seeded_sd(hp, 1), torch.float64)
+    y, f = orc.energy_and_forces(sd, hp, z, pos.double(), batch, None, q.double())
+    fx = dict(name="tn2_256mol_charged", hparams=hp, generator="bench.workload('tn2', seed=0)", weight_seed=1, n_atoms=int(z.numel()),
+              ref_E64=y, ref_F64=f, input_digest=digest(z, pos, batch), note="fp64 oracle (plain mode)")
+    torch.save(fx, os.path.join(OUT, "tn2_256mol_charged.pt"))
+    print(f"[tn2] N={z.numel()} E={y.flatten()[:3].tolist()} max|F|={f.abs().max():.4f}  ({time.time() - t0:.0f} s)")
+
+
 def main():
     which = set(sys.argv[1:]) or {"c4", "c3", "c5"}
+    if "tn2" in which:
+        torch.set_num_threads(os.cpu_count() or 8)
+        os.makedirs(OUT, exist_ok=True)
+        write_tn2()
+        which.discard("tn2")
+        if not which:
+            return
     torch.set_num_threads(os.cpu_count() or 8)
     os.makedirs(OUT, exist_ok=True)
     pin_chunked_mode()

@@ -27,7 +27,7 @@ from torchmdnet_b200.extensions import fused  # noqa: E402
 if args.exact:
     fused.USE_RADIAL_TABLE = False
 dev = torch.device("cuda:0")
-hp, z, pos, batch, box, desc = bench.workload(args.workload, seed=0)
+hp, z, pos, batch, box, desc, q_sys = bench.workload(args.workload, seed=0)
 hp["static_shapes"] = hp["model"] == "tensornet"
 model = bench.seeded_model(hp).to(dev)
 for p_ in model.parameters():
@@ -35,12 +35,13 @@ for p_ in model.parameters():
 zd, pd, bd = z.to(dev), pos.to(dev), batch.to(dev)
 xd = None if box is None else box.to(dev)
 n_sys = int(batch.max()) + 1
+qd = None if q_sys is None else q_sys.to(dev)
 for _ in range(3):
-    model(zd, pd.clone(), bd, box=xd, num_systems=n_sys)
+    model(zd, pd.clone(), bd, box=xd, q=qd, num_systems=n_sys)
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
 for _ in range(args.frames):
-    y, f = model(zd, pd.clone(), bd, box=xd, num_systems=n_sys)
+    y, f = model(zd, pd.clone(), bd, box=xd, q=qd, num_systems=n_sys)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print(desc, float(y.sum()))

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch, bench
 from torchmdnet_b200.calculators import CUDAGraphForceField
 dev = torch.device("cuda:0")
-hp, z, pos, batch, box, desc = bench.workload("c4", seed=0)
+hp, z, pos, batch, box, desc, q_sys = bench.workload("c4", seed=0)
 hp["static_shapes"] = True
 model = bench.seeded_model(hp).to(dev)
 for p_ in model.parameters(): p_.requires_grad_(False)

@@ -86,3 +86,16 @@ def test_c5_eight_boxes_of_5000():
     eE, eF = errs(y, f, fx)
     print(f"C5 per GPU: relE={eE:.2e} relF={eF:.2e}")
     assert eE < TOL and eF < TOL
+
+
+def test_tn2_256_charged_molecules():
+    """SURVEY 8(f) item 3 at bench size: TensorNet2 + ScalarPlusWeightedCoulomb (all-pairs Coulomb, total charges -1/0/+1) on the
+    `bench.py --workload tn2` input against the fp64 oracle (pinned to the unmodified reference by oracle/make_golden_tn2.py)"""
+    import bench
+    hp, z, pos, batch, box, _, q = bench.workload("tn2", seed=0)
+    fx = load("tn2_256mol_charged", z, pos, batch)
+    m = seeded_model(hp, fx["weight_seed"])
+    y, f = m(z.to(dev), pos.to(dev), batch.to(dev), q=q.to(dev), num_systems=256)
+    eE, eF = errs(y, f, fx)
+    print(f"TN2 256 molecules: relE={eE:.2e} relF={eF:.2e}")
+    assert eE < TOL and eF < TOL
