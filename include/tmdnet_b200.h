@@ -258,6 +258,8 @@ int tmd_embed_moments_bwd(const float* vec, const float* dist, const int* nbr_j,
  *   epi 0: z = acc + vec[col]; zout (may be NULL) = z; out = SiLU(z)        (forward layer, saves the pre-activation)
  *   epi 1: out = acc * SiLU'(aux[row,col])                                  (backward through an activation)
  *   epi 2: out = acc * vec[col]                                             (backward into a LayerNorm: x gamma)
+ *   epi 3: out = acc (+ vec[col] when vec != NULL)                          (plain Linear / its transposed backward)
+ *   epi 4: out = acc + aux[row,col]                                         (gradient of a tensor consumed by two Linears)
  * K % 16 == 0, N % 32 == 0.
  * tmd_norm_ln_fwd: xn = LayerNorm(norm(X)), mode 3: norm = (3 I^2, |A|^2, |S|^2) in R^{3F} (tensor_norm3), mode 2: |X|^2 per channel
  * in R^F; saves (mu, rstd) [N,2].  tmd_norm_ln_bwd: g [N,K] = d xn * gamma -> gX = add + d/dX (add: all NULL or all given).
@@ -276,6 +278,20 @@ int tmd_head_seed(const float* gy, const int64_t* batch, int M, const float* std
                   void* stream);
 int tmd_gate_bwd_preact(const float* I, const float* A, const float* S, const float* z, const float* dI, const float* dA, const float* dS,
                         float* gI, float* gA, float* gS, float* dg, int chain, int N, int F, void* stream);
+/* ---- a15: EquivariantScalar head of the ET = two GatedEquivariantBlocks (reference models/utils.py:583-655, output_modules.py:159-163).
+ * The projections and the update MLP run on tmd_rows_gemm (epilogue 3 = plain Linear, 4 = acc + aux for a tensor consumed by two
+ * Linears) or, for layers with <= 8 outputs (the last block's Linear(F/2 -> 2) and vec2_proj(F/2 -> 1)), on tmd_rows_narrow_fwd/bwd;
+ * around them: tmd_geb_cat_fwd: cat [N,2H] = [x | |P1|] with |P1| the norm over the 3 vector components of P1 = vec1_proj(v)
+ * (0 for an all-zero row, like the reference's masked torch.norm); tmd_geb_cat_bwd: g_P1 = g_vec1 * P1 / |P1|;
+ * tmd_geb_out_fwd: hh [N,2O] = [xo | gate] -> xo_out = act ? SiLU(xo) : xo, vo = gate * V2; tmd_geb_out_bwd: its backward
+ * (g_xo with row stride ldgx, g_xo / g_vo may be NULL = zero). */
+int tmd_geb_cat_fwd(const float* x, const float* P1, int N, int H, float* cat, void* stream);
+int tmd_geb_cat_bwd(const float* P1, const float* cat, const float* g_cat, int N, int H, float* g_P1, void* stream);
+int tmd_geb_out_fwd(const float* hh, const float* V2, int N, int O, int act, float* xo, float* vo, void* stream);
+int tmd_geb_out_bwd(const float* hh, const float* V2, const float* g_xo, int ldgx, const float* g_vo, int N, int O, int act, float* g_hh,
+                    float* g_V2, void* stream);
+int tmd_rows_narrow_fwd(const float* A, int lda, const float* W, int M, int K, int Nn, const float* b, float* out, void* stream);
+int tmd_rows_narrow_bwd(const float* dOut, const float* Wn, int M, int K, int Nn, int accumulate, const float* aux, float* dA, void* stream);
 /* P1 backward with the incoming gradient given as two tensors (d1 + d2), and P3 backward for the dX branch only (the Xn branch of
  * X' = Xn + dX + qf dX.dX is the identity): what the hand-sequenced backward of one interaction layer needs
  * (extensions/fused.py::_InteractionLayer; models/tensornet.py:745, :812). */

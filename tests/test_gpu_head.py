@@ -75,3 +75,30 @@ def test_model_selects_fused_head_and_matches_torch_head():
     m.fused_head_path = False
     y0, f0 = m(*args, box=box.to(dev))
     assert (y1 - y0).abs().max() <= 1e-5 * (1 + y0.abs().max()) and (f1 - f0).abs().max() <= 2e-5 * f0.abs().max()
+
+
+@pytest.mark.parametrize("F,prior", [(128, False), (64, True)])
+def test_et_head_kernels_vs_torch_head(F, prior):
+    """row a15: the two gated equivariant blocks of EquivariantScalar + std / atomref / per-molecule sum / mean as one autograd node
+    (fused.et_head_energy: GEMM launches + the geb_* kernels, hand-sequenced backward) == the torch-op head, energies and forces"""
+    from torchmdnet_b200.models.model import create_model
+    from torchmdnet_b200 import priors
+    hp = systems.et_hparams(num_layers=2, F=F, R=32, H=4, cutoff=5.0, max_nb=64)
+    hp["output_model"] = "EquivariantScalar"
+    random.seed(7); np.random.seed(7); torch.manual_seed(7)
+    pm = None
+    if prior:
+        pm = priors.Atomref(max_z=hp["max_z"])
+        pm.atomref.weight.data.copy_(torch.randn(hp["max_z"], 1))
+    m = create_model(dict(hp), prior_model=pm, mean=torch.tensor(-0.21), std=torch.tensor(1.7)).eval().to(dev)
+    z, pos, batch, _ = systems.molecule_batch(n_mol=5, lo=9, hi=15, spread=3.0, seed=3)
+    args = (z.to(dev), pos.to(dev), batch.to(dev))
+    assert m._fused_et_head() is None               # parameters require grad: torch-op head
+    for p_ in m.parameters():
+        p_.requires_grad_(False)
+    assert m._fused_et_head() is not None
+    y1, f1 = m(*args)
+    m.fused_head_path = False
+    y0, f0 = m(*args)
+    assert (y1 - y0).abs().max() <= 2e-5 * (1 + y0.abs().max()), float((y1 - y0).abs().max())
+    assert (f1 - f0).abs().max() <= 2e-5 * (1e-6 + f0.abs().max()), float((f1 - f0).abs().max() / f0.abs().max())

@@ -82,6 +82,12 @@ SIGNATURES = {
     "tmd_norm_ln_bwd": ([P, P, P, I, I, I] + [P] * 8 + [P], 1),
     "tmd_head_energy": ([P, I, I, P, P, P, P, P, I, P, P], 1),
     "tmd_head_seed": ([P, P, I, P, P, P, I, I, P, P], 1),
+    "tmd_geb_cat_fwd": ([P, P, I, I, P, P], 1),
+    "tmd_geb_cat_bwd": ([P, P, P, I, I, P, P], 1),
+    "tmd_geb_out_fwd": ([P, P, I, I, I, P, P, P], 1),
+    "tmd_geb_out_bwd": ([P, P, P, I, P, I, I, I, P, P, P], 1),
+    "tmd_rows_narrow_fwd": ([P, I, P, I, I, I, P, P, P], 1),
+    "tmd_rows_narrow_bwd": ([P, P, I, I, I, I, P, P, P], 1),
     "tmd_p1_bwd2": ([P] * 12 + [I, I, P], 1),
     "tmd_p3_bwd_dx": ([P] * 10 + [I, I, P], 1),
     "tmd_embed_moments_fwd": ([P] * 10 + [D, D, D, I, I, I, I] + [P] * 3 + [P], 1),

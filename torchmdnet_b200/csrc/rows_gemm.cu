@@ -26,7 +26,7 @@ namespace {
 constexpr int BM = 64, BK = 16, GST = 4, GT = 256;     // rows per tile, k per stage, stages, threads
 constexpr int ALD = BK + 4;                            // A tile row stride (20: fragment reads hit 32 banks)
 
-enum Epi { EPI_BIAS_SILU = 0, EPI_MUL_SILU_GRAD = 1, EPI_COLSCALE = 2 };
+enum Epi { EPI_BIAS_SILU = 0, EPI_MUL_SILU_GRAD = 1, EPI_COLSCALE = 2, EPI_LINEAR = 3, EPI_ADD = 4 };
 
 template <int BN>
 __device__ __forceinline__ void stage_tiles(float* As, float* Bs, const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
@@ -119,8 +119,13 @@ __global__ void __launch_bounds__(GT) rows_gemm_kernel(const float* __restrict__
       } else if (EPI == EPI_MUL_SILU_GRAD) {
         const float2 z = *reinterpret_cast<const float2*>(aux + (size_t)row * ldaux + col);
         v0 *= tn::silu_grad(z.x); v1 *= tn::silu_grad(z.y);
-      } else {
+      } else if (EPI == EPI_COLSCALE) {
         v0 *= __ldg(vec + col); v1 *= __ldg(vec + col + 1);
+      } else if (EPI == EPI_LINEAR) {
+        if (vec) { v0 += __ldg(vec + col); v1 += __ldg(vec + col + 1); }
+      } else {
+        const float2 z = *reinterpret_cast<const float2*>(aux + (size_t)row * ldaux + col);
+        v0 += z.x; v1 += z.y;
       }
       *reinterpret_cast<float2*>(out + (size_t)row * ldo + col) = make_float2(v0, v1);
     }
@@ -241,6 +246,90 @@ __global__ void head_seed_kernel(const float* __restrict__ gy, const int64_t* __
   }
 }
 
+// ---------------------------------------------------------------------------------------------- a15: GatedEquivariantBlock pieces
+// (reference models/utils.py:583-655).  cat [N, 2H] = [x | vec1], vec1[n,h] = |P1[n,:,h]| over the 3 vector components (0 for an
+// all-zero row; the reference masks those rows out of torch.norm so that the gradient stays finite).
+__global__ void geb_cat_fwd_kernel(const float* __restrict__ x, const float* __restrict__ P1, int N, int H, float* __restrict__ cat) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)N * H; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / H; const int h = (int)(i - n * H);
+    const float a = P1[(n * 3) * H + h], b = P1[(n * 3 + 1) * H + h], c = P1[(n * 3 + 2) * H + h];
+    const float sq = a * a + b * b + c * c;
+    cat[n * 2 * H + h] = x[i];
+    cat[n * 2 * H + H + h] = sq > 0.f ? sqrtf(sq) : 0.f;
+  }
+}
+// g_P1[n,c,h] = g_vec1[n,h] * P1[n,c,h] / vec1[n,h]  (0 where vec1 = 0); g_cat [N, 2H] holds g_vec1 in its second half
+__global__ void geb_cat_bwd_kernel(const float* __restrict__ P1, const float* __restrict__ cat, const float* __restrict__ g_cat, int N, int H,
+                                   float* __restrict__ g_P1) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)N * H; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / H; const int h = (int)(i - n * H);
+    const float v1 = cat[n * 2 * H + H + h];
+    const float s = v1 > 0.f ? g_cat[n * 2 * H + H + h] / v1 : 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g_P1[(n * 3 + c) * H + h] = s * P1[(n * 3 + c) * H + h];
+  }
+}
+// hh [N, 2O] = [xo | gate]; V2 [N,3,O]: xo_out = act ? SiLU(xo) : xo, vo = gate * V2
+__global__ void geb_out_fwd_kernel(const float* __restrict__ hh, const float* __restrict__ V2, int N, int O, int act, float* __restrict__ xo,
+                                   float* __restrict__ vo) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)N * O; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / O; const int o = (int)(i - n * O);
+    const float a = hh[n * 2 * O + o], gate = hh[n * 2 * O + O + o];
+    xo[i] = act ? tn::silu(a) : a;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) vo[(n * 3 + c) * O + o] = gate * V2[(n * 3 + c) * O + o];
+  }
+}
+// g_hh [N, 2O] = [g_xo * (act ? SiLU'(xo) : 1) | sum_c g_vo * V2],  g_V2 = gate * g_vo   (g_xo / g_vo may be NULL = zero)
+__global__ void geb_out_bwd_kernel(const float* __restrict__ hh, const float* __restrict__ V2, const float* __restrict__ g_xo, int ldgx,
+                                   const float* __restrict__ g_vo, int N, int O, int act, float* __restrict__ g_hh, float* __restrict__ g_V2) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)N * O; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / O; const int o = (int)(i - n * O);
+    const float a = hh[n * 2 * O + o], gate = hh[n * 2 * O + O + o];
+    const float gx = g_xo ? g_xo[n * ldgx + o] : 0.f;
+    g_hh[n * 2 * O + o] = act ? gx * tn::silu_grad(a) : gx;
+    float gg = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float gv = g_vo ? g_vo[(n * 3 + c) * O + o] : 0.f;
+      gg = fmaf(gv, V2[(n * 3 + c) * O + o], gg);
+      g_V2[(n * 3 + c) * O + o] = gate * gv;
+    }
+    g_hh[n * 2 * O + O + o] = gg;
+  }
+}
+// narrow layers (Nn <= 8 outputs, e.g. the last block's Linear(F/2 -> 2) and vec2_proj(F/2 -> 1)): warp per row.
+// fwd: out[r][c] = sum_k A[r][k] W[k][c] (+ b[c]);   bwd: dA[r][k] (+)= sum_c dOut[r][c] Wn[c][k]   (Wn = the nn.Linear weight)
+__global__ void __launch_bounds__(256) rows_narrow_fwd_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int M, int K,
+                                                              int Nn, const float* __restrict__ b, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (long long r = blockIdx.x * wpb + (threadIdx.x >> 5); r < M; r += (long long)gridDim.x * wpb) {
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float a = A[r * lda + k];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) if (c < Nn) acc[c] = fmaf(a, __ldg(W + (size_t)k * Nn + c), acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) if (c < Nn) acc[c] = warp_sum(acc[c]);
+    if (lane == 0)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) if (c < Nn) out[r * Nn + c] = acc[c] + (b ? __ldg(b + c) : 0.f);
+  }
+}
+__global__ void rows_narrow_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Wn, int M, int K, int Nn, int accumulate,
+                                       const float* __restrict__ aux, float* __restrict__ dA) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)M * K; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / K; const int k = (int)(i - r * K);
+    float s = 0.f;
+    for (int c = 0; c < Nn; ++c) s = fmaf(dOut[r * Nn + c], __ldg(Wn + (size_t)c * K + k), s);
+    if (aux) s *= tn::silu_grad(aux[i]);          // backward through the activation that produced the layer's input
+    dA[i] = accumulate ? dA[i] + s : s;
+  }
+}
+
 template <int BN, int EPI>
 int launch_gemm(const float* A, int lda, const float* W, int ldw, int M, int K, int N, const float* vec, const float* aux, int ldaux,
                 float* zout, float* out, int ldo, cudaStream_t st) {
@@ -259,13 +348,16 @@ extern "C" {
 // epi 0: z = acc + vec[col]; zout (may be NULL, row stride ldo) = z; out = SiLU(z)
 // epi 1: out = acc * SiLU'(aux[row, col])
 // epi 2: out = acc * vec[col]
+// epi 3: out = acc (+ vec[col] when vec != NULL)          plain Linear / its transposed backward
+// epi 4: out = acc + aux[row, col]                         backward of a tensor consumed by two Linears
 int tmd_rows_gemm(const float* A, int lda, const float* W, int ldw, int M, int K, int N, int epi, const float* vec, const float* aux,
                   int ldaux, float* zout, float* out, int ldo, void* stream) {
   TMD_REQUIRE(A && W && out, "rows_gemm: null pointer");
   TMD_REQUIRE(M >= 0 && K > 0 && K % BK == 0 && N > 0 && N % 32 == 0, "rows_gemm: need K % 16 == 0 and N % 32 == 0");
   TMD_REQUIRE(lda % 4 == 0 && ldw % 4 == 0 && ldo % 2 == 0 && lda >= K && ldw >= N && ldo >= N, "rows_gemm: bad leading dimension");
-  TMD_REQUIRE(epi >= 0 && epi <= 2, "rows_gemm: unknown epilogue");
-  TMD_REQUIRE(epi == EPI_MUL_SILU_GRAD ? (aux && ldaux >= N && ldaux % 2 == 0) : vec != nullptr, "rows_gemm: epilogue operand missing");
+  TMD_REQUIRE(epi >= 0 && epi <= 4, "rows_gemm: unknown epilogue");
+  TMD_REQUIRE((epi == EPI_MUL_SILU_GRAD || epi == EPI_ADD) ? (aux && ldaux >= N && ldaux % 2 == 0) : (epi == EPI_LINEAR || vec != nullptr),
+              "rows_gemm: epilogue operand missing");
   if (M == 0) return TMD_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const bool wide = N % 64 == 0;
@@ -274,7 +366,9 @@ int tmd_rows_gemm(const float* A, int lda, const float* W, int ldw, int M, int K
               : launch_gemm<32, E>(A, lda, W, ldw, M, K, N, vec, aux, ldaux, zout, out, ldo, st)
   if (epi == EPI_BIAS_SILU) { TMD_GEMM_CASE(EPI_BIAS_SILU); }
   if (epi == EPI_MUL_SILU_GRAD) { TMD_GEMM_CASE(EPI_MUL_SILU_GRAD); }
-  TMD_GEMM_CASE(EPI_COLSCALE);
+  if (epi == EPI_COLSCALE) { TMD_GEMM_CASE(EPI_COLSCALE); }
+  if (epi == EPI_LINEAR) { TMD_GEMM_CASE(EPI_LINEAR); }
+  TMD_GEMM_CASE(EPI_ADD);
 #undef TMD_GEMM_CASE
 }
 
@@ -321,6 +415,47 @@ int tmd_head_seed(const float* gy, const int64_t* batch, int M, const float* std
   if (N == 0) return TMD_OK;
   head_seed_kernel<<<tmd_blocks_for((long long)N * H, 256), 256, 0, (cudaStream_t)stream>>>(gy, batch, M, std_, w3, z2, N, H, dz2);
   return tmd_check_launch("head_seed");
+}
+
+// ---- a15 (ET output head): pieces of GatedEquivariantBlock around the GEMM launches (reference models/utils.py:583-655)
+int tmd_geb_cat_fwd(const float* x, const float* P1, int N, int H, float* cat, void* stream) {
+  TMD_REQUIRE(x && P1 && cat && H > 0, "geb_cat_fwd: null pointer");
+  if (N == 0) return TMD_OK;
+  geb_cat_fwd_kernel<<<tmd_blocks_for((long long)N * H, 256), 256, 0, (cudaStream_t)stream>>>(x, P1, N, H, cat);
+  return tmd_check_launch("geb_cat_fwd");
+}
+int tmd_geb_cat_bwd(const float* P1, const float* cat, const float* g_cat, int N, int H, float* g_P1, void* stream) {
+  TMD_REQUIRE(P1 && cat && g_cat && g_P1 && H > 0, "geb_cat_bwd: null pointer");
+  if (N == 0) return TMD_OK;
+  geb_cat_bwd_kernel<<<tmd_blocks_for((long long)N * H, 256), 256, 0, (cudaStream_t)stream>>>(P1, cat, g_cat, N, H, g_P1);
+  return tmd_check_launch("geb_cat_bwd");
+}
+int tmd_geb_out_fwd(const float* hh, const float* V2, int N, int O, int act, float* xo, float* vo, void* stream) {
+  TMD_REQUIRE(hh && V2 && xo && vo && O > 0, "geb_out_fwd: null pointer");
+  if (N == 0) return TMD_OK;
+  geb_out_fwd_kernel<<<tmd_blocks_for((long long)N * O, 256), 256, 0, (cudaStream_t)stream>>>(hh, V2, N, O, act, xo, vo);
+  return tmd_check_launch("geb_out_fwd");
+}
+int tmd_geb_out_bwd(const float* hh, const float* V2, const float* g_xo, int ldgx, const float* g_vo, int N, int O, int act, float* g_hh,
+                    float* g_V2, void* stream) {
+  TMD_REQUIRE(hh && V2 && g_hh && g_V2 && O > 0 && (!g_xo || ldgx >= O), "geb_out_bwd: null pointer / bad stride");
+  if (N == 0) return TMD_OK;
+  geb_out_bwd_kernel<<<tmd_blocks_for((long long)N * O, 256), 256, 0, (cudaStream_t)stream>>>(hh, V2, g_xo, ldgx, g_vo, N, O, act, g_hh, g_V2);
+  return tmd_check_launch("geb_out_bwd");
+}
+// out[M, Nn] = A[M, K] . W[K, Nn] (+ b), Nn <= 8
+int tmd_rows_narrow_fwd(const float* A, int lda, const float* W, int M, int K, int Nn, const float* b, float* out, void* stream) {
+  TMD_REQUIRE(A && W && out && K > 0 && Nn > 0 && Nn <= 8 && lda >= K, "rows_narrow_fwd: need 1 <= Nn <= 8");
+  if (M == 0) return TMD_OK;
+  rows_narrow_fwd_kernel<<<tmd_blocks_for((long long)M * 32, 256), 256, 0, (cudaStream_t)stream>>>(A, lda, W, M, K, Nn, b, out);
+  return tmd_check_launch("rows_narrow_fwd");
+}
+// dA[M, K] (+)= (dOut[M, Nn] . Wn[Nn, K]) (* SiLU'(aux[M, K]) when aux != NULL), Nn <= 8
+int tmd_rows_narrow_bwd(const float* dOut, const float* Wn, int M, int K, int Nn, int accumulate, const float* aux, float* dA, void* stream) {
+  TMD_REQUIRE(dOut && Wn && dA && K > 0 && Nn > 0 && Nn <= 8, "rows_narrow_bwd: need 1 <= Nn <= 8");
+  if (M == 0) return TMD_OK;
+  rows_narrow_bwd_kernel<<<tmd_blocks_for((long long)M * K, 256), 256, 0, (cudaStream_t)stream>>>(dOut, Wn, M, K, Nn, accumulate, aux, dA);
+  return tmd_check_launch("rows_narrow_bwd");
 }
 
 }  // extern "C"

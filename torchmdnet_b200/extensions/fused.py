@@ -886,6 +886,141 @@ def embedding_tail(X, nl: IrrepsLinearWeights, mw: EmbedMlpWeights):
     return _EmbeddingTail.apply(X[0], X[1], X[2], nl, mw)
 
 
+# ------------------------------------------------------------------------------------------ ET output head (row a15)
+def _linear_rows(A: Tensor, Wt: Tensor, bias: Optional[Tensor] = None) -> Tensor:
+    """A [M,K] . Wt [K,Nout] (+ bias): the weight-tiled GEMM, or the warp-per-row kernel for layers with <= 8 outputs"""
+    if Wt.shape[1] % 32 == 0:
+        return rows_gemm(A, Wt, 3, vec=bias)
+    M, K = A.shape
+    out = torch.empty(M, Wt.shape[1], device=A.device, dtype=torch.float32)
+    _lib.call("tmd_rows_narrow_fwd", p(A), A.stride(0), p(Wt), M, K, Wt.shape[1], p(bias), p(out), device=A.device)
+    return out
+
+
+class GatedBlockWeights:
+    """One GatedEquivariantBlock (reference models/utils.py:583-655) in the layouts of csrc/rows_gemm.cu, cached per weight version."""
+
+    def __init__(self, block):
+        self.block = block
+        self._key = None
+
+    def params(self):
+        b = self.block
+        lin_a, lin_b = b.update_net.layers[0], b.update_net.layers[-1]
+        return [b.vec1_proj.weight, b.vec2_proj.weight, lin_a.weight, lin_a.bias, lin_b.weight, lin_b.bias]
+
+    def frozen(self) -> bool:
+        return not any(t.requires_grad for t in self.params())
+
+    def supported(self) -> bool:
+        b = self.block
+        layers = b.update_net.layers
+        if len(layers) != 3 or not isinstance(layers[1], torch.nn.SiLU) or (b.act is not None and not isinstance(b.act, torch.nn.SiLU)):
+            return False
+        Hh, O, I = b.vec1_proj.in_features, b.out_channels, layers[0].out_features
+        wide = lambda n: n % 32 == 0
+        return (Hh % 32 == 0 and I % 32 == 0 and layers[0].in_features == 2 * Hh and layers[-1].out_features == 2 * O and
+                (wide(O) and O % 16 == 0 or O <= 4) and all(t.dtype == torch.float32 for t in self.params()))
+
+    def tensors(self):
+        key = tuple((t.data_ptr(), t._version) for t in self.params())
+        if key != self._key:
+            b = self.block
+            lin_a, lin_b = b.update_net.layers[0], b.update_net.layers[-1]
+            d = lambda t: t.detach().contiguous()
+            self._t = dict(W1T=d(b.vec1_proj.weight.detach().t()), W1=d(b.vec1_proj.weight), W2T=d(b.vec2_proj.weight.detach().t()),
+                           W2=d(b.vec2_proj.weight), WaT=d(lin_a.weight.detach().t()), Wa=d(lin_a.weight), ba=d(lin_a.bias),
+                           WbT=d(lin_b.weight.detach().t()), Wb=d(lin_b.weight), bb=d(lin_b.bias), O=b.out_channels,
+                           act=int(b.act is not None))
+            self._key = key
+        return self._t
+
+
+def _geb_forward(x, v, t):
+    """one gated block: x [N,Hh], v [N,3,Hh] -> (xo [N,O], vo [N,3,O], saved tensors)"""
+    N, Hh, O, dev = x.shape[0], x.shape[1], t["O"], x.device
+    v2d = v.reshape(3 * N, Hh)
+    P1 = _linear_rows(v2d, t["W1T"])
+    V2 = _linear_rows(v2d, t["W2T"])
+    cat = torch.empty(N, 2 * Hh, device=dev, dtype=torch.float32)
+    _lib.call("tmd_geb_cat_fwd", p(x), p(P1), N, Hh, p(cat), device=dev)
+    z1, h1 = rows_gemm(cat, t["WaT"], 0, vec=t["ba"], save_z=True)
+    hh = _linear_rows(h1, t["WbT"], t["bb"])
+    xo = torch.empty(N, O, device=dev, dtype=torch.float32)
+    vo = torch.empty(N, 3, O, device=dev, dtype=torch.float32)
+    _lib.call("tmd_geb_out_fwd", p(hh), p(V2), N, O, t["act"], p(xo), p(vo), device=dev)
+    return xo, vo, (P1, V2, cat, z1, hh)
+
+
+def _geb_backward(saved, t, g_xo, g_vo):
+    """-> (g_x as a strided [N,Hh] view of g_cat, g_v [N,3,Hh]); g_xo may be a strided view (row stride passed on), g_vo contiguous"""
+    P1, V2, cat, z1, hh = saved
+    N, Hh, O, I, dev = cat.shape[0], cat.shape[1] // 2, t["O"], z1.shape[1], cat.device
+    g_hh = torch.empty(N, 2 * O, device=dev, dtype=torch.float32)
+    g_V2 = torch.empty(3 * N, O, device=dev, dtype=torch.float32)
+    _lib.call("tmd_geb_out_bwd", p(hh), p(V2), p(g_xo), 0 if g_xo is None else g_xo.stride(0), p(g_vo), N, O, t["act"], p(g_hh), p(g_V2),
+              device=dev)
+    if (2 * O) % 32 == 0:
+        g_h1 = rows_gemm(g_hh, t["Wb"], 1, aux=z1)
+    else:
+        g_h1 = torch.empty(N, I, device=dev, dtype=torch.float32)
+        _lib.call("tmd_rows_narrow_bwd", p(g_hh), p(t["Wb"]), N, I, 2 * O, 0, p(z1), p(g_h1), device=dev)
+    g_cat = rows_gemm(g_h1, t["Wa"], 3)
+    g_P1 = torch.empty(3 * N, Hh, device=dev, dtype=torch.float32)
+    _lib.call("tmd_geb_cat_bwd", p(P1), p(cat), p(g_cat), N, Hh, p(g_P1), device=dev)
+    if O % 32 == 0:
+        g_v = rows_gemm(g_P1, t["W1"], 3)
+        g_v = rows_gemm(g_V2, t["W2"], 4, aux=g_v)
+    else:
+        g_v = rows_gemm(g_P1, t["W1"], 3)
+        _lib.call("tmd_rows_narrow_bwd", p(g_V2), p(t["W2"]), 3 * N, Hh, O, 1, None, p(g_v), device=dev)
+    return g_cat[:, :Hh], g_v.view(N, 3, Hh)
+
+
+class _ETHead(torch.autograd.Function):
+    """EquivariantScalar.pre_reduce (two gated equivariant blocks) -> * std -> + atomref[z] -> per-molecule sum -> + mean, as one
+    autograd node with a hand-sequenced backward w.r.t. (x, vec) -- frozen weights (row a15 + the reduce of a11)."""
+
+    @staticmethod
+    def forward(ctx, x, v, z, batch, M, blocks, std, mean, atomref):
+        x, v = x.contiguous(), v.contiguous()
+        dev, N = x.device, x.shape[0]
+        ts = [b.tensors() for b in blocks]
+        saved = []
+        for t in ts:
+            x, v, sv = _geb_forward(x, v, t)
+            saved.append(sv)
+        std_c, mean_c = std.detach().reshape(1).contiguous(), mean.detach().reshape(1).contiguous()
+        aref = None if atomref is None else atomref.detach().contiguous()
+        one, zero = torch.ones(1, device=dev), torch.zeros(1, device=dev)
+        e = torch.empty(N, device=dev, dtype=torch.float32)
+        z_c, batch_c = z.contiguous(), batch.contiguous()
+        _lib.call("tmd_head_energy", p(x), N, 1, p(one), p(zero), p(std_c), p(z_c), p(aref), 0 if aref is None else aref.shape[0], p(e), device=dev)
+        y = torch.empty(M, 1, device=dev, dtype=torch.float32)
+        flag = torch.empty(1, device=dev, dtype=torch.int32)
+        _lib.call("tmd_segment_sum", p(e), p(batch_c), N, M, p(mean_c), p(flag), p(y), device=dev)
+        flat = [tt for sv in saved for tt in sv]
+        ctx.save_for_backward(batch_c, std_c, *flat)
+        ctx.ts, ctx.nsv = ts, len(saved[0])
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        batch, std_c, *flat = ctx.saved_tensors
+        ts, k = ctx.ts, ctx.nsv
+        saved = [tuple(flat[i * k:(i + 1) * k]) for i in range(len(ts))]
+        g_x = (gy.reshape(-1).index_select(0, batch) * std_c).reshape(-1, 1).contiguous()     # d y / d x_final
+        g_v = None
+        for t, sv in zip(reversed(ts), reversed(saved)):
+            g_x, g_v = _geb_backward(sv, t, g_x, None if g_v is None else g_v.contiguous())
+        return g_x, g_v, None, None, None, None, None, None, None
+
+
+def et_head_energy(x, v, z, batch, num_systems: int, blocks, std, mean, atomref=None):
+    return _ETHead.apply(x, v, z, batch, int(num_systems), blocks, std, mean, atomref)
+
+
 # ------------------------------------------------------------------------------------------ tail + head + reduce (rows a10, a11)
 class HeadWeights:
     """Contiguous (and transposed) copies of the weights behind norm3 -> LayerNorm -> Linear -> SiLU -> MLP(F -> F/2 -> 1), cached

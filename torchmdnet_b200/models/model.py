@@ -222,6 +222,32 @@ class TorchMD_Net(nn.Module):
             return None
         return hw, atomref
 
+    def _fused_et_head(self):
+        """(block weights, atomref weight or None) when the frame ends in EquivariantScalar on a frozen ET with a sum reduction: the
+        two gated equivariant blocks, * std, + atomref, per-molecule sum and + mean run as one autograd node (fused.et_head_energy,
+        row a15); else None."""
+        from .torchmd_et import TorchMD_ET
+        rep, out = self.representation_model, self.output_model
+        if self.fused_head_path is False or type(rep) is not TorchMD_ET or type(out) is not output_modules.EquivariantScalar:
+            return None
+        if out.reduce_op not in ("add", "sum") or self.mean is None or self.std is None or self.mean.dtype != torch.float32:
+            return None
+        atomref = None
+        if self.prior_model is not None and len(self.prior_model) > 0:
+            if len(self.prior_model) != 1 or type(self.prior_model[0]) is not priors.Atomref or self.prior_model[0].atomref.weight.requires_grad:
+                return None
+            if self.prior_model[0].enable:
+                atomref = self.prior_model[0].atomref.weight
+        from ..extensions import fused
+        if getattr(self, "_et_head_w", None) is None or any(w.block is not b for w, b in zip(self._et_head_w, out.output_network)):
+            self._et_head_w = [fused.GatedBlockWeights(b) for b in out.output_network]
+        ws = self._et_head_w
+        if not all(w.supported() and w.frozen() for w in ws) or ws[-1].block.out_channels != 1:
+            return None
+        if any(t.requires_grad for t in rep.parameters()):
+            return None
+        return ws, atomref
+
     def forward(self, z: Tensor, pos: Tensor, batch: Optional[Tensor] = None, box: Optional[Tensor] = None,
                 q: Optional[Tensor] = None, s: Optional[Tensor] = None, extra_args: Optional[Dict[str, Tensor]] = None,
                 num_systems: Optional[int] = None) -> Tuple[Tensor, Tensor]:
@@ -240,6 +266,12 @@ class TorchMD_Net(nn.Module):
             X = self.representation_model.forward_irreps(z, pos, batch, box=box, q=q, s=s)
             m = self.output_model.resolve_num_systems(batch, num_systems)
             y = fused.tail_head_energy(X, z, batch, m, hw, self.std, self.mean, atomref)
+        elif self._fused_et_head() is not None:
+            from ..extensions import fused
+            ws, atomref = self._fused_et_head()
+            x, v, z, pos, batch = self.representation_model(z, pos, batch, box=box, q=q, s=s)
+            m = self.output_model.resolve_num_systems(batch, num_systems)
+            y = fused.et_head_energy(x, v, z, batch, m, ws, self.std, self.mean, atomref)
         else:
             x, v, z, pos, batch = self.representation_model(z, pos, batch, box=box, q=q, s=s)
             x = self.output_model.pre_reduce(x, v, z, pos, batch, box=box)
