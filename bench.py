@@ -444,11 +444,22 @@ def main():
                            "gathered_vs_local_relE_max": max(errs), "total_energy_allreduce": float(tot),
                            "total_energy_from_gather": float(yall.sum())}
 
+    def leave():
+        """Multi-rank exit without the NCCL communicator teardown: the frame's CUDA graphs hold captured all-reduce kernels of that
+        communicator, and destroy_process_group() behind them blocked for the whole launcher timeout (observed at N = 2: the JSON
+        line was out, the ranks never exited).  Everything measured is on the host by now; flush and leave."""
+        sys.stdout.flush(); sys.stderr.flush()
+        torch.cuda.synchronize()
+        os._exit(0)
+
     if rank != 0:
         if dist_on:
-            dist.destroy_process_group()
+            dist.barrier()      # rank 0 has no collective after this point either
+            leave()
         return
 
+    if dist_on:
+        dist.barrier()          # pairs with the other ranks' last barrier: no collective below this line
     # ================================================================ rank 0: parity, rooflines, baselines ================================
     N = z.numel()
     gold = load_golden(args.workload, z, pos, batch)
@@ -573,7 +584,7 @@ def main():
            "shard_check": shard_check}
     print(json.dumps(out), flush=True)
     if dist_on:
-        dist.destroy_process_group()
+        leave()
 
 
 if __name__ == "__main__":

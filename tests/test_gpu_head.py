@@ -83,8 +83,7 @@ def test_et_head_kernels_vs_torch_head(F, prior):
     (fused.et_head_energy: GEMM launches + the geb_* kernels, hand-sequenced backward) == the torch-op head, energies and forces"""
     from torchmdnet_b200.models.model import create_model
     from torchmdnet_b200 import priors
-    hp = systems.et_hparams(num_layers=2, F=F, R=32, H=4, cutoff=5.0, max_nb=64)
-    hp["output_model"] = "EquivariantScalar"
+    hp = systems.et_hparams(num_layers=2, F=F, R=32, H=4, cutoff=5.0, max_nb=64)   # output_model "Scalar" -> EquivariantScalar for the ET
     random.seed(7); np.random.seed(7); torch.manual_seed(7)
     pm = None
     if prior:
@@ -93,6 +92,7 @@ def test_et_head_kernels_vs_torch_head(F, prior):
     m = create_model(dict(hp), prior_model=pm, mean=torch.tensor(-0.21), std=torch.tensor(1.7)).eval().to(dev)
     z, pos, batch, _ = systems.molecule_batch(n_mol=5, lo=9, hi=15, spread=3.0, seed=3)
     args = (z.to(dev), pos.to(dev), batch.to(dev))
+    assert type(m.output_model).__name__ == "EquivariantScalar"
     assert m._fused_et_head() is None               # parameters require grad: torch-op head
     for p_ in m.parameters():
         p_.requires_grad_(False)

@@ -886,6 +886,37 @@ def embedding_tail(X, nl: IrrepsLinearWeights, mw: EmbedMlpWeights):
     return _EmbeddingTail.apply(X[0], X[1], X[2], nl, mw)
 
 
+# ------------------------------------------------------------------------------------------ frozen nn.Linear on the GEMM launcher
+class _RowsLinear(torch.autograd.Function):
+    """y = x W^T + b for a frozen nn.Linear on tmd_rows_gemm (3xTF32 tensor-core tiles, fp32 parity) instead of a cuBLAS SIMT SGEMM;
+    backward w.r.t. x only."""
+
+    @staticmethod
+    def forward(ctx, x2d, Wt, W, bias):
+        ctx.W = W
+        return rows_gemm(x2d.contiguous(), Wt, 3, vec=bias)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        return rows_gemm(g.contiguous(), ctx.W, 3), None, None, None
+
+
+def rows_linear(x: Tensor, lin: torch.nn.Linear) -> Tensor:
+    """lin(x) over the last dimension through _RowsLinear when the layer is frozen and its widths fit the tiles, else lin(x)."""
+    K, N = lin.in_features, lin.out_features
+    if lin.weight.requires_grad or K % 16 or N % 32 or x.dtype != torch.float32 or not x.is_cuda or lin.weight.dtype != torch.float32:
+        return lin(x)
+    key = (lin.weight.data_ptr(), lin.weight._version, None if lin.bias is None else lin.bias._version)
+    cache = getattr(lin, "_rows_w", None)
+    if cache is None or cache[0] != key:
+        cache = (key, lin.weight.detach().t().contiguous(), lin.weight.detach().contiguous(),
+                 None if lin.bias is None else lin.bias.detach().contiguous())
+        lin._rows_w = cache
+    y = _RowsLinear.apply(x.reshape(-1, K), cache[1], cache[2], cache[3])
+    return y.view(*x.shape[:-1], N)
+
+
 # ------------------------------------------------------------------------------------------ ET output head (row a15)
 def _linear_rows(A: Tensor, Wt: Tensor, bias: Optional[Tensor] = None) -> Tensor:
     """A [M,K] . Wt [K,Nout] (+ bias): the weight-tiled GEMM, or the warp-per-row kernel for layers with <= 8 outputs"""

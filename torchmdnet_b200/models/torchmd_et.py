@@ -65,12 +65,13 @@ class EquivariantMultiHeadAttention(nn.Module):
         dist, rhat, pair_r, g, pidx, rbf_mod, rbf_op = fast
         F_ = self.hidden_channels
         xl = self.layernorm(x)
-        q, k, v = self.q_proj(xl), self.k_proj(xl), self.v_proj(xl)
-        vec1, vec2, vec3 = torch.split(self.vec_proj(vec), F_, dim=-1)
+        lin = fused.rows_linear     # frozen projections on the 3xTF32 GEMM launcher (csrc/rows_gemm.cu) instead of cuBLAS SIMT SGEMMs
+        q, k, v = lin(xl, self.q_proj), lin(xl, self.k_proj), lin(xl, self.v_proj)
+        vec1, vec2, vec3 = torch.split(lin(vec, self.vec_proj), F_, dim=-1)
         vec_dot = (vec1 * vec2).sum(dim=1)
         xa, va = fused.et_message(q, k, v, vec, dist, rhat, pair_r, self.radial_chain(), rbf_mod, self.cutoff.cutoff_lower,
                                   self.cutoff.cutoff_upper, self.vector_cutoff, self.head_dim, g, pidx, rbf_op)
-        o1, o2, o3 = torch.split(self.o_proj(xa), F_, dim=1)
+        o1, o2, o3 = torch.split(lin(xa, self.o_proj), F_, dim=1)
         return vec_dot * o2 + o3, vec3 * o1.unsqueeze(1) + va
 
     def forward(self, x, vec, src, dst, cut, f_ij, d_ij):
