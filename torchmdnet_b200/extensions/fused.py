@@ -755,19 +755,69 @@ def rows_gemm(A: Tensor, W: Tensor, epi: int, vec: Optional[Tensor] = None, aux:
     return (z, out) if save_z else out
 
 
+# radial functions of all interaction layers ahead of time on a forked stream (TMD_TABLE_OVERLAP=0: inside each layer, in order)
+USE_TABLE_OVERLAP = os.environ.get("TMD_TABLE_OVERLAP", "1") != "0"
+_side_streams = {}
+
+
+class LayerRadials:
+    """(f, f') of every interaction layer, evaluated on a side stream forked from the caller's stream.
+
+    With frozen weights the radial functions depend on the pair distances only, so all layers' table lookups (HBM-write-bound:
+    0.85 GB per layer at C4) can run while the main stream does the issue- / latency-bound start of the frame (message-passing plan,
+    moments embedding, embedding tail).  `get(i)` joins the side stream into the current one on first use.  Fork and join are plain
+    stream waits, so the pattern is CUDA-graph capturable."""
+
+    def __init__(self, chains, pair_r, num_unique, rbf_mod, lo, hi, want_tangent):
+        cur = torch.cuda.current_stream(pair_r.device)
+        side = _side_streams.get(pair_r.device)
+        if side is None:
+            side = _side_streams[pair_r.device] = torch.cuda.Stream(device=pair_r.device)
+        self._side, self._joined, self.out = side, False, []
+        P = pair_r.shape[0]
+        tabs = [c.table(rbf_mod, lo, hi) for c in chains]
+        for c, tab in zip(chains, tabs):     # outputs are allocated on the CALLER's stream (they are consumed and freed there);
+            n_last = c.tensors()[0][-1].shape[1]   # the side stream only fills them between the fork and the join
+            f = torch.empty(P, n_last, device=pair_r.device, dtype=torch.float32)
+            self.out.append((f, torch.empty_like(f) if want_tangent else None))
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for tab, (f, fp) in zip(tabs, self.out):
+                _lib.call("tmd_radial_table", p(pair_r), p(num_unique), P, p(tab[0]), tab[1], tab[2], f.shape[1], p(f), p(fp),
+                          device=pair_r.device)
+
+    def get(self, i):
+        if not self._joined:
+            torch.cuda.current_stream(self.out[0][0].device).wait_stream(self._side)
+            self._joined = True
+        return self.out[i]
+
+
+def layer_radials(chains, pair_r, num_unique, rbf_mod, lo, hi, want_tangent):
+    """LayerRadials when every chain is read from its table (the overlap pays for the HBM-bound lookup), else None"""
+    if not (USE_TABLE_OVERLAP and USE_RADIAL_TABLE and len(chains) > 0 and pair_r.shape[0] > 0):
+        return None
+    if not all(c.table(rbf_mod, lo, hi) is not None for c in chains):
+        return None
+    return LayerRadials(chains, pair_r.detach(), num_unique, rbf_mod, lo, hi, want_tangent)
+
+
 class _InteractionLayer(torch.autograd.Function):
     """One TensorNet interaction (reference tensornet.py:723-814): P1 -> node linears -> radial chain / table -> message passing ->
     P2 -> node linears -> P3.  Inputs X = (I, A, S) [N,{1,3,5},F] and the per-slot distances; output X'."""
 
     @staticmethod
-    def forward(ctx, XI, XA, XS, dist, qf, o3, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op, plan, nl0, nl1):
+    def forward(ctx, XI, XA, XS, dist, qf, o3, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op, plan, nl0, nl1, radial):
         XI, XA, XS, qf = XI.contiguous(), XA.contiguous(), XS.contiguous(), qf.contiguous()
         N, F, dev = XI.shape[0], XI.shape[-1], XI.device
         (w0, _), (w1, _) = nl0.tensors(), nl1.tensors()
         Xn = _triple(N, F, dev)
         _lib.call("tmd_p1_fwd", p(XI), p(XA), p(XS), p(Xn[0]), p(Xn[1]), p(Xn[2]), N, F, device=dev)
         Y = _irreps_gemm(Xn[0], Xn[1], Xn[2], w0[0], w0[1])
-        f, fp = run_chain(chain, pair_r.detach(), pidx.num_unique, rbf_mod, lo, hi, dist.requires_grad, rbf_op)
+        if radial is not None:       # evaluated ahead of time on the forked stream (LayerRadials)
+            f, fp = radial
+        else:
+            f, fp = run_chain(chain, pair_r.detach(), pidx.num_unique, rbf_mod, lo, hi, dist.requires_grad, rbf_op)
         if plan is None:
             plan = MessagePassingPlan(g, pidx, F)
         M = plan.forward(Y, f)
@@ -801,11 +851,12 @@ class _InteractionLayer(torch.autograd.Function):
         gX = _triple(N, F, dev)
         _lib.call("tmd_p1_bwd2", p(XI), p(XA), p(XS), p(dO[0]), p(dO[1]), p(dO[2]), p(gXn[0]), p(gXn[1]), p(gXn[2]), p(gX[0]), p(gX[1]), p(gX[2]),
                   N, F, device=dev)
-        return (gX[0], gX[1], gX[2], g_dist) + (None,) * 13
+        return (gX[0], gX[1], gX[2], g_dist) + (None,) * 14
 
 
-def interaction_layer(X, dist, qf, o3, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op, plan, nl0, nl1):
-    return _InteractionLayer.apply(X[0], X[1], X[2], dist, qf, bool(o3), pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op, plan, nl0, nl1)
+def interaction_layer(X, dist, qf, o3, pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op, plan, nl0, nl1, radial=None):
+    return _InteractionLayer.apply(X[0], X[1], X[2], dist, qf, bool(o3), pair_r, chain, rbf_mod, lo, hi, g, pidx, rbf_op, plan, nl0, nl1,
+                                   radial)
 
 
 class EmbedMlpWeights:

@@ -187,7 +187,7 @@ class Interaction(nn.Module):
             self._nl = (fused.IrrepsLinearWeights(self.linears_tensor[0:3]), fused.IrrepsLinearWeights(self.linears_tensor[3:6]))
         return self._nl[which]
 
-    def forward(self, X, g, rbf, cut, qf, fast=None):
+    def forward(self, X, g, rbf, cut, qf, fast=None, radial=None):
         lt = self.linears_tensor
         tc_lin = fast is not None and all(self.node_linear(k).supported() and self.node_linear(k).frozen() for k in (0, 1))
         if tc_lin and fused.USE_FUSED_LAYER:
@@ -195,7 +195,7 @@ class Interaction(nn.Module):
             dist, pair_r, pidx, rbf_mod, rbf_op, plan = fast
             return fused.interaction_layer(X, dist, qf, self.equivariance_invariance_group == "O(3)", pair_r, self.radial_chain(), rbf_mod,
                                            self.cutoff.cutoff_lower, self.cutoff.cutoff_upper, g, pidx, rbf_op, plan,
-                                           self.node_linear(0), self.node_linear(1))
+                                           self.node_linear(0), self.node_linear(1), radial=radial)
         Xn = ops.interaction_normalize(*X)
         Y = fused.irreps_linear(Xn, self.node_linear(0)) if tc_lin else (lt[0](Xn[0]), lt[1](Xn[1]), lt[2](Xn[2]))
         if fast is not None:
@@ -320,12 +320,18 @@ class TensorNet(nn.Module):
                 chains = [self.tensor_embedding.radial_chain()] + chains
             rbf_op = fused.shared_rbf_operand(chains, pair_r, pidx.num_unique, self.distance_expansion,
                                               self.cutoff_lower, self.cutoff_upper, dist.requires_grad)
+            # the layers' radial functions depend on the pair distances only: with tables they are looked up ahead of time on a forked
+            # stream, next to the plan / embedding work of this one (fused.LayerRadials)
+            tc_layers = all(l.node_linear(k).supported() and l.node_linear(k).frozen() for l in self.layers for k in (0, 1))
+            radials = fused.layer_radials([l.radial_chain() for l in self.layers], pair_r, pidx.num_unique, self.distance_expansion,
+                                          self.cutoff_lower, self.cutoff_upper, dist.requires_grad) \
+                if (rbf_op is None and tc_layers and fused.USE_FUSED_LAYER) else None
             # one plan per frame for the message passing of all layers (row groups + their neighbour unions, csrc/mp_coop.cu)
             plan = fused.MessagePassingPlan(g, pidx, self.hidden_channels) if self.num_layers > 0 else None
             fast = (dist, pair_r, pidx, self.distance_expansion, rbf_op, plan)
             X = self.tensor_embedding(z, g, None, None, None, None, None, fast=fast)
-            for layer in self.layers:
-                X = layer(X, g, None, None, qf, fast=fast)
+            for i, layer in enumerate(self.layers):
+                X = layer(X, g, None, None, qf, fast=fast, radial=None if radials is None else radials.get(i))
         else:
             # padded slots (static shapes) belong to no CSR row; clamp their indices so gathers stay in range
             li, lj = nbr_i.clamp(min=0).long(), nbr_j.clamp(min=0).long()
