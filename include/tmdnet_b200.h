@@ -38,15 +38,17 @@ const char* tmd_last_error(void);
  * past max_pairs are dropped).  Slots >= num_pairs are left untouched (caller pre-fills -1 / 0).
  * box: [1 or n_batch,3,3]; box_stride = 0 (shared) or 9 (per sample).  rev (optional, may be NULL): slot of the
  * transposed pair.  transpose=0 gives the half list (j <= i).  max_cells > 0 enables the O(N) cell-grid candidate
- * search for one rectangular periodic box with >= 3 cells per axis (decided on the device; identical output, other
- * inputs use the ordered batch-segment scan).  workspace: 5*n + 8 + 3*(max_cells+1) int32. */
+ * search: one grid per periodic rectangular box with >= 3 cells per axis (n_boxes = number of box matrices, 1 for a shared
+ * box; the reference's cell kernel handles a single box only, warp_ops/neighbors.py:222-229); decided on the device, identical
+ * output; any other input (triclinic, small or non-periodic boxes, more cells than max_cells) uses the ordered batch-segment
+ * scan.  workspace: 5*n + 8 + 3*(max_cells+1) + 4*n_boxes int32. */
 int tmd_neighbor_csr_f32(const float* pos, const int64_t* batch, const float* box, int box_stride, int periodic,
                          int n, double cutoff_lower, double cutoff_upper, int loop, int transpose, int max_pairs,
-                         int max_cells, int* indptr, int* nbr_i, int* nbr_j, float* vec, float* dist, int* num_pairs,
+                         int max_cells, int n_boxes, int* indptr, int* nbr_i, int* nbr_j, float* vec, float* dist, int* num_pairs,
                          int* rev, int* workspace, void* stream);
 int tmd_neighbor_csr_f64(const double* pos, const int64_t* batch, const double* box, int box_stride, int periodic,
                          int n, double cutoff_lower, double cutoff_upper, int loop, int transpose, int max_pairs,
-                         int max_cells, int* indptr, int* nbr_i, int* nbr_j, double* vec, double* dist, int* num_pairs,
+                         int max_cells, int n_boxes, int* indptr, int* nbr_i, int* nbr_j, double* vec, double* dist, int* num_pairs,
                          int* rev, int* workspace, void* stream);
 
 /* ---- a2: position gradient of the neighbour outputs -------------------------------------------------------

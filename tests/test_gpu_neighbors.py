@@ -144,6 +144,38 @@ def test_large_and_many_batches():
     assert torch.equal(nb, ei) and torch.equal(vec, v)
 
 
+def test_per_box_cell_grids():
+    """several rectangular periodic boxes of DIFFERENT sizes in one batch (per-sample box matrices): every box gets its own cell
+    grid (csrc/neighbors.cu; the reference's cell kernel handles one box only, warp_ops/neighbors.py:222-229); indices, deltas and
+    distances bit-exact vs the oracle, and the grid path was really taken (order flag)"""
+    from torchmdnet_b200.extensions.neighbors import neighbor_graph
+    g0 = torch.Generator().manual_seed(11)
+    sizes, dims = [700, 500, 900], [(19.0, 17.5, 21.0), (16.0, 18.2, 17.1), (23.0, 20.0, 19.5)]
+    pos, batch, boxes = [], [], []
+    for b, (n, L) in enumerate(zip(sizes, dims)):
+        Lt = torch.tensor(L)
+        pos.append((torch.rand(n, 3, generator=g0) * 1.4 - 0.2) * Lt)      # some atoms outside the primary cell
+        batch.append(torch.full((n,), b, dtype=torch.long))
+        boxes.append(torch.diag(Lt))
+    pos, batch, box = torch.cat(pos), torch.cat(batch), torch.stack(boxes)
+    ei, v, d = orc.neighbor_list(pos, batch, box, 0.0, 5.0, True, True)
+    nb, vec, dist, n = run_op(pos, batch, box, 0.0, 5.0, True, True, ei.shape[1] + 7)
+    assert n == ei.shape[1]
+    assert torch.equal(nb, ei) and torch.equal(vec, v) and torch.equal(dist, d)
+    g = neighbor_graph(pos.to(dev), batch.to(dev), box.to(dev), True, 0.0, 5.0, True, ei.shape[1] + 7)
+    assert int(g.order_flag) != 0, "the per-box cell grids were not used"
+    order = g.order.cpu().long()
+    assert torch.equal(torch.sort(order).values, torch.arange(pos.shape[0]))       # a permutation: atoms listed cell by cell
+    assert torch.equal(batch[order], torch.sort(batch).values)                      # box-major
+    # one triclinic box among them: the whole call falls back to the ordered scan, same result
+    box2 = box.clone(); box2[1, 1, 0] = 2.0
+    ei2, v2, d2 = orc.neighbor_list(pos, batch, box2, 0.0, 5.0, True, True)
+    nb2, vec2, dist2, n2 = run_op(pos, batch, box2, 0.0, 5.0, True, True, ei2.shape[1] + 7)
+    assert torch.equal(nb2, ei2) and torch.equal(dist2, d2)
+    g2 = neighbor_graph(pos.to(dev), batch.to(dev), box2.to(dev), True, 0.0, 5.0, True, ei2.shape[1] + 7)
+    assert int(g2.order_flag) == 0
+
+
 def test_graph_transform():
     from torchmdnet_b200.extensions.tensornet_ops import graph_transform
     g = torch.Generator().manual_seed(0)

@@ -21,8 +21,8 @@ P, I, D, LL = c_void_p, c_int, c_double, c_longlong
 
 # symbol -> (argtypes, number of CUDA kernels one call launches)
 SIGNATURES = {
-    "tmd_neighbor_csr_f32": ([P, P, P, I, I, I, D, D, I, I, I, I, P, P, P, P, P, P, P, P, P], 9),
-    "tmd_neighbor_csr_f64": ([P, P, P, I, I, I, D, D, I, I, I, I, P, P, P, P, P, P, P, P, P], 9),
+    "tmd_neighbor_csr_f32": ([P, P, P, I, I, I, D, D, I, I, I, I, I, P, P, P, P, P, P, P, P, P], 9),
+    "tmd_neighbor_csr_f64": ([P, P, P, I, I, I, D, D, I, I, I, I, I, P, P, P, P, P, P, P, P, P], 9),
     "tmd_neighbor_grad_csr_f32": ([P, P, P, I, I, P, P, P, P, P, P], 1),
     "tmd_neighbor_grad_csr_f64": ([P, P, P, I, I, P, P, P, P, P, P], 1),
     "tmd_neighbor_grad_coo_f32": ([P, LL, P, P, P, P, P, P], 1),

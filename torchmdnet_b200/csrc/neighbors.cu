@@ -76,35 +76,45 @@ __device__ __forceinline__ bool pair_delta(const T* __restrict__ pos, int i, int
   return ok;
 }
 
-// ---- cell grid (single rectangular periodic box): header ints {nx, ny, nz, ok}
-__global__ void cell_setup_kernel(const float* boxf, const double* boxd, int box_stride, int periodic, double cutoff,
-                                  int max_cells, int* __restrict__ hdr) {
-  int ok = (periodic && box_stride == 0 && max_cells >= 27) ? 1 : 0;
-  double b[9];
-  for (int k = 0; k < 9; ++k) b[k] = ok ? (boxf ? (double)boxf[k] : boxd[k]) : 0.0;
-  if (ok && (b[3] != 0.0 || b[6] != 0.0 || b[7] != 0.0 || b[1] != 0.0 || b[2] != 0.0 || b[5] != 0.0)) ok = 0;  // rectangular only
-  int nc[3] = {1, 1, 1};
-  if (ok) {
+// ---- cell grids: one per periodic rectangular box.  hdr = {total cells, 0, 0, ok}; boxhdr[4 b ..] = {nx, ny, nz, first cell of box b}.
+// A single box (box_stride == 0) is box 0 for every atom.  Any non-rectangular box, a box with fewer than 3 cells along an axis,
+// or more cells than the workspace holds switches the whole call to the ordered segment scan (ok = 0).
+__global__ void cell_setup_kernel(const float* boxf, const double* boxd, int box_stride, int n_boxes, int periodic, double cutoff,
+                                  int max_cells, int* __restrict__ hdr, int* __restrict__ boxhdr) {
+  int ok = (periodic && max_cells >= 27 && n_boxes >= 1) ? 1 : 0;
+  long long total = 0;
+  for (int bx = 0; ok && bx < n_boxes; ++bx) {
+    double b[9];
+    for (int k = 0; k < 9; ++k) b[k] = boxf ? (double)boxf[(size_t)bx * box_stride + k] : boxd[(size_t)bx * box_stride + k];
+    if (b[3] != 0.0 || b[6] != 0.0 || b[7] != 0.0 || b[1] != 0.0 || b[2] != 0.0 || b[5] != 0.0) { ok = 0; break; }  // rectangular only
     const double L[3] = {b[0], b[4], b[8]};
+    int nc[3];
     for (int d = 0; d < 3; ++d) {
       nc[d] = (int)floor(L[d] / (cutoff * 1.0001));   // cell edge strictly larger than the cutoff
       if (nc[d] < 3) ok = 0;                           // 27 distinct neighbour cells needed
     }
-    while (ok && (long long)nc[0] * nc[1] * nc[2] > max_cells) {  // coarsen the longest axis until it fits
-      int d = (nc[0] >= nc[1] && nc[0] >= nc[2]) ? 0 : (nc[1] >= nc[2] ? 1 : 2);
-      if (--nc[d] < 3) ok = 0;
-    }
+    if (n_boxes == 1)
+      while (ok && (long long)nc[0] * nc[1] * nc[2] > max_cells) {  // coarsen the longest axis until it fits
+        int d = (nc[0] >= nc[1] && nc[0] >= nc[2]) ? 0 : (nc[1] >= nc[2] ? 1 : 2);
+        if (--nc[d] < 3) ok = 0;
+      }
+    boxhdr[4 * bx] = nc[0]; boxhdr[4 * bx + 1] = nc[1]; boxhdr[4 * bx + 2] = nc[2]; boxhdr[4 * bx + 3] = (int)total;
+    total += (long long)nc[0] * nc[1] * nc[2];
+    if (total > max_cells) ok = 0;
   }
-  hdr[0] = nc[0]; hdr[1] = nc[1]; hdr[2] = nc[2]; hdr[3] = ok;
+  hdr[0] = ok ? (int)total : 0; hdr[1] = 0; hdr[2] = 0; hdr[3] = ok;
 }
 template <typename T>
-__global__ void cell_assign_kernel(const T* __restrict__ pos, const T* __restrict__ box, int n, const int* __restrict__ hdr,
-                                   int* __restrict__ cell_of, int* __restrict__ cell_count) {
+__global__ void cell_assign_kernel(const T* __restrict__ pos, const int64_t* __restrict__ batch, const T* __restrict__ box, int box_stride,
+                                   int n, const int* __restrict__ hdr, const int* __restrict__ boxhdr, int* __restrict__ cell_of,
+                                   int* __restrict__ cell_count) {
   if (!hdr[3]) return;
-  const int nx = hdr[0], ny = hdr[1], nz = hdr[2];
-  const T L[3] = {box[0], box[4], box[8]};
-  const int nc[3] = {nx, ny, nz};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int64_t bx = box_stride ? batch[i] : 0;
+    const T* bb = box + (size_t)bx * box_stride;
+    const T L[3] = {bb[0], bb[4], bb[8]};
+    const int nc[3] = {boxhdr[4 * bx], boxhdr[4 * bx + 1], boxhdr[4 * bx + 2]};
+    const int ny = nc[1], nz = nc[2];
     int c[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -113,7 +123,7 @@ __global__ void cell_assign_kernel(const T* __restrict__ pos, const T* __restric
       int k = (int)(f * (T)nc[d]);
       c[d] = k < 0 ? 0 : (k >= nc[d] ? nc[d] - 1 : k);
     }
-    const int id = (c[0] * ny + c[1]) * nz + c[2];
+    const int id = boxhdr[4 * bx + 3] + (c[0] * ny + c[1]) * nz + c[2];
     cell_of[i] = id;
     atomicAdd(cell_count + id, 1);
   }
@@ -138,7 +148,7 @@ __global__ void __launch_bounds__(256) neighbor_rows_kernel(
     int periodic, int n, T lo2, T hi2, int loop, int transpose, const int* __restrict__ seg_lo,
     const int* __restrict__ seg_hi, const int* __restrict__ unsorted_flag, const int* __restrict__ indptr,
     int max_pairs, int* __restrict__ deg, int* __restrict__ out_i, int* __restrict__ out_j, T* __restrict__ out_vec,
-    T* __restrict__ out_dist, const int* __restrict__ cell_hdr, const int* __restrict__ cell_of,
+    T* __restrict__ out_dist, const int* __restrict__ cell_hdr, const int* __restrict__ boxhdr, const int* __restrict__ cell_of,
     const int* __restrict__ cell_start, const int* __restrict__ cell_atoms) {
   extern __shared__ unsigned char nb_smem[];
   const int lane = threadIdx.x & 31;
@@ -163,12 +173,13 @@ __global__ void __launch_bounds__(256) neighbor_rows_kernel(
     bool row_done = false;
     if (use_cells) {
       // ------------------------------------------------------------------ cell path
-      const int nx = cell_hdr[0], ny = cell_hdr[1], nz = cell_hdr[2];
-      const int ci = cell_of[i];
+      const int64_t bxi = box_stride ? bi : 0;          // the row's own box grid
+      const int nx = boxhdr[4 * bxi], ny = boxhdr[4 * bxi + 1], nz = boxhdr[4 * bxi + 2], coff = boxhdr[4 * bxi + 3];
+      const int ci = cell_of[i] - coff;
       const int cz = ci % nz, cy = (ci / nz) % ny, cx = ci / (nz * ny);
       for (int nb = 0; nb < 27; ++nb) {
         const int ax = (cx + nb / 9 - 1 + nx) % nx, ay = (cy + (nb / 3) % 3 - 1 + ny) % ny, az = (cz + nb % 3 - 1 + nz) % nz;
-        const int c2 = (ax * ny + ay) * nz + az;
+        const int c2 = coff + (ax * ny + ay) * nz + az;
         const int s0 = cell_start[c2], s1 = cell_start[c2 + 1];
         for (int t0 = s0; t0 < s1; t0 += 32) {
           const int t = t0 + lane;
@@ -389,7 +400,7 @@ __global__ void csr_sort_rows_kernel(const int* __restrict__ ei, int E, int n, c
 template <typename T>
 static int neighbor_csr_impl(const T* pos, const int64_t* batch, const T* box, int box_stride, int periodic, int n,
                              double cutoff_lower, double cutoff_upper, int loop, int transpose, int max_pairs,
-                             int max_cells, int* indptr, int* nbr_i, int* nbr_j, T* vec, T* dist, int* num_pairs,
+                             int max_cells, int n_boxes, int* indptr, int* nbr_i, int* nbr_j, T* vec, T* dist, int* num_pairs,
                              int* rev, int* workspace, cudaStream_t st) {
   TMD_REQUIRE(n >= 0 && max_pairs >= 0 && max_cells >= 0, "neighbor_csr: negative size");
   TMD_REQUIRE(pos && batch && indptr && nbr_i && nbr_j && vec && dist && num_pairs && workspace,
@@ -397,19 +408,22 @@ static int neighbor_csr_impl(const T* pos, const int64_t* batch, const T* box, i
   TMD_REQUIRE(!periodic || box, "neighbor_csr: periodic without box");
   if (n == 0) { cudaMemsetAsync(num_pairs, 0, sizeof(int), st); cudaMemsetAsync(indptr, 0, sizeof(int), st); return tmd_check_launch("neighbor_csr(empty)"); }
   // workspace (ints): seg_lo[n] seg_hi[n] deg[n] flag[1] | hdr[4] cell_of[n] cell_atoms[n] cell_count[C+1] cell_start[C+1] cursor[C+1]
+  //                   boxhdr[4 n_boxes]
   int* seg_lo = workspace; int* seg_hi = workspace + n; int* deg = workspace + 2 * n; int* flag = workspace + 3 * n;
   int* hdr = workspace + 3 * n + 1; int* cell_of = hdr + 4; int* cell_atoms = cell_of + n;
   int* cell_count = cell_atoms + n; int* cell_start = cell_count + (max_cells + 1); int* cursor = cell_start + (max_cells + 1);
-  const bool cells = max_cells >= 27 && periodic && box_stride == 0;
+  int* boxhdr = cursor + (max_cells + 1);
+  TMD_REQUIRE(n_boxes >= 0 && (box_stride == 0 ? n_boxes <= 1 : true), "neighbor_csr: n_boxes must be the number of box matrices");
+  const bool cells = max_cells >= 27 && periodic && n_boxes >= 1 && n_boxes <= 4096;
   cudaMemsetAsync(flag, 0, sizeof(int) * 5, st);  // flag + hdr (hdr.ok = 0 unless the setup kernel enables the grid)
   batch_segments_kernel<<<tmd_blocks_for(n, 256), 256, 0, st>>>(batch, n, seg_lo, seg_hi, flag);
   if (cells) {
     cudaMemsetAsync(cell_count, 0, sizeof(int) * 3 * (max_cells + 1), st);
     const bool f32 = sizeof(T) == 4;
     cell_setup_kernel<<<1, 1, 0, st>>>(f32 ? reinterpret_cast<const float*>(box) : nullptr,
-                                       f32 ? nullptr : reinterpret_cast<const double*>(box), box_stride, periodic,
-                                       cutoff_upper, max_cells, hdr);
-    cell_assign_kernel<T><<<tmd_blocks_for(n, 256), 256, 0, st>>>(pos, box, n, hdr, cell_of, cell_count);
+                                       f32 ? nullptr : reinterpret_cast<const double*>(box), box_stride, n_boxes, periodic,
+                                       cutoff_upper, max_cells, hdr, boxhdr);
+    cell_assign_kernel<T><<<tmd_blocks_for(n, 256), 256, 0, st>>>(pos, batch, box, box_stride, n, hdr, boxhdr, cell_of, cell_count);
     exclusive_scan_kernel<<<1, 1024, 0, st>>>(cell_count, max_cells, cell_start, nullptr);
     cell_fill_kernel<<<tmd_blocks_for(n, 256), 256, 0, st>>>(n, hdr, cell_of, cell_start, cursor, cell_atoms);
   }
@@ -424,11 +438,11 @@ static int neighbor_csr_impl(const T* pos, const int64_t* batch, const T* box, i
   const int* chdr = cells ? hdr : nullptr;
   neighbor_rows_kernel<T, false><<<blocks, 256, smem, st>>>(pos, batch, box, box_stride, periodic, n, lo2, hi2, loop,
                                                              transpose, seg_lo, seg_hi, flag, nullptr, max_pairs, deg,
-                                                             nullptr, nullptr, nullptr, nullptr, chdr, cell_of, cell_start, cell_atoms);
+                                                             nullptr, nullptr, nullptr, nullptr, chdr, boxhdr, cell_of, cell_start, cell_atoms);
   exclusive_scan_kernel<<<1, 1024, 0, st>>>(deg, n, indptr, num_pairs);
   neighbor_rows_kernel<T, true><<<blocks, 256, smem, st>>>(pos, batch, box, box_stride, periodic, n, lo2, hi2, loop,
                                                             transpose, seg_lo, seg_hi, flag, indptr, max_pairs, deg,
-                                                            nbr_i, nbr_j, vec, dist, chdr, cell_of, cell_start, cell_atoms);
+                                                            nbr_i, nbr_j, vec, dist, chdr, boxhdr, cell_of, cell_start, cell_atoms);
   if (rev) reverse_edge_kernel<<<tmd_blocks_for(max_pairs, 256), 256, 0, st>>>(indptr, nbr_i, nbr_j, num_pairs, max_pairs, rev);
   return tmd_check_launch("neighbor_csr");
 }
@@ -437,18 +451,18 @@ extern "C" {
 
 int tmd_neighbor_csr_f32(const float* pos, const int64_t* batch, const float* box, int box_stride, int periodic,
                          int n, double cutoff_lower, double cutoff_upper, int loop, int transpose, int max_pairs,
-                         int max_cells, int* indptr, int* nbr_i, int* nbr_j, float* vec, float* dist, int* num_pairs,
+                         int max_cells, int n_boxes, int* indptr, int* nbr_i, int* nbr_j, float* vec, float* dist, int* num_pairs,
                          int* rev, int* workspace, void* stream) {
   return neighbor_csr_impl<float>(pos, batch, box, box_stride, periodic, n, cutoff_lower, cutoff_upper, loop,
-                                  transpose, max_pairs, max_cells, indptr, nbr_i, nbr_j, vec, dist, num_pairs, rev,
+                                  transpose, max_pairs, max_cells, n_boxes, indptr, nbr_i, nbr_j, vec, dist, num_pairs, rev,
                                   workspace, (cudaStream_t)stream);
 }
 int tmd_neighbor_csr_f64(const double* pos, const int64_t* batch, const double* box, int box_stride, int periodic,
                          int n, double cutoff_lower, double cutoff_upper, int loop, int transpose, int max_pairs,
-                         int max_cells, int* indptr, int* nbr_i, int* nbr_j, double* vec, double* dist, int* num_pairs,
+                         int max_cells, int n_boxes, int* indptr, int* nbr_i, int* nbr_j, double* vec, double* dist, int* num_pairs,
                          int* rev, int* workspace, void* stream) {
   return neighbor_csr_impl<double>(pos, batch, box, box_stride, periodic, n, cutoff_lower, cutoff_upper, loop,
-                                   transpose, max_pairs, max_cells, indptr, nbr_i, nbr_j, vec, dist, num_pairs, rev,
+                                   transpose, max_pairs, max_cells, n_boxes, indptr, nbr_i, nbr_j, vec, dist, num_pairs, rev,
                                    workspace, (cudaStream_t)stream);
 }
 

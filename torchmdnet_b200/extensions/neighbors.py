@@ -66,11 +66,12 @@ def _build(pos, batch, box, use_periodic, lo, hi, loop, transpose, max_pairs, wa
     if n == 0:
         indptr.zero_()
         return indptr, nbr_i, nbr_j, rev, num_pairs, vec, dist, None, None
-    # cell grid for one rectangular periodic box (decided on the device from the box tensor); otherwise segment scan
-    max_cells = min(4 * n + 64, 1 << 20) if (use_periodic and stride == 0 and n >= 512) else 0
-    ws = torch.empty(5 * n + 8 + 3 * (max_cells + 1), **i32)
+    # cell grids, one per periodic rectangular box (decided on the device from the box tensor); otherwise segment scan
+    n_boxes = 0 if box_c is None else int(box_c.shape[0])
+    max_cells = min(4 * n + 64, 1 << 20) if (use_periodic and n >= 512 and 1 <= n_boxes <= 4096) else 0
+    ws = torch.empty(5 * n + 8 + 3 * (max_cells + 1) + 4 * max(n_boxes, 1), **i32)
     _lib.call("tmd_neighbor_csr_" + _suffix(pos.dtype), _lib.ptr(pos_c), _lib.ptr(batch_c), _lib.ptr(box_c), stride,
-              int(use_periodic), n, float(lo), float(hi), int(loop), int(transpose), int(max_pairs), max_cells, _lib.ptr(indptr),
+              int(use_periodic), n, float(lo), float(hi), int(loop), int(transpose), int(max_pairs), max_cells, n_boxes, _lib.ptr(indptr),
               _lib.ptr(nbr_i), _lib.ptr(nbr_j), _lib.ptr(vec), _lib.ptr(dist), _lib.ptr(num_pairs), _lib.ptr(rev),
               _lib.ptr(ws), device=dev)
     # workspace layout (csrc/neighbors.cu): seg_lo[n] seg_hi[n] deg[n] flag[1] | hdr[4] cell_of[n] cell_atoms[n] ...;
