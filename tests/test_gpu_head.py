@@ -25,9 +25,13 @@ def seeded_model(hp, seed, prior=False):
     return m.eval().to(dev)
 
 
+@pytest.mark.parametrize("rows_gemm", [True, False])
 @pytest.mark.parametrize("F,n_mol,prior", [(128, 1, False), (64, 5, True), (192, 3, False), (256, 2, True)])
-def test_head_kernels_vs_torch_ops(F, n_mol, prior):
+def test_head_kernels_vs_torch_ops(F, n_mol, prior, rows_gemm, monkeypatch):
+    """both forms of rows a10 + a11: weight-tiled GEMM launches (csrc/rows_gemm.cu, default) and the one-launch-per-32-atom-tile
+    kernels (csrc/head.cu, TMD_ROWS_GEMM=0)"""
     from torchmdnet_b200.extensions import fused, tensornet_ops as ops
+    monkeypatch.setattr(fused, "USE_ROWS_GEMM", rows_gemm)
     from torchmdnet_b200.models.utils import scatter
     hp = systems.tensornet_hparams(num_layers=1, F=F, R=16, max_nb=64)
     m = seeded_model(hp, 3, prior)
