@@ -18,21 +18,23 @@
 // tmd_norm_ln_fwd / tmd_norm_ln_bwd: per-atom norms of the node tensors (|X|^2 per channel, or the three irrep norms) followed by
 // LayerNorm, and their backward fused with the gradient that reached the node tensors along another path.
 // tmd_head_energy / tmd_head_seed: the last Linear(H -> 1) * std + atomref of the Scalar head, and the seed of its backward.
+#include <stdlib.h>
 #include "common.cuh"
 #include "mlp_tile.cuh"
 
 namespace {
 
-constexpr int BM = 64, BK = 16, GST = 4, GT = 256;     // rows per tile, k per stage, stages, threads
+constexpr int BK = 16, GST = 4, GT = 256;               // k per stage, stages, threads; rows per tile BM = 64 or 128 (template)
 constexpr int ALD = BK + 4;                            // A tile row stride (20: fragment reads hit 32 banks)
 
 enum Epi { EPI_BIAS_SILU = 0, EPI_MUL_SILU_GRAD = 1, EPI_COLSCALE = 2, EPI_LINEAR = 3, EPI_ADD = 4 };
 
-template <int BN>
+template <int BM, int BN>
 __device__ __forceinline__ void stage_tiles(float* As, float* Bs, const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
                                             int m0, int n0, int k0, int M, int tid) {
-  {   // A: 64 rows x 16 columns = 256 float4
-    const int r = tid >> 2, c4 = tid & 3;
+#pragma unroll
+  for (int i = tid; i < BM * 4; i += GT) {   // A: BM rows x 16 columns = BM * 4 float4
+    const int r = i >> 2, c4 = i & 3;
     const int row = min(m0 + r, M - 1);                // rows past M read the last row (never stored)
     mlp::cp_async16(As + (size_t)r * ALD + 4 * c4, A + (size_t)row * lda + k0 + 4 * c4);
   }
@@ -46,26 +48,31 @@ __device__ __forceinline__ void stage_tiles(float* As, float* Bs, const float* _
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-template <int BN, int EPI>
+// BM = 64: 8 warps = 4 (rows) x 2 (columns), warp tile 16 x BN/2.  BM = 128: warp tile 32 x BN/2 (two m16 tiles per warp share
+// every B fragment and its split: fewer shared-memory reads and conversions per MMA); used when the grid still fills the SMs.
+template <int BM, int BN, int EPI>
 __global__ void __launch_bounds__(GT) rows_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw, int M, int K,
                                                        int N, const float* __restrict__ vec, const float* __restrict__ aux, int ldaux,
                                                        float* __restrict__ zout, float* __restrict__ out, int ldo) {
   extern __shared__ __align__(16) float sm[];
-  constexpr int NT = BN / 16;                          // n8 tiles per warp: 8 warps = 4 (rows) x 2 (columns)
+  constexpr int NT = BN / 16;                          // n8 tiles per warp
+  constexpr int MT = BM / 64;                          // m16 tiles per warp
   constexpr int ASZ = BM * ALD, BSZ = BK * (BN + 8);
   float* As = sm; float* Bs = sm + GST * ASZ;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 1, wn = warp & 1;
   const int g = lane >> 2, t = lane & 3;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int nchunks = K / BK;
-  float acc[NT][4];
+  float acc[MT][NT][4];
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int r = 0; r < 4; ++r) acc[nt][r] = 0.f;
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[mt][nt][r] = 0.f;
 #pragma unroll
   for (int s = 0; s < GST - 1; ++s) {
-    if (s < nchunks) stage_tiles<BN>(As + s * ASZ, Bs + s * BSZ, A, lda, W, ldw, m0, n0, s * BK, M, tid);
+    if (s < nchunks) stage_tiles<BM, BN>(As + s * ASZ, Bs + s * BSZ, A, lda, W, ldw, m0, n0, s * BK, M, tid);
     else asm volatile("cp.async.commit_group;" ::: "memory");
   }
   for (int c = 0; c < nchunks; ++c) {
@@ -73,7 +80,7 @@ __global__ void __launch_bounds__(GT) rows_gemm_kernel(const float* __restrict__
     __syncthreads();
     if (c + GST - 1 < nchunks) {
       const int s = (c + GST - 1) % GST;
-      stage_tiles<BN>(As + s * ASZ, Bs + s * BSZ, A, lda, W, ldw, m0, n0, (c + GST - 1) * BK, M, tid);
+      stage_tiles<BM, BN>(As + s * ASZ, Bs + s * BSZ, A, lda, W, ldw, m0, n0, (c + GST - 1) * BK, M, tid);
     } else {
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
@@ -81,37 +88,45 @@ __global__ void __launch_bounds__(GT) rows_gemm_kernel(const float* __restrict__
     const float* bs = Bs + (c % GST) * BSZ;
 #pragma unroll
     for (int ks = 0; ks < BK; ks += 8) {
-      uint32_t ah[4], al[4];
-      const float* a = as + (size_t)(16 * wm + g) * ALD + ks + t;
-      mlp::split_tf32(a[0], ah[0], al[0]);
-      mlp::split_tf32(a[8 * ALD], ah[1], al[1]);
-      mlp::split_tf32(a[4], ah[2], al[2]);
-      mlp::split_tf32(a[8 * ALD + 4], ah[3], al[3]);
+      uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const float* a = as + (size_t)(16 * (MT * wm + mt) + g) * ALD + ks + t;
+        mlp::split_tf32(a[0], ah[mt][0], al[mt][0]);
+        mlp::split_tf32(a[8 * ALD], ah[mt][1], al[mt][1]);
+        mlp::split_tf32(a[4], ah[mt][2], al[mt][2]);
+        mlp::split_tf32(a[8 * ALD + 4], ah[mt][3], al[mt][3]);
+      }
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const float* b = bs + (size_t)(ks + t) * (BN + 8) + wn * (BN / 2) + 8 * nt + g;
         uint32_t bh0, bl0, bh1, bl1;
         mlp::split_tf32(b[0], bh0, bl0);
         mlp::split_tf32(b[4 * (BN + 8)], bh1, bl1);
-        float tmp[4] = {0.f, 0.f, 0.f, 0.f};
-        mlp::mma_tf32(tmp, al, bh0, bh1);
-        mlp::mma_tf32(tmp, ah, bl0, bl1);
-        mlp::mma_tf32(tmp, ah, bh0, bh1);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) acc[nt][r] += tmp[r];
+        for (int mt = 0; mt < MT; ++mt) {
+          float tmp[4] = {0.f, 0.f, 0.f, 0.f};
+          mlp::mma_tf32(tmp, al[mt], bh0, bh1);
+          mlp::mma_tf32(tmp, ah[mt], bl0, bl1);
+          mlp::mma_tf32(tmp, ah[mt], bh0, bh1);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) acc[mt][nt][r] += tmp[r];
+        }
       }
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
-  // epilogue: rows 16 wm + g (+ 8), columns n0 + wn BN/2 + 8 nt + 2 t (+ 1): one 8-byte store per (row, tile)
+  // epilogue: rows 16 (MT wm + mt) + g (+ 8), columns n0 + wn BN/2 + 8 nt + 2 t (+ 1): one 8-byte store per (row, tile)
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
     const int col = n0 + wn * (BN / 2) + 8 * nt + 2 * t;
 #pragma unroll
     for (int hr = 0; hr < 2; ++hr) {
-      const int row = m0 + 16 * wm + g + 8 * hr;
+      const int row = m0 + 16 * (MT * wm + mt) + g + 8 * hr;
       if (row >= M) continue;
-      float v0 = acc[nt][2 * hr], v1 = acc[nt][2 * hr + 1];
+      float v0 = acc[mt][nt][2 * hr], v1 = acc[mt][nt][2 * hr + 1];
       if (EPI == EPI_BIAS_SILU) {
         v0 += __ldg(vec + col); v1 += __ldg(vec + col + 1);
         if (zout) *reinterpret_cast<float2*>(zout + (size_t)row * ldo + col) = make_float2(v0, v1);
@@ -330,14 +345,25 @@ __global__ void rows_narrow_bwd_kernel(const float* __restrict__ dOut, const flo
   }
 }
 
+template <int BM, int BN, int EPI>
+int launch_gemm_bm(const float* A, int lda, const float* W, int ldw, int M, int K, int N, const float* vec, const float* aux, int ldaux,
+                   float* zout, float* out, int ldo, cudaStream_t st) {
+  const size_t smem = (size_t)GST * (BM * ALD + BK * (BN + 8)) * sizeof(float);
+  cudaFuncSetAttribute(rows_gemm_kernel<BM, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid((M + BM - 1) / BM, N / BN);
+  rows_gemm_kernel<BM, BN, EPI><<<grid, GT, smem, st>>>(A, lda, W, ldw, M, K, N, vec, aux, ldaux, zout, out, ldo);
+  return tmd_check_launch("rows_gemm");
+}
 template <int BN, int EPI>
 int launch_gemm(const float* A, int lda, const float* W, int ldw, int M, int K, int N, const float* vec, const float* aux, int ldaux,
                 float* zout, float* out, int ldo, cudaStream_t st) {
-  const size_t smem = (size_t)GST * (BM * ALD + BK * (BN + 8)) * sizeof(float);
-  cudaFuncSetAttribute(rows_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dim3 grid((M + BM - 1) / BM, N / BN);
-  rows_gemm_kernel<BN, EPI><<<grid, GT, smem, st>>>(A, lda, W, ldw, M, K, N, vec, aux, ldaux, zout, out, ldo);
-  return tmd_check_launch("rows_gemm");
+  // 64-row tiles by default.  The 128-row form (two m16 tiles per warp share each B fragment: ~20 % fewer instructions per MMA) was
+  // measured SLOWER on both bench workloads -- C4 4.251 vs 4.220 ms per frame, C3 7.16 vs 7.09 ms per batch: half as many CTAs to
+  // cover the L2 latency of the operand stream -- and is kept behind TMD_GEMM_BM=128 as a tuning aid.
+  static const int forced = getenv("TMD_GEMM_BM") ? atoi(getenv("TMD_GEMM_BM")) : 0;
+  const bool big = forced == 128;
+  return big ? launch_gemm_bm<128, BN, EPI>(A, lda, W, ldw, M, K, N, vec, aux, ldaux, zout, out, ldo, st)
+             : launch_gemm_bm<64, BN, EPI>(A, lda, W, ldw, M, K, N, vec, aux, ldaux, zout, out, ldo, st);
 }
 
 }  // namespace
