@@ -188,6 +188,13 @@ class TorchMD_Net(nn.Module):
         self.register_buffer("mean", (torch.scalar_tensor(0) if mean is None else mean).to(dtype=dtype))
         self.register_buffer("std", (torch.scalar_tensor(1) if std is None else std).to(dtype=dtype))
         self.reset_parameters()
+        from ..extensions import frame_op      # handle of this module for the whole-frame op (torch.compile support); set here, outside
+        self._frame_op_handle = frame_op.handle_of(self)   # any traced region: Dynamo cannot trace the weak registry itself
+
+    def __setstate__(self, state):
+        super().__setstate__(state)            # copies / unpickled modules get a handle of their own
+        from ..extensions import frame_op
+        self._frame_op_handle = frame_op.handle_of(self)
 
     def reset_parameters(self):
         self.representation_model.reset_parameters()
@@ -251,6 +258,21 @@ class TorchMD_Net(nn.Module):
     def forward(self, z: Tensor, pos: Tensor, batch: Optional[Tensor] = None, box: Optional[Tensor] = None,
                 q: Optional[Tensor] = None, s: Optional[Tensor] = None, extra_args: Optional[Dict[str, Tensor]] = None,
                 num_systems: Optional[int] = None) -> Tuple[Tensor, Tensor]:
+        if torch.compiler.is_compiling():
+            # torch.compile(model, fullgraph=True): the frame is one opaque op with a fake implementation (extensions/frame_op.py)
+            from ..extensions import frame_op
+            if not self.derivative:
+                raise RuntimeError("torch.compile of torchmdnet_b200 models needs derivative=True (the compiled frame returns the forces "
+                                   "itself); for energy.backward() callers use TMDNETCalculator(compile=True) / CUDAGraphForceField")
+            if num_systems is None:
+                raise RuntimeError("torch.compile of torchmdnet_b200 models needs num_systems (the output shape must be known at trace time)")
+            batch = torch.zeros_like(z) if batch is None else batch
+            return torch.ops.torchmdnet_b200.energy_forces(self._frame_op_handle, z, pos, batch, box, q, num_systems)
+        return self._forward_impl(z, pos, batch, box=box, q=q, s=s, extra_args=extra_args, num_systems=num_systems)
+
+    def _forward_impl(self, z: Tensor, pos: Tensor, batch: Optional[Tensor] = None, box: Optional[Tensor] = None,
+                      q: Optional[Tensor] = None, s: Optional[Tensor] = None, extra_args: Optional[Dict[str, Tensor]] = None,
+                      num_systems: Optional[int] = None) -> Tuple[Tensor, Tensor]:
         assert z.dim() == 1 and z.dtype == torch.long
         if not pos.is_cuda:
             raise RuntimeError("torchmdnet_b200 runs on CUDA (sm_100a) only; there is no CPU path")
