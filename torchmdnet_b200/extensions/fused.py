@@ -521,7 +521,7 @@ class SpeciesSlots:
         c = self._z
         if c is not None and c.data_ptr() == z.data_ptr() and c.shape == z.shape and self._ver == z._version and c.device == z.device:
             return self._val
-        if torch.cuda.is_current_stream_capturing():
+        if z.is_cuda and torch.cuda.is_current_stream_capturing():
             return None
         species = torch.unique(z)                         # host sync: output size
         if species.numel() == 0 or species.numel() > MAX_SPECIES:
