@@ -109,3 +109,23 @@ def test_frame_op_fake_and_rows_linear_fallbacks():
     lin = torch.nn.Linear(32, 64)
     x = torch.randn(5, 32)
     assert torch.equal(fused.rows_linear(x, lin), lin(x))
+
+
+def test_torchscript_in_process_wrapper():
+    """torch.jit.script(model) (reference tests/test_model.py:207-262) compiles: the scripted graph is one call of the whole-frame op
+    with TorchMD_Net.forward's signature; the model is pinned so the handle stays valid.  (Execution needs a GPU; the op body is the one
+    `test_torch_compile_fullgraph` runs.)"""
+    import io
+    from torchmdnet_b200.extensions import frame_op
+    from torchmdnet_b200.models.model import create_model
+    m = create_model(dict(systems.tensornet_hparams(num_layers=1, F=32, R=16, max_nb=32)))
+    sm = torch.jit.script(m)
+    assert "torchmdnet_b200::energy_forces" in str(sm.graph)
+    names = [a.name for a in sm.forward.schema.arguments]
+    assert names == ["self", "z", "pos", "batch", "box", "q", "s", "extra_args", "num_systems"]
+    assert frame_op._pinned[m._frame_op_handle] is m
+    buf = io.BytesIO()
+    torch.jit.save(sm, buf)                       # serialisable; loadable where this package (and the model) lives
+    buf.seek(0)
+    sm2 = torch.jit.load(buf)
+    assert "torchmdnet_b200::energy_forces" in str(sm2.graph)

@@ -14,7 +14,7 @@ device-side counters).  Only the force-returning form (`derivative=True`) is exp
 autograd formula is registered.  `model` is a handle into a weak registry (custom ops take no module arguments)."""
 import concurrent.futures
 import weakref
-from typing import Optional, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -54,3 +54,36 @@ def energy_forces(model: int, z: Tensor, pos: Tensor, batch: Tensor, box: Option
 @energy_forces.register_fake
 def _(model, z, pos, batch, box, q, num_systems):
     return pos.new_empty(num_systems, 1), pos.new_empty(pos.shape[0], 3)
+
+
+# ------------------------------------------------------------------------------------------ TorchScript (in-process)
+# The reference scripts its model in-process (tests/test_model.py:207-262; its Warp ops are Python-registered too, so a scripted
+# module only runs where those registrations exist).  `torch.jit.script(model)` on a TorchMD_Net of this build goes through
+# `__prepare_scriptable__`, which hands the compiler this module: the scripted graph is ONE call of torchmdnet_b200::energy_forces.
+_pinned = {}     # handle -> model: a scripted wrapper refers to its model by handle only, so the model is kept alive here
+
+
+class ScriptedFrame(torch.nn.Module):
+    """forward(z, pos, batch, box, q, s, extra_args, num_systems) -> (energy, forces) with TorchMD_Net.forward's signature"""
+
+    def __init__(self, handle: int):
+        super().__init__()
+        self.handle = handle
+
+    def forward(self, z: Tensor, pos: Tensor, batch: Optional[Tensor] = None, box: Optional[Tensor] = None, q: Optional[Tensor] = None,
+                s: Optional[Tensor] = None, extra_args: Optional[Dict[str, Tensor]] = None,
+                num_systems: Optional[int] = None) -> Tuple[Tensor, Tensor]:
+        if batch is None:
+            batch = torch.zeros_like(z)
+        n = 0
+        if num_systems is not None:
+            n = num_systems
+        else:
+            n = int(batch.max().item()) + 1
+        y, f = torch.ops.torchmdnet_b200.energy_forces(self.handle, z, pos, batch, box, q, n)
+        return y, f
+
+
+def scriptable(model) -> ScriptedFrame:
+    _pinned[model._frame_op_handle] = model
+    return ScriptedFrame(model._frame_op_handle)

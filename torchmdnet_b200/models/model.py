@@ -191,6 +191,12 @@ class TorchMD_Net(nn.Module):
         from ..extensions import frame_op      # handle of this module for the whole-frame op (torch.compile support); set here, outside
         self._frame_op_handle = frame_op.handle_of(self)   # any traced region: Dynamo cannot trace the weak registry itself
 
+    def __prepare_scriptable__(self):
+        """torch.jit.script(model): the scripting compiler gets a module whose graph is one call of the whole-frame op
+        (extensions/frame_op.py); in-process only, like the reference's Python-registered ops (tests/test_model.py:207-262)"""
+        from ..extensions import frame_op
+        return frame_op.scriptable(self)
+
     def __setstate__(self, state):
         super().__setstate__(state)            # copies / unpickled modules get a handle of their own
         from ..extensions import frame_op
