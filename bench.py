@@ -10,6 +10,8 @@ random-init weights (seed 1), synthetic positions (seed = rank).  One step = one
 whole box.  N > 1: one box per GPU (weak scaling, independent boxes, seeds differ), one NCCL all-reduce of the scalar
 total energy per step -- captured INSIDE the frame's CUDA graph -- and nothing else; value = N frames / max-over-ranks device time.
 `--workload c5 --gpus N`: ONE batch of 8N boxes x 5000 atoms sharded over the ranks with parallel.shard_batch (BASELINE configs[4]).
+`--workload c2 | c3 | tn2`: the 1000-atom box, the ET-SPICE batch (configs[1], configs[2]) and TensorNet2 + weighted Coulomb on 256 charged
+molecules, each compared with its full-size fp64 golden where one is committed.
 
 Timing: W untimed warm-up steps, then exactly K steps between CUDA events on the launching stream, bracketed by
 barrier + synchronize; max over ranks.  The per-frame working set (~4 GB of pair tensors) is >> the 126 MB L2, so no
